@@ -1,0 +1,32 @@
+// Error plumbing and library-level queries of the C ABI (include/ddfa_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ddfa {
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace ddfa
+
+extern "C" {
+
+int ddfa_abi_version(void) { return DDFA_ABI_VERSION; }
+
+const char *ddfa_last_error(void) { return ddfa::g_err; }
+
+int ddfa_device_supported(void) {
+  int dev = 0;
+  DDFA_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  DDFA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Shared helpers for libddfa_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ddfa_b200.h"
+
+namespace ddfa {
+
+void set_error(const char *fmt, ...);
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define DDFA_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ddfa::set_error(__VA_ARGS__);        \
+      return DDFA_ERR_INVALID_ARG;         \
+    }                                      \
+  } while (0)
+
+#define DDFA_CHECK_LAUNCH(name)                                                        \
+  do {                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      ddfa::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));         \
+      return DDFA_ERR_CUDA;                                                            \
+    }                                                                                  \
+  } while (0)
+
+#define DDFA_CUDA(call)                                                                \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ddfa::set_error("%s failed: %s", #call, cudaGetErrorString(e__));                \
+      return DDFA_ERR_CUDA;                                                            \
+    }                                                                                  \
+  } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// sgemm.cu — SIMT fp32 GEMM, C = alpha*op(A)op(B) + beta*C (row-major)
+int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
+          float beta, float *C, int ldc, int split_k, cudaStream_t stream);
+// gru_tc.cu — tcgen05 engine entry points (D == 128)
+size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
+int gru_tc_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
+                    const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,
+                    float *save_gates, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+__device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void f4_add(float4 &a, const float4 &b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+__device__ __forceinline__ void f4_fma(float4 &a, float s, const float4 &b) {
+  a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y); a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
+}
+__device__ __forceinline__ float f4_dot(const float4 &a, const float4 &b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+}  // namespace ddfa

@@ -1,0 +1,124 @@
+// K1 — embedding lookup + concat, forward and backward.
+// Reference: 4x nn.Embedding(input_dim, hidden_dim) + torch.cat(dim=1) (ggnn.py:47-52,84-89) or a
+// single nn.Embedding (ggnn.py:54,91-92).  Tables total 4*1002*32*4 B = 513 KB -> L2 resident;
+// the op is bound by the index read (8 B/node/table) and the 4*D B/node output write.
+#include "common.cuh"
+
+namespace ddfa {
+
+constexpr int kMaxTables = 8;
+struct EmbedPtrs {
+  const int64_t *idx[kMaxTables];
+  const float *table[kMaxTables];
+  float *dtable[kMaxTables];
+};
+
+// one thread per 16-byte output chunk
+__global__ void __launch_bounds__(256) embed_concat_fwd_kernel(const EmbedPtrs p, int32_t K, int32_t V, int32_t H,
+                                                               int32_t N, float *__restrict__ x, int32_t *__restrict__ oob) {
+  const int hq = H >> 2;           // chunks per table
+  const int dq = K * hq;           // chunks per node row
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)N * dq) return;
+  const int32_t n = (int32_t)(t / dq);
+  const int c = (int)(t - (int64_t)n * dq);
+  const int k = c / hq, j = (c - k * hq) * 4;
+  int64_t i = p.idx[k][n];
+  if (i < 0 || i >= V) {
+    if (oob && j == 0) atomicAdd(oob, 1);
+    i = i < 0 ? 0 : V - 1;
+  }
+  const float4 v = ldg_nc_f4(p.table[k] + i * H + j);
+  *reinterpret_cast<float4 *>(x + (int64_t)n * (K * H) + c * 4) = v;
+}
+
+// Backward: dtable[k][idx_k[n], :] += (dx + dx2)[n, kH:(k+1)H]   (dx2 optional).
+// ~75 % of Big-Vul nodes carry index 0 ("not a definition", dbize_absdf.py:39) and a few % index 1
+// (UNKNOWN), so rows 0 and 1 are privatised: each thread accumulates them in registers over its
+// rows, the CTA reduces through shared memory and issues ONE RED per element per CTA; all other
+// rows go straight to L2 with RED.ADD.F32.
+constexpr int kEmbRows = 256;  // node rows per CTA
+__global__ void __launch_bounds__(256) embed_concat_bwd_kernel(const EmbedPtrs p, int32_t K, int32_t V, int32_t H,
+                                                               int32_t N, const float *__restrict__ dx,
+                                                               const float *__restrict__ dx2) {
+  extern __shared__ __align__(16) float red[];  // [ny][2][D]
+  const int D = K * H;
+  const int c = threadIdx.x;  // chunk inside the row (blockDim.x == D/4)
+  const int hq = H >> 2;
+  const int k = c / hq, j = (c - k * hq) * 4;
+  const int64_t *idx = p.idx[k];
+  float *dt = p.dtable[k];
+  float4 hot[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  const int32_t row0 = blockIdx.x * kEmbRows;
+  const int32_t row1 = min(N, row0 + kEmbRows);
+  for (int32_t n = row0 + threadIdx.y; n < row1; n += blockDim.y) {
+    float4 g = *reinterpret_cast<const float4 *>(dx + (int64_t)n * D + c * 4);
+    if (dx2) f4_add(g, *reinterpret_cast<const float4 *>(dx2 + (int64_t)n * D + c * 4));
+    int64_t i = idx[n];
+    i = i < 0 ? 0 : (i >= V ? V - 1 : i);
+    if (i == 0) f4_add(hot[0], g);
+    else if (i == 1) f4_add(hot[1], g);
+    else {
+      float *q = dt + i * H + j;
+      atomicAdd(q + 0, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w);
+    }
+  }
+  *reinterpret_cast<float4 *>(&red[((size_t)threadIdx.y * 2 + 0) * D + c * 4]) = hot[0];
+  *reinterpret_cast<float4 *>(&red[((size_t)threadIdx.y * 2 + 1) * D + c * 4]) = hot[1];
+  __syncthreads();
+  if (threadIdx.y < 2) {
+    const int r = threadIdx.y;  // hot row 0 or 1
+    if (r < V) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int y = 0; y < blockDim.y; ++y) f4_add(s, *reinterpret_cast<const float4 *>(&red[((size_t)y * 2 + r) * D + c * 4]));
+      float *q = dt + (int64_t)r * H + j;
+      atomicAdd(q + 0, s.x); atomicAdd(q + 1, s.y); atomicAdd(q + 2, s.z); atomicAdd(q + 3, s.w);
+    }
+  }
+}
+
+}  // namespace ddfa
+
+extern "C" {
+
+int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables, int32_t K, int32_t V, int32_t H,
+                          int32_t N, float *x, int32_t *oob_count, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(K >= 1 && K <= kMaxTables && V > 0 && H > 0 && H % 4 == 0 && N >= 0,
+               "ddfa_embed_concat_fwd: unsupported shape K=%d V=%d H=%d N=%d (H%%4==0, K<=%d)", K, V, H, N, kMaxTables);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(idx && tables && x && aligned16(x), "ddfa_embed_concat_fwd: NULL or unaligned pointer");
+  EmbedPtrs p{};
+  for (int k = 0; k < K; ++k) {
+    DDFA_REQUIRE(idx[k] && tables[k] && aligned16(tables[k]), "ddfa_embed_concat_fwd: table %d pointer NULL or unaligned", k);
+    p.idx[k] = idx[k];
+    p.table[k] = tables[k];
+  }
+  const int64_t tot = (int64_t)N * K * (H / 4);
+  embed_concat_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream_)>>>(p, K, V, H, N, x, oob_count);
+  DDFA_CHECK_LAUNCH("embed_concat_fwd_kernel");
+  return DDFA_OK;
+}
+
+int ddfa_embed_concat_bwd(const int64_t *const *idx, const float *dx, const float *dx2, int32_t K, int32_t V, int32_t H,
+                          int32_t N, float *const *dtables, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(K >= 1 && K <= kMaxTables && V > 0 && H > 0 && H % 4 == 0 && N >= 0 && K * H <= 512,
+               "ddfa_embed_concat_bwd: unsupported shape K=%d V=%d H=%d N=%d", K, V, H, N);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(idx && dx && dtables && aligned16(dx) && aligned16(dx2), "ddfa_embed_concat_bwd: NULL or unaligned pointer");
+  EmbedPtrs p{};
+  for (int k = 0; k < K; ++k) {
+    DDFA_REQUIRE(idx[k] && dtables[k], "ddfa_embed_concat_bwd: table %d pointer NULL", k);
+    p.idx[k] = idx[k];
+    p.dtable[k] = dtables[k];
+  }
+  const int D = K * H;
+  dim3 block(D / 4, (256 / (D / 4)) > 2 ? 256 / (D / 4) : 2);
+  const size_t smem = sizeof(float) * block.y * 2 * D;
+  embed_concat_bwd_kernel<<<(N + kEmbRows - 1) / kEmbRows, block, smem, as_stream(stream_)>>>(p, K, V, H, N, dx, dx2);
+  DDFA_CHECK_LAUNCH("embed_concat_bwd_kernel");
+  return DDFA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+// SIMT engine: generic row-major fp32 GEMM,  C[M,N] = alpha * op(A) op(B) + beta * C.
+//
+// This is the fp32 FFMA building block of the DDFA_ENGINE_SIMT path (any hidden width) and the
+// bisecting reference for the tcgen05 engine.  It stands in for the cuBLAS SGEMM calls behind
+// nn.Linear / nn.GRUCell in the reference (ggnn.py:57-60,71-80) and for autograd's wgrad/dgrad.
+//
+// 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, double-buffered shared memory
+// with register prefetch.  split_k > 1 distributes K over gridDim.z and accumulates with RED.ADD
+// (used for the weight gradients, where M,N are tiny and K = number of nodes).
+#include "common.cuh"
+
+namespace ddfa {
+
+constexpr int BM = 128, BN = 128, BK = 16, LDS_PAD = 4;
+
+// Loads a [128 (mn) x 16 (k)] tile into registers.  KCONTIG: memory is contiguous along k
+// (element (mn,k) at p[mn*ld + k]); otherwise contiguous along mn (element at p[k*ld + mn]).
+template <bool KCONTIG>
+__device__ __forceinline__ void load_tile(const float *__restrict__ p, int ld, int mn0, int k0, int MN, int Kend,
+                                          bool vec_ok, float4 (&reg)[2]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int mn, k;
+    if (KCONTIG) { mn = mn0 + (t >> 2) + i * 64; k = k0 + (t & 3) * 4; }
+    else         { k = k0 + (t >> 5) + i * 8;    mn = mn0 + (t & 31) * 4; }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {
+      if (mn < MN) {
+        const float *q = p + (int64_t)mn * ld + k;
+        if (vec_ok && k + 3 < Kend) v = *reinterpret_cast<const float4 *>(q);
+        else {
+          if (k + 0 < Kend) v.x = q[0];
+          if (k + 1 < Kend) v.y = q[1];
+          if (k + 2 < Kend) v.z = q[2];
+          if (k + 3 < Kend) v.w = q[3];
+        }
+      }
+    } else {
+      if (k < Kend) {
+        const float *q = p + (int64_t)k * ld + mn;
+        if (vec_ok && mn + 3 < MN) v = *reinterpret_cast<const float4 *>(q);
+        else {
+          if (mn + 0 < MN) v.x = q[0];
+          if (mn + 1 < MN) v.y = q[1];
+          if (mn + 2 < MN) v.z = q[2];
+          if (mn + 3 < MN) v.w = q[3];
+        }
+      }
+    }
+    reg[i] = v;
+  }
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void store_tile(float (*s)[BM + LDS_PAD], const float4 (&reg)[2]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (KCONTIG) {
+      const int mn = (t >> 2) + i * 64, k = (t & 3) * 4;
+      s[k + 0][mn] = reg[i].x; s[k + 1][mn] = reg[i].y; s[k + 2][mn] = reg[i].z; s[k + 3][mn] = reg[i].w;
+    } else {
+      const int k = (t >> 5) + i * 8, mn = (t & 31) * 4;
+      *reinterpret_cast<float4 *>(&s[k][mn]) = reg[i];
+    }
+  }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
+                                                    int lda, const float *__restrict__ B, int ldb, float beta,
+                                                    float *__restrict__ C, int ldc, int k_per_split, int use_atomic,
+                                                    int vec_a, int vec_b) {
+  __shared__ __align__(16) float As[2][BK][BM + LDS_PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + LDS_PAD];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  // op(A)[m][k]: !TA -> A[m*lda+k] (k contiguous); TA -> A[k*lda+m] (m contiguous)
+  // op(B)[k][n]: !TB -> B[k*ldb+n] (n contiguous); TB -> B[n*ldb+k] (k contiguous)
+  if (kbeg < kend) {
+    load_tile<!TA>(A, lda, m0, kbeg, M, kend, vec_a, ra);
+    load_tile<TB>(B, ldb, n0, kbeg, N, kend, vec_b, rb);
+    store_tile<!TA>(As[0], ra);
+    store_tile<TB>(Bs[0], rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool has_next = k0 + BK < kend;
+    if (has_next) {
+      load_tile<!TA>(A, lda, m0, k0 + BK, M, kend, vec_a, ra);
+      load_tile<TB>(B, ldb, n0, k0 + BK, N, kend, vec_b, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_tile<!TA>(As[buf ^ 1], ra);
+      store_tile<TB>(Bs[buf ^ 1], rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  if (kbeg >= kend && (use_atomic || blockIdx.z > 0)) return;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float *c = C + (int64_t)m * ldc + n;
+      const float v = alpha * acc[i][j];
+      if (use_atomic) atomicAdd(c, v);
+      else *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
+    }
+  }
+}
+
+int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
+          float beta, float *C, int ldc, int split_k, cudaStream_t stream) {
+  if (M == 0 || N == 0) return DDFA_OK;
+  if (split_k < 1) split_k = 1;
+  int k_tiles = (K + BK - 1) / BK;
+  if (split_k > k_tiles) split_k = k_tiles > 0 ? k_tiles : 1;
+  const int k_per_split = ((k_tiles + split_k - 1) / split_k) * BK;
+  const int use_atomic = split_k > 1;
+  if (use_atomic && beta != 1.f) {
+    set_error("ddfa_sgemm: split_k > 1 requires beta == 1 (atomic accumulation into C)");
+    return DDFA_ERR_INVALID_ARG;
+  }
+  const int vec_a = aligned16(A) && (lda % 4 == 0);
+  const int vec_b = aligned16(B) && (ldb % 4 == 0);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
+  if (grid.y > 65535u) {
+    set_error("ddfa_sgemm: M=%d too large for grid.y", M);
+    return DDFA_ERR_UNSUPPORTED;
+  }
+#define LAUNCH(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_per_split, use_atomic, vec_a, vec_b)
+  if (!ta && !tb) LAUNCH(false, false);
+  else if (!ta && tb) LAUNCH(false, true);
+  else if (ta && !tb) LAUNCH(true, false);
+  else LAUNCH(true, true);
+#undef LAUNCH
+  DDFA_CHECK_LAUNCH("sgemm_kernel");
+  return DDFA_OK;
+}
+
+}  // namespace ddfa
+
+extern "C" int ddfa_sgemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float alpha, const float *a,
+                          int32_t lda, const float *b, int32_t ldb, float beta, float *c, int32_t ldc,
+                          int32_t split_k, void *stream) {
+  using namespace ddfa;
+  DDFA_REQUIRE(m >= 0 && n >= 0 && k >= 0, "ddfa_sgemm: negative dimension");
+  DDFA_REQUIRE((m == 0 || n == 0) || (a && b && c) || k == 0, "ddfa_sgemm: NULL pointer");
+  return sgemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, split_k, as_stream(stream));
+}

@@ -1,0 +1,320 @@
+"""Host-side driver of the hot path: graph preparation, forward, backward — all device work is
+done by libddfa_b200.so through the C ABI (deepdfa_b200._lib); torch only owns device memory
+and streams.  There is no CPU path: every entry raises if the tensors are not on a CUDA device.
+
+Mirrors the control flow of the reference ``FlowGNNGGNNModule.forward``
+(DDFA/code_gnn/models/flow_gnn/ggnn.py:82-109) with DGL's GatedGraphConv / GlobalAttentionPooling
+replaced by the kernels documented in include/ddfa_b200.h.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ENGINE_SIMT, ENGINE_TCGEN05, DdfaError, ptr_array
+from .graph import ABS_DATAFLOW_SUBKEYS, BatchedCFG, as_batched_cfg
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DdfaError("deepdfa_b200 runs on CUDA (sm_100a) only: got a CPU tensor; there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------
+# Graph structure on the device
+# ------------------------------------------------------------------------------------------
+@dataclass
+class DeviceGraph:
+    """CSR (by destination) + transposed CSR + graph segment pointers, all int32 on the device."""
+    num_nodes: int
+    num_edges: int
+    batch_size: int
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    indptr_t: torch.Tensor
+    indices_t: torch.Tensor
+    graph_ptr: torch.Tensor
+    device: torch.device
+
+
+def prepare_graph(g, device=None, need_transpose: bool = True) -> DeviceGraph:
+    """COO (as handed over by DGL / BatchedCFG) -> DeviceGraph, entirely on the device, no host sync.
+    Cached on the graph object."""
+    g = as_batched_cfg(g)
+    device = torch.device(device) if device is not None else g.device
+    if device.type != "cuda":
+        raise DdfaError("prepare_graph: target device must be CUDA; deepdfa_b200 has no CPU path")
+    key = f"devgraph:{device}:{int(need_transpose)}"
+    cached = g._cache.get(key) or g._cache.get(f"devgraph:{device}:1")
+    if cached is not None:
+        return cached
+    src, dst = g.edges()
+    src = src.to(device, non_blocking=True)
+    dst = dst.to(device, non_blocking=True)
+    bnn = g.batch_num_nodes().to(device=device, dtype=torch.int64, non_blocking=True)
+    if src.dtype not in (torch.int64, torch.int32) or dst.dtype != src.dtype:
+        src, dst = src.to(torch.int64), dst.to(torch.int64)
+    src, dst = src.contiguous(), dst.contiguous()
+    N, E, B = g.num_nodes(), g.num_edges(), g.batch_size
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        indptr = torch.empty(N + 1, dtype=torch.int32, device=device)
+        indices = torch.empty(max(E, 1), dtype=torch.int32, device=device)
+        if need_transpose:
+            indptr_t = torch.empty(N + 1, dtype=torch.int32, device=device)
+            indices_t = torch.empty(max(E, 1), dtype=torch.int32, device=device)
+        else:
+            indptr_t = indices_t = None
+        graph_ptr = torch.empty(B + 1, dtype=torch.int32, device=device)
+        ws_bytes = L.call("ddfa_build_csr_workspace_bytes", E, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        st = _stream_ptr()
+        L.call("ddfa_build_csr", _p(src), _p(dst), src.element_size(), E, N, _p(indptr), _p(indices),
+               _p(indptr_t), _p(indices_t), _p(ws), ws_bytes, st)
+        L.call("ddfa_graph_ptr", _p(bnn), B, _p(graph_ptr), st)
+    dg = DeviceGraph(N, E, B, indptr, indices, indptr_t, indices_t, graph_ptr, device)
+    dg._csr_ws = ws  # keep the error counter alive (ws[0:4] = dropped-edge count)
+    g._cache[key] = dg
+    return dg
+
+
+# ------------------------------------------------------------------------------------------
+# Parameters
+# ------------------------------------------------------------------------------------------
+@dataclass
+class ParamPack:
+    """Tensors of one FlowGNNGGNNModule, in the reference's state_dict naming:
+    tables: all_embeddings.{api,datatype,literal,operator}.weight (or [embedding.weight]);
+    w_msg/b_msg: ggnn.linears.0.{weight,bias}; w_ih/w_hh/b_ih/b_hh: ggnn.gru.*;
+    w_gate/b_gate: pooling.gate_nn.{weight,bias}; mlp_w/mlp_b: output_layer.{0,2,..}.{weight,bias}."""
+    tables: List[torch.Tensor]
+    w_msg: torch.Tensor
+    b_msg: torch.Tensor
+    w_ih: torch.Tensor
+    w_hh: torch.Tensor
+    b_ih: torch.Tensor
+    b_hh: torch.Tensor
+    w_gate: torch.Tensor
+    b_gate: torch.Tensor
+    mlp_w: List[torch.Tensor] = field(default_factory=list)
+    mlp_b: List[torch.Tensor] = field(default_factory=list)
+
+    def flat_list(self) -> List[torch.Tensor]:
+        return [*self.tables, self.w_msg, self.b_msg, self.w_ih, self.w_hh, self.b_ih, self.b_hh,
+                self.w_gate, self.b_gate, *self.mlp_w, *self.mlp_b]
+
+    @staticmethod
+    def from_flat_list(ts, num_tables: int, num_layers: int) -> "ParamPack":
+        ts = list(ts)
+        k = num_tables
+        return ParamPack(ts[:k], *ts[k:k + 8], mlp_w=ts[k + 8:k + 8 + num_layers],
+                         mlp_b=ts[k + 8 + num_layers:k + 8 + 2 * num_layers])
+
+    def zeros_like(self) -> "ParamPack":
+        return ParamPack.from_flat_list([torch.zeros_like(t) for t in self.flat_list()], len(self.tables), len(self.mlp_w))
+
+
+@dataclass
+class Saved:
+    """Activations kept between forward and backward."""
+    T: int
+    D: int
+    x: torch.Tensor
+    h: List[torch.Tensor]            # h[0..T]
+    s: List[torch.Tensor]            # s[0..T-1]
+    gates: List[torch.Tensor]        # [4,N,D] per step
+    w_fold: torch.Tensor
+    b_fold: torch.Tensor
+    pooled: torch.Tensor
+    gate_logit: torch.Tensor
+    seg_max: torch.Tensor
+    seg_sum: torch.Tensor
+    mlp_act: Optional[torch.Tensor]
+    idx: List[torch.Tensor]
+
+
+class Workspace:
+    """Grow-only named device buffers (used by the fused trainer to avoid per-step allocation)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32):
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = buf
+        return buf[:numel].view(*shape)
+
+
+class _FreshAlloc:
+    """Allocation policy of the autograd path: every buffer is a fresh tensor (caching allocator)."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def get(self, name, shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+
+def node_indices(g: BatchedCFG, concat_all_absdf: bool, feature_key: str, device) -> List[torch.Tensor]:
+    """ggnn.py:84-92: which ndata vectors feed the embedding(s)."""
+    if concat_all_absdf:
+        keys = [f"_ABS_DATAFLOW_{k}" for k in ABS_DATAFLOW_SUBKEYS]
+    else:
+        keys = [feature_key]
+    out = []
+    for k in keys:
+        t = g.ndata[k]
+        if t.dtype != torch.int64:
+            t = t.to(torch.int64)
+        out.append(t.to(device, non_blocking=True).contiguous())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Forward / backward
+# ------------------------------------------------------------------------------------------
+def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps: int, *, training: bool,
+            engine: int = ENGINE_SIMT, alloc=None, oob_counter: Optional[torch.Tensor] = None):
+    """Returns (pooled [B,2D], logits [B] or None, Saved or None)."""
+    _require_cuda(*params.flat_list(), dg.indptr, *idx)
+    L = _lib.lib()
+    dev = dg.device
+    alloc = alloc or _FreshAlloc(dev)
+    K = len(params.tables)
+    V, H = params.tables[0].shape
+    D = K * H
+    N, B, T = dg.num_nodes, dg.batch_size, n_steps
+    nl = len(params.mlp_w)
+    st = _stream_ptr()
+
+    x = alloc.get("x", (N, D))
+    L.call("ddfa_embed_concat_fwd", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
+           K, V, H, N, _p(x), _p(oob_counter), st)
+    w_fold = alloc.get("w_fold", (3 * D, D))
+    b_fold = alloc.get("b_fold", (3 * D,))
+    L.call("ddfa_fold_weights_fwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), D, _p(w_fold), _p(b_fold), st)
+
+    ws_bytes = L.call("ddfa_gru_step_workspace_bytes", N, D, engine)
+    ws = alloc.get("gru_ws", (max(ws_bytes, 16),), torch.uint8)
+    hs, ss, gs = [x], [], []
+    h_cur = x
+    for t in range(T):
+        if training:
+            s_t = alloc.get(f"s{t}", (N, D))
+            h_next = alloc.get(f"h{t + 1}", (N, D))
+            g_t = alloc.get(f"gates{t}", (4, N, D))
+        else:
+            s_t = alloc.get("s", (N, D))
+            h_next = alloc.get(f"hpp{t % 2}", (N, D))
+            g_t = None
+        L.call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st)
+        L.call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
+               _p(params.w_hh), _p(params.b_hh), N, D, _p(h_next), _p(g_t), _p(ws), ws_bytes, engine, st)
+        if training:
+            hs.append(h_next); ss.append(s_t); gs.append(g_t)
+        h_cur = h_next
+
+    pooled = alloc.get("pooled", (B, 2 * D))
+    logits = alloc.get("logits", (B,)) if nl > 0 else None
+    gate_logit = alloc.get("gate_logit", (N,)) if training else None
+    seg_max = alloc.get("seg_max", (B,)) if training else None
+    seg_sum = alloc.get("seg_sum", (B,)) if training else None
+    mlp_act = alloc.get("mlp_act", (max(nl - 1, 1), B, 2 * D)) if (training and nl > 1) else None
+    L.call("ddfa_readout_mlp_fwd", _p(h_cur), _p(x), _p(dg.graph_ptr), B, D, _p(params.w_gate), _p(params.b_gate),
+           ptr_array([_p(t) for t in params.mlp_w]) if nl else None,
+           ptr_array([_p(t) for t in params.mlp_b]) if nl else None,
+           nl, _p(pooled), _p(logits), _p(gate_logit), _p(seg_max), _p(seg_sum), _p(mlp_act), st)
+    saved = None
+    if training:
+        saved = Saved(T, D, x, hs, ss, gs, w_fold, b_fold, pooled, gate_logit, seg_max, seg_sum, mlp_act, idx)
+    return pooled, logits, saved
+
+
+def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack, *, dlogits: Optional[torch.Tensor] = None,
+             dpooled: Optional[torch.Tensor] = None, engine: int = ENGINE_SIMT, alloc=None):
+    """Accumulates (+=) parameter gradients into ``grads``.  Exactly one of dlogits / dpooled is given."""
+    L = _lib.lib()
+    dev = dg.device
+    alloc = alloc or _FreshAlloc(dev)
+    K = len(params.tables)
+    V, H = params.tables[0].shape
+    D, T = saved.D, saved.T
+    N, B = dg.num_nodes, dg.batch_size
+    nl = len(params.mlp_w)
+    st = _stream_ptr()
+    if dg.indptr_t is None:
+        raise DdfaError("backward needs the transposed CSR (prepare_graph(need_transpose=True))")
+
+    if dlogits is not None:
+        if nl == 0:
+            raise DdfaError("dlogits given but the module has no MLP head")
+        dpooled_buf = alloc.get("dpooled", (B, 2 * D))
+        scratch = alloc.get("mlp_scratch", (2, B, 2 * D))
+        L.call("ddfa_mlp_bwd", _p(dlogits), _p(saved.pooled), _p(saved.mlp_act), ptr_array([_p(t) for t in params.mlp_w]),
+               B, D, nl, _p(dpooled_buf), ptr_array([_p(t) for t in grads.mlp_w]), ptr_array([_p(t) for t in grads.mlp_b]),
+               _p(scratch), st)
+        dpooled = dpooled_buf
+    elif dpooled is None:
+        raise DdfaError("backward: neither dlogits nor dpooled given")
+
+    dh = alloc.get("dh_a", (N, D))
+    dh_alt = alloc.get("dh_b", (N, D))
+    dx_direct = alloc.get("dx_direct", (N, D))
+    L.call("ddfa_readout_bwd", _p(dpooled), _p(saved.pooled), _p(saved.h[T]), _p(saved.x), _p(dg.graph_ptr), B, D,
+           _p(params.w_gate), _p(saved.gate_logit), _p(saved.seg_max), _p(saved.seg_sum), _p(dh), _p(dx_direct),
+           _p(grads.w_gate), _p(grads.b_gate), st)
+
+    dw_fold = alloc.get("dw_fold", (3 * D, D))
+    db_fold = alloc.get("db_fold", (3 * D,))
+    dw_fold.zero_()
+    db_fold.zero_()
+    ds = alloc.get("ds", (N, D))
+    ws_bytes = 4 * 2 * N * 3 * D
+    ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
+    for t in range(T - 1, -1, -1):
+        L.call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
+               _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
+               _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes, engine, st)
+        # dh_t += A^T ds   (gather over the transposed graph)
+        L.call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st)
+        dh, dh_alt = dh_alt, dh
+    L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
+           _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)
+    L.call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,
+           ptr_array([_p(t) for t in grads.tables]), st)
+
+
+def graph_label_bce(dg: DeviceGraph, vuln: torch.Tensor, logits: Optional[torch.Tensor], pos_weight: float,
+                    loss_scale: float, grad_scale: float, want_grad: bool, alloc=None, loss_out=None):
+    """Labels (segment max of _VULN) + BCE-with-logits sum (+ dlogits). Returns (labels, loss[1], dlogits)."""
+    L = _lib.lib()
+    alloc = alloc or _FreshAlloc(dg.device)
+    B = dg.batch_size
+    labels = alloc.get("labels", (B,))
+    loss = None
+    if logits is not None:
+        loss = loss_out if loss_out is not None else alloc.get("loss", (1,))
+    dlogits = alloc.get("dlogits", (B,)) if (want_grad and logits is not None) else None
+    if vuln.dtype != torch.int32:
+        vuln = vuln.to(torch.int32)
+    L.call("ddfa_graph_label_bce", _p(logits), _p(vuln.contiguous()), _p(dg.graph_ptr), B, float(pos_weight),
+           float(loss_scale), float(grad_scale), _p(labels), _p(loss), _p(dlogits), _stream_ptr())
+    return labels, loss, dlogits

@@ -1,0 +1,114 @@
+"""Fused data-parallel train step for ``FlowGNNGGNNModule`` on B200.
+
+One process per GPU.  Per step: forward (T x {gather, GRU}) -> readout+MLP -> labels+BCE ->
+hand-written backward -> ONE all-reduce of the flat gradient buffer (NCCL over NVLink/NVSwitch via
+``torch.distributed``; the loss rides in the buffer's last element) -> fused Adam over the flat
+parameter buffer.  Graphs never exchange messages, so the batch shards across ranks with no
+data-path collective; the gradient all-reduce is the only exchange step.
+
+Replaces, for the hot path only, Lightning's ``Trainer.fit`` loop around
+``BaseModule.training_step`` (base_module.py:171-199) + ``torch.optim.Adam`` (config_default.yaml:43-47).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import engine as E
+from .module import FlowGNNGGNNModule, _ENGINES
+
+_ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat buffers
+
+
+class FusedTrainer:
+    def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False):
+        if module.device.type != "cuda":
+            raise _lib.DdfaError("FusedTrainer needs the module on a CUDA device (no CPU fallback)")
+        self.module = module
+        self.device = module.device
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_cuda_graph = use_cuda_graph
+        plist = module.param_list()
+        offs, total = [], 0
+        for p in plist:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = total
+        with torch.cuda.device(self.device):
+            self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.flat_g = torch.zeros(total + _ALIGN, dtype=torch.float32, device=self.device)  # [+ loss slot]
+            self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        gviews = []
+        for p, o in zip(plist, offs):
+            view = self.flat_p[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view                      # module parameters now alias the flat buffer
+            gviews.append(self.flat_g[o:o + p.numel()].view_as(p))
+        K, nl = len(module._tables()), module._num_layers
+        self.params = E.ParamPack.from_flat_list([p.data for p in plist], K, nl)
+        self.grads = E.ParamPack.from_flat_list(gviews, K, nl)
+        self.loss_slot = self.flat_g[total:total + 1]
+        self.ws = E.Workspace(self.device)
+        self._graphs = {}
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------------------------
+    def _enqueue(self, g, dg, idx, vuln, global_batch: int):
+        m = self.module
+        eng = _ENGINES[m.engine]
+        pw = 1.0 if m.hparams.positive_weight is None else float(m.hparams.positive_weight)
+        self.flat_g.zero_()
+        _, logits, saved = E.forward(self.params, dg, idx, m.hparams.n_steps, training=True, engine=eng, alloc=self.ws)
+        _, _, dlogits = E.graph_label_bce(dg, vuln, logits, pw, 1.0 / global_batch, 1.0 / global_batch, True,
+                                          alloc=self.ws, loss_out=self.loss_slot)
+        E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws)
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        L = _lib.lib()
+        L.call("ddfa_adam_flat", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+               self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.numel, self.lr, self.betas[0], self.betas[1],
+               self.eps, self.weight_decay, torch.cuda.current_stream().cuda_stream)
+
+    def step(self, batch, global_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on this rank's shard.  Returns the device tensor holding the
+        global mean loss (valid after the step's stream work completes)."""
+        m = self.module
+        g, dg, idx = m._prepare(batch)
+        vuln = g.ndata["_VULN"]
+        if vuln.device != self.device or vuln.dtype != torch.int32:
+            key = "vuln_dev"
+            cached = g._cache.get(key)
+            if cached is None:
+                cached = vuln.to(self.device, non_blocking=True).to(torch.int32).contiguous()
+                g._cache[key] = cached
+            vuln = cached
+        if global_batch is None:
+            global_batch = dg.batch_size * self.world
+        with torch.cuda.device(self.device):
+            if not self.use_cuda_graph:
+                self._enqueue(g, dg, idx, vuln, global_batch)
+            else:
+                key = id(g)
+                graph = self._graphs.get(key)
+                if graph is None:
+                    # warm the workspace outside capture, then capture this batch's step
+                    self._enqueue(g, dg, idx, vuln, global_batch)
+                    torch.cuda.synchronize(self.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._enqueue(g, dg, idx, vuln, global_batch)
+                    self._graphs[key] = (graph, g)
+                else:
+                    graph = graph[0]
+                if isinstance(graph, tuple):
+                    graph = graph[0]
+                graph.replay()
+        return self.loss_slot

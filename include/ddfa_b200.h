@@ -1,0 +1,191 @@
+/*
+ * ddfa_b200.h — C ABI of libddfa_b200.so: the B200 (sm_100a) implementation of the DDFA
+ * code_gnn GGNN hot path (embedding -> T x {edge gather-sum, GRU} -> attention readout -> MLP,
+ * loss, backward, Adam).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
+ *   - tensors are dense, row-major, fp32 activations/parameters, int32 graph structure;
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it
+ *     (no allocation, no synchronisation, CUDA-graph-capture safe);
+ *   - return value: 0 on success, negative ddfa_status otherwise; ddfa_last_error()
+ *     returns a thread-local message for the last failing call;
+ *   - the caller owns all memory; workspace sizes are reported by *_workspace_bytes().
+ *
+ * Notation: N nodes, E edges (DGL orientation: message src -> dst, aggregated at dst),
+ * B graphs, K embedding tables (1 or 4), H embedding width, D = K*H hidden width,
+ * T propagation steps, L MLP layers, V vocabulary size.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the DeepDFA repo).
+ */
+#ifndef DDFA_B200_H
+#define DDFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDFA_ABI_VERSION 1
+
+typedef enum ddfa_status {
+  DDFA_OK = 0,
+  DDFA_ERR_INVALID_ARG = -1,   /* bad pointer / size / unsupported shape            */
+  DDFA_ERR_CUDA = -2,          /* a CUDA runtime call or launch failed              */
+  DDFA_ERR_UNSUPPORTED = -3,   /* shape outside what the selected engine supports   */
+  DDFA_ERR_WORKSPACE = -4      /* workspace too small                               */
+} ddfa_status;
+
+/* GEMM engines for the dense GRU matmuls */
+#define DDFA_ENGINE_SIMT 0     /* fp32 FFMA reference kernels (any D % 4 == 0)              */
+#define DDFA_ENGINE_TCGEN05 1  /* tcgen05 / TMEM, bf16x3 split operands, fp32 accumulate (D == 128) */
+
+int ddfa_abi_version(void);
+const char *ddfa_last_error(void);
+/* 1 if the current device is compute capability 10.x, 0 otherwise, <0 on CUDA error */
+int ddfa_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Graph structure.  Replaces the DGLGraph the reference hands to GatedGraphConv / pooling
+ * (DDFA/code_gnn/models/flow_gnn/ggnn.py:95,102; batches built by dgl.batch,
+ * DDFA/sastvd/linevd/dataset.py:76, datamodule.py:116-141).
+ * ------------------------------------------------------------------------------------- */
+
+/* COO -> CSR-by-destination (indptr/indices: in-neighbours of each node, sorted by source id)
+ * and CSR-by-source (indptr_t/indices_t: out-neighbours, sorted; the transposed graph used by
+ * the backward gather).  src/dst are int64 (idx_bytes=8, what DGL hands over) or int32
+ * (idx_bytes=4).  indptr, indptr_t: int32[N+1]; indices, indices_t: int32[E].
+ * Either output pair may be NULL to skip it.  Returns DDFA_ERR_INVALID_ARG for N<0/E<0. */
+size_t ddfa_build_csr_workspace_bytes(int64_t num_edges, int32_t num_nodes);
+int ddfa_build_csr(const void *src, const void *dst, int idx_bytes, int64_t num_edges,
+                   int32_t num_nodes, int32_t *indptr, int32_t *indices, int32_t *indptr_t,
+                   int32_t *indices_t, void *workspace, size_t workspace_bytes, void *stream);
+
+/* batch_num_nodes int64[B] (DGLGraph.batch_num_nodes()) -> graph_ptr int32[B+1] (exclusive scan). */
+int ddfa_graph_ptr(const int64_t *batch_num_nodes, int32_t num_graphs, int32_t *graph_ptr,
+                   void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  embedding + concat.  Replaces ggnn.py:84-92 (4x nn.Embedding + torch.cat, or one).
+ * idx[k]: int64[N] with values in [0,V); tables[k]: fp32[V,H]; x: fp32[N, K*H].
+ * idx/tables are HOST arrays of K device pointers.  Out-of-range indices are clamped and
+ * counted in *oob_count (int32 device counter, may be NULL) — the module raises on non-zero.
+ * ------------------------------------------------------------------------------------- */
+int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables, int32_t num_tables,
+                          int32_t vocab, int32_t width, int32_t num_nodes, float *x,
+                          int32_t *oob_count, void *stream);
+/* dtables[k][idx_k[n], :] += (dx + dx2)[n, k*H:(k+1)*H]   (autograd of ggnn.py:84-92).
+ * dx2 may be NULL; it lets the caller sum the two gradient paths into x (through the GGNN and
+ * through the concat of ggnn.py:98) without a separate add kernel. */
+int ddfa_embed_concat_bwd(const int64_t *const *idx, const float *dx, const float *dx2,
+                          int32_t num_tables, int32_t vocab, int32_t width, int32_t num_nodes,
+                          float *const *dtables, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  CSR edge gather-sum: out[v,:] = (accumulate ? out[v,:] : 0) + sum_{e in row v} h[indices[e],:]
+ * Replaces DGL update_all(fn.copy_u('h','m'), fn.sum('m','a')) inside GatedGraphConv
+ * (call site ggnn.py:95).  With the CSR-by-source arrays it is the backward of the same op.
+ * D % 4 == 0, D <= 1024.  This is the HBM-roofline kernel (bytes: E*D*4 + N*D*4 + E*4 + (N+1)*4).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *h,
+                    int32_t num_nodes, int32_t dim, float *out, int accumulate, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Weight folding (done once per forward): w_fold = W_ih @ W  [3D,D], b_fold = W_ih @ b [3D]
+ * so that  gi = (A h) w_fold^T + indeg * b_fold + b_ih  ==  GRUCell's  a W_ih^T + b_ih  with
+ * a_v = sum_{u->v} (W h_u + b)   (DGL GatedGraphConv linears[0] + sum; ggnn.py:57-60).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_fold_weights_fwd(const float *w_msg, const float *b_msg, const float *w_ih, int32_t dim,
+                          float *w_fold, float *b_fold, void *stream);
+/* dW_ih += dw_fold W^T + db_fold b^T ; dW += W_ih^T dw_fold ; db += W_ih^T db_fold */
+int ddfa_fold_weights_bwd(const float *w_msg, const float *b_msg, const float *w_ih,
+                          const float *dw_fold, const float *db_fold, int32_t dim, float *dw_msg,
+                          float *db_msg, float *dw_ih, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  one GRU propagation step (torch.nn.GRUCell inside DGL GatedGraphConv; gate order r,z,n):
+ *   gi = s w_fold^T + indeg b_fold + b_ih ; gh = h w_hh^T + b_hh
+ *   r = sig(gi_r+gh_r) ; z = sig(gi_z+gh_z) ; n = tanh(gi_n + r*gh_n) ; h_out = (1-z)*n + z*h
+ * s = gather-sum of h (K3).  indptr gives indeg.  If save_gates != NULL it receives
+ * fp32[4][N][D] = r, z, n, gh_n (with b_hh_n) for the backward pass.
+ * workspace: engine-dependent scratch (ddfa_gru_step_workspace_bytes).
+ * ------------------------------------------------------------------------------------- */
+size_t ddfa_gru_step_workspace_bytes(int32_t num_nodes, int32_t dim, int engine);
+int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold,
+                      const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
+                      int32_t num_nodes, int32_t dim, float *h_out, float *save_gates,
+                      void *workspace, size_t workspace_bytes, int engine, void *stream);
+/* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
+ * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
+ * Accumulated (+=): dw_fold[3D,D], db_fold[3D], db_ih[3D], dw_hh[3D,D], db_hh[3D]. */
+int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates,
+                      const int32_t *indptr, const float *w_fold, const float *w_hh,
+                      int32_t num_nodes, int32_t dim, float *ds, float *dh, float *dw_fold,
+                      float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
+                      size_t workspace_bytes, int engine, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K5-K7  readout + MLP.  Replaces torch.cat([ggnn_out, feat_embed]) (ggnn.py:98, never
+ * materialised), DGL GlobalAttentionPooling(Linear(2D,1)) (ggnn.py:66-68,102) and the
+ * output_layer MLP (ggnn.py:70-80,107).
+ *   o_n = [h_T[n] | x[n]] ; g_n = <o_n, w_gate> + b_gate ; alpha = softmax of g over each graph
+ *   pooled[b] = sum_n alpha_n o_n   (fp32[B,2D]; the encoder_mode output, ggnn.py:104-105)
+ *   logits[b] = MLP(pooled[b])      (num_layers linears, ReLU between, last -> 1)
+ * mlp_w / mlp_b: HOST arrays of num_layers device pointers ([2D,2D] ... [1,2D]); num_layers==0
+ * skips the MLP (encoder mode; logits may be NULL).  Saved for backward when non-NULL:
+ * gate_logit fp32[N], seg_max fp32[B], seg_sum fp32[B], mlp_act fp32[(L-1)][B][2D] (post-ReLU).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_readout_mlp_fwd(const float *h_final, const float *x, const int32_t *graph_ptr,
+                         int32_t num_graphs, int32_t dim, const float *w_gate, const float *b_gate,
+                         const float *const *mlp_w, const float *const *mlp_b, int32_t num_layers,
+                         float *pooled, float *logits, float *gate_logit, float *seg_max,
+                         float *seg_sum, float *mlp_act, void *stream);
+/* MLP backward: dlogits[B] -> dpooled[B,2D]; accumulates dmlp_w / dmlp_b (+=).
+ * scratch: fp32[2][B][2D]. */
+int ddfa_mlp_bwd(const float *dlogits, const float *pooled, const float *mlp_act,
+                 const float *const *mlp_w, int32_t num_graphs, int32_t dim, int32_t num_layers,
+                 float *dpooled, float *const *dmlp_w, float *const *dmlp_b, float *scratch,
+                 void *stream);
+/* Readout backward: dpooled[B,2D] -> dh_final[N,D], dx[N,D] (both overwritten);
+ * accumulates dw_gate[2D], db_gate[1] (+=). */
+int ddfa_readout_bwd(const float *dpooled, const float *pooled, const float *h_final, const float *x,
+                     const int32_t *graph_ptr, int32_t num_graphs, int32_t dim, const float *w_gate,
+                     const float *gate_logit, const float *seg_max, const float *seg_sum,
+                     float *dh_final, float *dx, float *dw_gate, float *db_gate, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K8  graph labels + loss.  Replaces BaseModule.get_label (base_module.py:83-95: dgl.unbatch +
+ * per-graph max of ndata["_VULN"]) and BCEWithLogitsLoss(pos_weight) (base_module.py:72-74,183).
+ *   label[b] = max_n vuln[n] ; loss = (1/B) sum_b bce(logit_b, label_b; pos_weight)
+ * dlogits[b] = grad_scale * d(sum_b bce)/dlogit_b  (caller passes grad_scale = 1/B_global).
+ * loss_out: fp32[1] receives  loss_scale * sum_b bce  (caller passes loss_scale = 1/B_global).
+ * vuln: int32[N].  labels: fp32[B] out.  dlogits may be NULL (evaluation).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_graph_label_bce(const float *logits, const int32_t *vuln, const int32_t *graph_ptr,
+                         int32_t num_graphs, float pos_weight, float loss_scale, float grad_scale,
+                         float *labels, float *loss_out, float *dlogits, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K10  torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2 (DDFA/configs/
+ * config_default.yaml:43-47) over one flat parameter buffer.  step_count: int32[1] device
+ * counter, incremented by the kernel (graph-capture safe).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_adam_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                   int32_t *step_count, int64_t numel, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Generic row-major fp32 GEMM on the SIMT engine (building block, exported for tests):
+ *   C[M,N] = alpha * op(A) op(B) + beta * C,  op(X) = X or X^T per trans flag.
+ * split_k > 1 accumulates partial products with atomics (requires beta == 1, C pre-initialised).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_sgemm(int trans_a, int trans_b, int32_t m, int32_t n, int32_t k, float alpha, const float *a,
+               int32_t lda, const float *b, int32_t ldb, float beta, float *c, int32_t ldc,
+               int32_t split_k, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDFA_B200_H */
