@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — DDFA GGNN hot path: CFG graphs/sec of a full train step on B200.
+
+Workload (BASELINE.json configs[1], "C0"): synthetic Big-Vul-shaped batches of 256 CFGs x 150 nodes /
+300 edges (incl. self loops), 4 x Embedding(1002,32) -> 128-d, T=8 propagation steps, attention
+readout, 2-layer MLP head, BCE loss, backward, gradient all-reduce (N>1), Adam (coupled L2).
+Per-GPU batch is fixed as N grows (weak scaling; the batch shards by graphs, no data-path collective).
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA, libddfa_b200.so)
+  python bench.py --impl reference --steps K --warmup W    # reference arm: the reference path's CPU
+                                                           # restatement (oracle/) on the host cores
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FEAT = "_ABS_DATAFLOW_api_all_limitall_1000_limitsubkeys_1000"
+CFG = dict(graphs=256, nodes=150, edges_per_node=2.0, input_dim=1002, hidden_dim=32, n_steps=8, layers=2)
+METRIC = "CFG graphs/sec (train step)"
+UNIT = "graphs/s"
+NUM_BATCHES = 8  # distinct resident batches rotated through the timed region
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"C0: {args.graphs} CFGs/GPU x {CFG['nodes']} nodes / {int(CFG['nodes'] * CFG['edges_per_node'])} edges, "
+                    f"4xEmb(1002,32)->128-d, T={CFG['n_steps']}, attention readout, {CFG['layers']}-layer MLP, "
+                    "BCE, backward, Adam (coupled L2)",
+        "global_batch": args.graphs * world,
+        "per_gpu_batch": args.graphs,
+        "n_steps": CFG["n_steps"], "hidden": 128, "mlp_layers": CFG["layers"],
+        "parallelism": f"dp{world}",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thread = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, mxc = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # timed region shorter than the sampling period: fall back to all samples
+            for ts, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-event span profiler for selected C-ABI calls (engine.profile_hook)
+# ------------------------------------------------------------------------------------------------
+class SpanProfiler:
+    def __init__(self, names):
+        self.names = set(names)
+        self.spans = {n: [] for n in names}
+        self._open = {}
+        self.enabled = True
+
+    def wants(self, name):
+        return self.enabled and name in self.names
+
+    def begin(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._open[name] = e
+
+    def end(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.spans[name].append((self._open.pop(name), e))
+
+    def mean_ms(self, name):
+        xs = [a.elapsed_time(b) for a, b in self.spans[name]]
+        return (sum(xs) / len(xs), len(xs)) if xs else (None, 0)
+
+    def total_ms(self, name):
+        return sum(a.elapsed_time(b) for a, b in self.spans[name])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference path's restatement (oracle/) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(graphs, steps, warmup, budget_s=None):
+    """Times full train steps (fwd + BCE + bwd + Adam) of the oracle on the CPU. Returns (graphs/s, s/step, steps, threads)."""
+    from deepdfa_b200 import synth
+    from oracle import ggnn_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = O.OracleFlowGNNGGNN(FEAT, CFG["input_dim"], CFG["hidden_dim"], CFG["n_steps"], CFG["layers"], concat_all_absdf=True)
+    opt = O.make_optimizer(model)
+    batches = [synth.make_batch(graphs, CFG["nodes"], CFG["edges_per_node"], CFG["input_dim"], seed=i) for i in range(2)]
+
+    def one(i):
+        opt.zero_grad()
+        loss, _ = model.training_loss(batches[i % len(batches)])
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        one(i)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return graphs * done / dt, dt / done, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return 0
+    val, s_per_step, done, threads = cpu_train_steps(args.graphs, args.steps, max(args.warmup, 1), budget_s=240.0)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{done} full train steps of one {args.graphs}-graph C0 batch (reference cannot run: dgl/"
+                                   "pytorch_lightning absent; pure-PyTorch restatement oracle/ggnn_oracle.py, torch CPU, all host threads)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": f"world_size={world}: rank 0 alone runs the CPU arm",
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def batch_bytes(g):
+    src, dst = g.edges()
+    keys = [f"_ABS_DATAFLOW_{k}" for k in ("api", "datatype", "literal", "operator")] + ["_VULN"]
+    n = src.numel() * src.element_size() + dst.numel() * dst.element_size() + g.batch_num_nodes().numel() * 8
+    for k in keys:
+        n += g.ndata[k].numel() * g.ndata[k].element_size()
+    return n
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import deepdfa_b200 as D
+    from deepdfa_b200 import _lib, engine as E, synth
+    from deepdfa_b200.batched_graph import BatchedCFG
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    if L.call("ddfa_device_supported") != 1:
+        raise SystemExit("bench.py: device is not compute capability 10.x")
+
+    torch.manual_seed(0)
+    model = D.FlowGNNGGNNModule(FEAT, CFG["input_dim"], CFG["hidden_dim"], CFG["n_steps"], CFG["layers"], concat_all_absdf=True,
+                                engine=args.engine).to(dev)
+    trainer = D.FusedTrainer(model)
+    # distinct batches per rank and per slot (weak scaling: every rank has its own args.graphs graphs)
+    host_batches = [synth.make_batch(args.graphs, CFG["nodes"], CFG["edges_per_node"], CFG["input_dim"], seed=1000 * rank + i).pin_memory()
+                    for i in range(NUM_BATCHES)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    N, Eg = dev_batches[0].num_nodes(), dev_batches[0].num_edges()
+    Dh, T = 128, CFG["n_steps"]
+    global_batch = args.graphs * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds + caches the device CSR of every resident batch) -------------------
+    for i in range(max(args.warmup, 3)):
+        trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
+    torch.cuda.synchronize()
+    l0 = L.call("ddfa_launch_count")
+    trainer.step(dev_batches[0], global_batch)
+    torch.cuda.synchronize()
+    launches_per_step = L.call("ddfa_launch_count") - l0
+
+    # ---- timed region: K resident-input train steps ------------------------------------------------
+    prof = SpanProfiler(["gather_fwd", "gather_bwd", "ddfa_gru_step_fwd", "ddfa_gru_step_bwd"])
+    E.profile_hook = prof
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    E.profile_hook = None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    final_loss = float(trainer.loss_slot.item())
+    value = global_batch * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host (pinned) buffers -> H2D -> device CSR build -> train step -> loss D2H, every step ----
+    def fresh(b):  # a new graph object: no cached device CSR, so the whole input path is inside the timed region
+        return BatchedCFG(*b.edges(), b.batch_num_nodes(), dict(b.ndata))
+    for i in range(3):
+        float(trainer.step(fresh(host_batches[i % NUM_BATCHES]), global_batch).item())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps = args.steps
+    for i in range(e2e_steps):
+        loss_val = float(trainer.step(fresh(host_batches[i % NUM_BATCHES]), global_batch).item())
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = global_batch * e2e_steps / (float(t2.item()) * 1e-3)
+    h2d = batch_bytes(host_batches[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the edge-gather kernel (BASELINE metric (ii)) + the GRU GEMM share --------------
+    peaks = measured_peaks()
+    gather_bytes = Eg * Dh * 4 + N * Dh * 4 + Eg * 4 + (N + 1) * 4          # SURVEY.md §8(d), per launch
+    gf_ms, gf_n = prof.mean_ms("gather_fwd")
+    gb_ms, gb_n = prof.mean_ms("gather_bwd")
+    g_all = [a.elapsed_time(b) for a, b in prof.spans["gather_fwd"] + prof.spans["gather_bwd"]]
+    g_ms = sum(g_all) / len(g_all)
+    achieved = gather_bytes / (g_ms * 1e-3) / 1e9
+    share = {k: prof.total_ms(k) / ms for k in prof.spans}
+    flops_fwd_step = 2.0 * N * (6 * Dh * Dh)                                  # folded GRU GEMMs per propagation step
+    gru_f_ms, _ = prof.mean_ms("ddfa_gru_step_fwd")
+    gru_b_ms, _ = prof.mean_ms("ddfa_gru_step_bwd")
+    roofline = {"kernel": "gather_sum_kernel (CSR edge gather, fwd over CSR + bwd over transposed CSR)", "bound": "hbm",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "peak_source": peaks["source"], "traffic": None, "bytes_per_launch": gather_bytes,
+                "avg_launch_us": g_ms * 1e3, "launches_timed": len(g_all),
+                "fwd_us": gf_ms * 1e3, "bwd_us": gb_ms * 1e3, "share_of_step": share["gather_fwd"] + share["gather_bwd"],
+                "storage_dtype": "f32"}
+    gru = {"kernel": f"GRU step ({args.engine} engine)", "bound": "tensor", "unit": "TFLOP/s",
+           "fwd_achieved": flops_fwd_step / (gru_f_ms * 1e-3) / 1e12, "bwd_achieved": 2 * flops_fwd_step / (gru_b_ms * 1e-3) / 1e12,
+           "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"],
+           "fwd_us": gru_f_ms * 1e3, "bwd_us": gru_b_ms * 1e3,
+           "share_of_step": share["ddfa_gru_step_fwd"] + share["ddfa_gru_step_bwd"],
+           "flops_per_launch_fwd": flops_fwd_step}
+    gru["frac_fwd"] = gru["fwd_achieved"] / gru["peak"]
+
+    # ---- cpu baseline on this box's host cores (bounded sample) ----------------------------------------
+    cpu_val, cpu_s, cpu_done, cpu_threads = cpu_train_steps(args.graphs, 12, 2, budget_s=20.0)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.engine == "simt" else "f32 (GRU GEMMs: bf16x3 split operands, f32 accumulate)",
+        "data": "synthetic", "config": dict(workload_config(args, world), engine=args.engine,
+                                             l2="per-step working set ~0.96 GB of saved activations > 126 MB L2; 8 distinct resident batches rotated"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "path": "pinned host COO + node indices -> H2D -> ddfa_build_csr -> fused train step -> loss .item()"},
+        "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline, "roofline_gru": gru,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": f"{cpu_done} full train steps of one {args.graphs}-graph C0 batch, oracle/ggnn_oracle.py (torch CPU)"},
+        "final_loss": final_loss, "e2e_last_loss": loss_val,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--graphs", type=int, default=CFG["graphs"], help="graphs per GPU per step")
+    ap.add_argument("--engine", choices=["simt", "tcgen05"], default=os.environ.get("DDFA_B200_ENGINE", "simt"))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

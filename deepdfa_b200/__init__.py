@@ -9,7 +9,7 @@ Public surface (mirrors the reference for this path only):
 Importing the package does not load the CUDA library; the first kernel call does, and raises if
 ``deepdfa_b200/lib/libddfa_b200.so`` is missing (there is no CPU fallback).
 """
-from .graph import BatchedCFG, add_self_loop, as_batched_cfg, batch, collate, graph, unbatch  # noqa: F401
+from .batched_graph import BatchedCFG, add_self_loop, as_batched_cfg, batch, collate, graph, unbatch  # noqa: F401
 from .module import FlowGNNGGNNModule, allfeats  # noqa: F401
 from .trainer import FusedTrainer  # noqa: F401
 from . import synth  # noqa: F401

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "ddfa_abi_version": (_int, []),
     "ddfa_last_error": (C.c_char_p, []),
     "ddfa_device_supported": (_int, []),
+    "ddfa_launch_count": (C.c_longlong, []),
+    "ddfa_engine_available": (_int, [_int]),
     "ddfa_build_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "ddfa_build_csr": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_graph_ptr": (_int, [_vp, _i32, _vp, _vp]),
@@ -56,7 +58,7 @@ _SIGNATURES = {
     "ddfa_sgemm": (_int, [_int, _int, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _i32, _f32, _vp, _i32, _i32, _vp]),
 }
 
-_NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported",
+_NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
               "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes"}
 
 

@@ -184,3 +184,45 @@ def collate(samples: Iterable):
     for k in extras[0] if extras and extras[0] else {}:
         merged[k] = torch.stack([torch.as_tensor(e[k]) for e in extras])
     return batch(list(graphs)), merged
+
+
+def partition_graphs(batch_num_nodes: torch.Tensor, world_size: int):
+    """Contiguous, node-count-balanced split of a batch's graphs over ``world_size`` ranks
+    (SURVEY.md §8e).  Returns ``world_size + 1`` graph offsets; rank r owns graphs [off[r], off[r+1]).
+    Every rank receives at least one graph when B >= world_size."""
+    bnn = batch_num_nodes.to(torch.int64).cpu()
+    B = int(bnn.shape[0])
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    if B < world_size:
+        raise ValueError(f"cannot split {B} graphs over {world_size} ranks")
+    csum = torch.cumsum(bnn, 0)
+    total = int(csum[-1]) if B else 0
+    offs = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        cut = int(torch.searchsorted(csum, torch.tensor(target, dtype=csum.dtype), right=False)) + 1
+        cut = max(cut, offs[-1] + 1)              # at least one graph per rank
+        cut = min(cut, B - (world_size - r))      # leave one graph for each remaining rank
+        offs.append(cut)
+    offs.append(B)
+    return offs
+
+
+def slice_batch(g: BatchedCFG, g0: int, g1: int) -> BatchedCFG:
+    """Graphs [g0, g1) of a batch as a new batch (node ids re-based).  Pure tensor slicing on the
+    graph's device: node ids of a batch are contiguous per graph."""
+    bnn = g.batch_num_nodes()
+    ptr = torch.zeros(bnn.shape[0] + 1, dtype=torch.int64, device=bnn.device)
+    ptr[1:] = torch.cumsum(bnn, 0)
+    n0, n1 = int(ptr[g0]), int(ptr[g1])
+    src, dst = g.edges()
+    keep = ((dst >= n0) & (dst < n1)).nonzero().squeeze(-1)
+    nd = {k: v[n0:n1] for k, v in g.ndata.items()}
+    return BatchedCFG(src[keep] - n0, dst[keep] - n0, bnn[g0:g1].clone(), nd)
+
+
+def split_batch(g: BatchedCFG, world_size: int) -> List[BatchedCFG]:
+    """Shard a batch over ranks (no data-path collective is needed: graphs never exchange messages)."""
+    offs = partition_graphs(g.batch_num_nodes(), world_size)
+    return [slice_batch(g, offs[r], offs[r + 1]) for r in range(world_size)]

@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (LIBDIR / "build.log").write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"]
     subprocess.run(cmd, check=True)
     STAMP.write_text(digest)
     return LIB

@@ -2,9 +2,14 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ddfa {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -20,6 +25,14 @@ extern "C" {
 int ddfa_abi_version(void) { return DDFA_ABI_VERSION; }
 
 const char *ddfa_last_error(void) { return ddfa::g_err; }
+
+int ddfa_engine_available(int engine) {
+  if (engine == DDFA_ENGINE_SIMT) return 1;
+  if (engine == DDFA_ENGINE_TCGEN05) return ddfa::gru_tc_available() ? 1 : 0;
+  return 0;
+}
+
+long long ddfa_launch_count(void) { return ddfa::g_launches.load(std::memory_order_relaxed); }
 
 int ddfa_device_supported(void) {
   int dev = 0;

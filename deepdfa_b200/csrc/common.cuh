@@ -9,6 +9,7 @@
 namespace ddfa {
 
 void set_error(const char *fmt, ...);
+void count_launch();  // abi.cu: process-wide counter of kernel launches issued by this library
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -27,6 +28,7 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
       ddfa::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));         \
       return DDFA_ERR_CUDA;                                                            \
     }                                                                                  \
+    ddfa::count_launch();                                                              \
   } while (0)
 
 #define DDFA_CUDA(call)                                                                \
@@ -46,6 +48,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
           float beta, float *C, int ldc, int split_k, cudaStream_t stream);
 // gru_tc.cu — tcgen05 engine entry points (D == 128)
+bool gru_tc_available();
 size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
 int gru_tc_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
                     const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,

@@ -3,6 +3,8 @@
 
 namespace ddfa {
 
+bool gru_tc_available() { return false; }
+
 size_t gru_tc_workspace_bytes(int32_t N, int32_t D) {
   (void)N; (void)D;
   return 16;

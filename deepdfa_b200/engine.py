@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import ENGINE_SIMT, ENGINE_TCGEN05, DdfaError, ptr_array
-from .graph import ABS_DATAFLOW_SUBKEYS, BatchedCFG, as_batched_cfg
+from .batched_graph import ABS_DATAFLOW_SUBKEYS, BatchedCFG, as_batched_cfg
 
 
 def _stream_ptr() -> int:
@@ -24,6 +24,23 @@ def _stream_ptr() -> int:
 
 def _p(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+# Optional timing hook (bench.py): an object with begin(name) / end(name) that records CUDA events
+# on the current stream around selected C-ABI calls.  None (default) costs nothing.
+profile_hook = None
+
+
+def _call(name, *args, tag=None):
+    """lib().call with the optional profiling span."""
+    hook = profile_hook
+    if hook is None or not hook.wants(tag or name):
+        return _lib.lib().call(name, *args)
+    hook.begin(tag or name)
+    try:
+        return _lib.lib().call(name, *args)
+    finally:
+        hook.end(tag or name)
 
 
 def _require_cuda(*tensors):
@@ -206,7 +223,7 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     st = _stream_ptr()
 
     x = alloc.get("x", (N, D))
-    L.call("ddfa_embed_concat_fwd", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
+    _call("ddfa_embed_concat_fwd", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
            K, V, H, N, _p(x), _p(oob_counter), st)
     w_fold = alloc.get("w_fold", (3 * D, D))
     b_fold = alloc.get("b_fold", (3 * D,))
@@ -225,8 +242,8 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
             s_t = alloc.get("s", (N, D))
             h_next = alloc.get(f"hpp{t % 2}", (N, D))
             g_t = None
-        L.call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st)
-        L.call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
+        _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
+        _call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
                _p(params.w_hh), _p(params.b_hh), N, D, _p(h_next), _p(g_t), _p(ws), ws_bytes, engine, st)
         if training:
             hs.append(h_next); ss.append(s_t); gs.append(g_t)
@@ -238,7 +255,7 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     seg_max = alloc.get("seg_max", (B,)) if training else None
     seg_sum = alloc.get("seg_sum", (B,)) if training else None
     mlp_act = alloc.get("mlp_act", (max(nl - 1, 1), B, 2 * D)) if (training and nl > 1) else None
-    L.call("ddfa_readout_mlp_fwd", _p(h_cur), _p(x), _p(dg.graph_ptr), B, D, _p(params.w_gate), _p(params.b_gate),
+    _call("ddfa_readout_mlp_fwd", _p(h_cur), _p(x), _p(dg.graph_ptr), B, D, _p(params.w_gate), _p(params.b_gate),
            ptr_array([_p(t) for t in params.mlp_w]) if nl else None,
            ptr_array([_p(t) for t in params.mlp_b]) if nl else None,
            nl, _p(pooled), _p(logits), _p(gate_logit), _p(seg_max), _p(seg_sum), _p(mlp_act), st)
@@ -278,7 +295,7 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     dh = alloc.get("dh_a", (N, D))
     dh_alt = alloc.get("dh_b", (N, D))
     dx_direct = alloc.get("dx_direct", (N, D))
-    L.call("ddfa_readout_bwd", _p(dpooled), _p(saved.pooled), _p(saved.h[T]), _p(saved.x), _p(dg.graph_ptr), B, D,
+    _call("ddfa_readout_bwd", _p(dpooled), _p(saved.pooled), _p(saved.h[T]), _p(saved.x), _p(dg.graph_ptr), B, D,
            _p(params.w_gate), _p(saved.gate_logit), _p(saved.seg_max), _p(saved.seg_sum), _p(dh), _p(dx_direct),
            _p(grads.w_gate), _p(grads.b_gate), st)
 
@@ -290,15 +307,15 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     ws_bytes = 4 * 2 * N * 3 * D
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
     for t in range(T - 1, -1, -1):
-        L.call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
+        _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
                _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
                _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes, engine, st)
         # dh_t += A^T ds   (gather over the transposed graph)
-        L.call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st)
+        _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st, tag="gather_bwd")
         dh, dh_alt = dh_alt, dh
     L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
            _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)
-    L.call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,
+    _call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,
            ptr_array([_p(t) for t in grads.tables]), st)
 
 

@@ -28,7 +28,7 @@ from torch import nn
 
 from . import engine as E
 from ._lib import ENGINE_SIMT, ENGINE_TCGEN05, DdfaError
-from .graph import as_batched_cfg
+from .batched_graph import as_batched_cfg
 
 logger = logging.getLogger(__name__)
 

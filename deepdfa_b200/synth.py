@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .graph import ABS_DATAFLOW_SUBKEYS, BatchedCFG
+from .batched_graph import ABS_DATAFLOW_SUBKEYS, BatchedCFG
 
 
 def _graph_sizes(rng: np.random.Generator, num_graphs: int, nodes_per_graph: int, variable: bool,

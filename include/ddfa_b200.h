@@ -46,6 +46,10 @@ int ddfa_abi_version(void);
 const char *ddfa_last_error(void);
 /* 1 if the current device is compute capability 10.x, 0 otherwise, <0 on CUDA error */
 int ddfa_device_supported(void);
+/* 1 if the given DDFA_ENGINE_* is compiled into this library, else 0 */
+int ddfa_engine_available(int engine);
+/* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
+long long ddfa_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Graph structure.  Replaces the DGLGraph the reference hands to GatedGraphConv / pooling

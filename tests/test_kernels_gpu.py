@@ -1,0 +1,334 @@
+"""GPU: every C-ABI entry point against the oracle's building blocks on the same seeded inputs.
+All calls go through libddfa_b200.so (ctypes); torch only holds the device buffers."""
+import numpy as np
+import pytest
+import torch
+
+from deepdfa_b200 import synth
+from deepdfa_b200._lib import ENGINE_SIMT, ENGINE_TCGEN05, DdfaError, lib, ptr_array
+from deepdfa_b200.engine import _p, _stream_ptr, prepare_graph
+from oracle import ggnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(t):
+    return t.to(DEV).contiguous()
+
+
+def st():
+    return _stream_ptr()
+
+
+def engines_for(D):
+    tc = lib().call("ddfa_engine_available", ENGINE_TCGEN05) == 1
+    return [ENGINE_SIMT, ENGINE_TCGEN05] if (D == 128 and tc) else [ENGINE_SIMT]
+
+
+# ---------------------------------------------------------------------------------------------
+def test_device_is_blackwell():
+    assert lib().call("ddfa_device_supported") == 1
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_build_csr_matches_numpy(idx_dtype):
+    rng = np.random.default_rng(0)
+    N, E = 1000, 5000
+    src = rng.integers(0, N, E); dst = rng.integers(0, N, E)
+    dst[:600] = 7            # a hub row with a long neighbour list
+    src[100:200] = 3         # duplicates
+    s, d = dev(torch.from_numpy(src).to(idx_dtype)), dev(torch.from_numpy(dst).to(idx_dtype))
+    L = lib()
+    indptr = torch.empty(N + 1, dtype=torch.int32, device=DEV); indices = torch.empty(E, dtype=torch.int32, device=DEV)
+    indptr_t = torch.empty_like(indptr); indices_t = torch.empty_like(indices)
+    wsb = L.call("ddfa_build_csr_workspace_bytes", E, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_build_csr", _p(s), _p(d), s.element_size(), E, N, _p(indptr), _p(indices), _p(indptr_t), _p(indices_t), _p(ws), wsb, st())
+    torch.cuda.synchronize()
+    order = np.lexsort((src, dst))
+    assert np.array_equal(indices.cpu().numpy(), src[order])
+    assert np.array_equal(indptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=N))]))
+    order_t = np.lexsort((dst, src))
+    assert np.array_equal(indices_t.cpu().numpy(), dst[order_t])
+    assert np.array_equal(indptr_t.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(src, minlength=N))]))
+    assert int(ws[:4].view(torch.int32)[0]) == 0
+
+
+def test_build_csr_large_scan_empty_and_out_of_range():
+    L = lib()
+    # > 4096 rows exercises the multi-pass scan carry
+    g = synth.make_batch(200, 150, seed=3, variable=True)
+    dg = prepare_graph(g, DEV)
+    src, dst = [t.numpy() for t in g.edges()]
+    torch.cuda.synchronize()
+    assert np.array_equal(dg.indptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=g.num_nodes()))]))
+    assert np.array_equal(dg.indices.cpu().numpy()[: g.num_edges()], src[np.lexsort((src, dst))])
+    assert np.array_equal(dg.graph_ptr.cpu().numpy(), np.concatenate([[0], np.cumsum(g.batch_num_nodes().numpy())]))
+    # empty edge list
+    indptr = torch.full((6,), -1, dtype=torch.int32, device=DEV); indices = torch.empty(1, dtype=torch.int32, device=DEV)
+    wsb = L.call("ddfa_build_csr_workspace_bytes", 0, 5); ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_build_csr", None, None, 8, 0, 5, _p(indptr), _p(indices), None, None, _p(ws), wsb, st())
+    assert indptr.cpu().tolist() == [0] * 6
+    # out-of-range ids are dropped and counted
+    s = dev(torch.tensor([0, 1, 9, 2])); d = dev(torch.tensor([1, 2, 0, -1]))
+    indptr = torch.empty(4, dtype=torch.int32, device=DEV); indices = torch.zeros(4, dtype=torch.int32, device=DEV)
+    wsb = L.call("ddfa_build_csr_workspace_bytes", 4, 3); ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_build_csr", _p(s), _p(d), 8, 4, 3, _p(indptr), _p(indices), None, None, _p(ws), wsb, st())
+    assert indptr.cpu().tolist() == [0, 0, 1, 2] and indices.cpu().tolist()[:2] == [0, 1]
+    assert int(ws[:4].view(torch.int32)[0]) == 2
+    with pytest.raises(DdfaError, match="workspace"):
+        L.call("ddfa_build_csr", _p(s), _p(d), 8, 4, 3, _p(indptr), _p(indices), None, None, _p(ws), 8, st())
+
+
+@pytest.mark.parametrize("D", [20, 32, 64, 128, 256, 512, 1024])
+def test_gather_sum_matches_index_add(D):
+    g = synth.make_edge_cases() if D != 128 else synth.make_batch(64, 150, seed=1, variable=True)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    torch.manual_seed(D)
+    h = torch.randn(N, D)
+    src, dst = g.edges()
+    ref = torch.zeros(N, D, dtype=torch.float64).index_add_(0, dst, h.double()[src])
+    hd, out = dev(h), torch.empty(N, D, device=DEV)
+    lib().call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(hd), N, D, _p(out), 0, st())
+    assert (out.cpu().double() - ref).abs().max() < 1e-5 * max(1.0, float(ref.abs().max()))
+    # accumulate over the transposed graph = backward of the op
+    base = torch.randn(N, D)
+    ref_t = base.double() + torch.zeros(N, D, dtype=torch.float64).index_add_(0, src, h.double()[dst])
+    out2 = dev(base)
+    lib().call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(hd), N, D, _p(out2), 1, st())
+    assert (out2.cpu().double() - ref_t).abs().max() < 1e-5 * max(1.0, float(ref_t.abs().max()))
+
+
+def test_gather_sum_is_deterministic_and_rejects_bad_shapes():
+    g = synth.make_batch(64, 150, seed=1)
+    dg = prepare_graph(g, DEV)
+    h = torch.randn(g.num_nodes(), 128, device=DEV)
+    a, b = torch.empty_like(h), torch.empty_like(h)
+    for o in (a, b):
+        lib().call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h), g.num_nodes(), 128, _p(o), 0, st())
+    assert torch.equal(a, b)
+    with pytest.raises(DdfaError, match="D=130"):
+        lib().call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h), 10, 130, _p(a), 0, st())
+    with pytest.raises(DdfaError, match="in-place"):
+        lib().call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h), 10, 128, _p(h), 0, st())
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(300, 384, 128), (37, 5, 19), (384, 128, 5000), (1, 256, 200), (256, 1, 256)])
+def test_sgemm(ta, tb, shape):
+    M, N, K = shape
+    torch.manual_seed(M * 7 + N)
+    A = torch.randn((K, M) if ta else (M, K)); B = torch.randn((N, K) if tb else (K, N)); C0 = torch.randn(M, N)
+    opA = A.t() if ta else A; opB = B.t() if tb else B
+    ref = 0.5 * opA.double() @ opB.double() + 2.0 * C0.double()
+    Ad, Bd, Cd = dev(A), dev(B), dev(C0)
+    lib().call("ddfa_sgemm", ta, tb, M, N, K, 0.5, _p(Ad), A.shape[1], _p(Bd), B.shape[1], 2.0, _p(Cd), N, 1, st())
+    tol = 1e-5 * (K ** 0.5) * 4
+    assert (Cd.cpu().double() - ref).abs().max() < tol * max(1.0, float(ref.abs().max()) / 10)
+    # split-K accumulates into C (beta must be 1)
+    Cd = dev(C0)
+    lib().call("ddfa_sgemm", ta, tb, M, N, K, 1.0, _p(Ad), A.shape[1], _p(Bd), B.shape[1], 1.0, _p(Cd), N, 7, st())
+    ref2 = opA.double() @ opB.double() + C0.double()
+    assert (Cd.cpu().double() - ref2).abs().max() < tol * max(1.0, float(ref2.abs().max()) / 10)
+    with pytest.raises(DdfaError, match="beta"):
+        lib().call("ddfa_sgemm", ta, tb, M, N, K, 1.0, _p(Ad), A.shape[1], _p(Bd), B.shape[1], 0.0, _p(Cd), N, 4, st())
+
+
+@pytest.mark.parametrize("K,H", [(4, 32), (1, 32), (4, 8), (1, 20)])
+def test_embed_concat_fwd_bwd(K, H):
+    V, N = 50, 3000
+    torch.manual_seed(K * 100 + H)
+    tables = [torch.randn(V, H) for _ in range(K)]
+    g = synth.make_batch(sizes=[N], input_dim=V, seed=K)
+    idx = [g.ndata[f"_ABS_DATAFLOW_{k}"] for k in ("api", "datatype", "literal", "operator")][:K]
+    ref = torch.cat([t[i] for t, i in zip(tables, idx)], 1)
+    td, idd = [dev(t) for t in tables], [dev(i) for i in idx]
+    x = torch.empty(N, K * H, device=DEV); oob = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lib().call("ddfa_embed_concat_fwd", ptr_array([_p(i) for i in idd]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
+    assert torch.equal(x.cpu(), ref) and int(oob) == 0
+    dx, dx2 = torch.randn(N, K * H), torch.randn(N, K * H)
+    for second in (None, dx2):
+        tot = dx + (second if second is not None else 0)
+        ref_g = [torch.zeros(V, H, dtype=torch.float64).index_add_(0, i, tot[:, k * H:(k + 1) * H].double()) for k, i in enumerate(idx)]
+        gd = [torch.zeros(V, H, device=DEV) for _ in range(K)]
+        lib().call("ddfa_embed_concat_bwd", ptr_array([_p(i) for i in idd]), _p(dev(dx)), _p(dev(second)) if second is not None else None,
+                   K, V, H, N, ptr_array([_p(t) for t in gd]), st())
+        for a, b in zip(gd, ref_g):
+            assert (a.cpu().double() - b).abs().max() < 2e-4 * max(1.0, float(b.abs().max()))
+    # out-of-range indices are clamped and counted
+    bad = [i.clone() for i in idx]; bad[0][5] = V + 3; bad[0][6] = -2
+    lib().call("ddfa_embed_concat_fwd", ptr_array([_p(dev(i)) for i in bad]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
+    assert int(oob) == 2
+
+
+def test_fold_weights_fwd_bwd():
+    D = 128
+    torch.manual_seed(5)
+    W = torch.randn(D, D, dtype=torch.float64, requires_grad=True); b = torch.randn(D, dtype=torch.float64, requires_grad=True)
+    Wih = torch.randn(3 * D, D, dtype=torch.float64, requires_grad=True)
+    wf, bf = Wih @ W, Wih @ b
+    dwf, dbf = torch.randn(3 * D, D, dtype=torch.float64), torch.randn(3 * D, dtype=torch.float64)
+    ((wf * dwf).sum() + (bf * dbf).sum()).backward()
+    Wd, bd, Wihd = dev(W.detach().float()), dev(b.detach().float()), dev(Wih.detach().float())
+    wfd, bfd = torch.empty(3 * D, D, device=DEV), torch.empty(3 * D, device=DEV)
+    lib().call("ddfa_fold_weights_fwd", _p(Wd), _p(bd), _p(Wihd), D, _p(wfd), _p(bfd), st())
+    assert (wfd.cpu().double() - wf.detach()).abs().max() < 1e-3 and (bfd.cpu().double() - bf.detach()).abs().max() < 1e-3
+    gW, gb, gWih = torch.ones(D, D, device=DEV), torch.ones(D, device=DEV), torch.ones(3 * D, D, device=DEV)   # += semantics
+    lib().call("ddfa_fold_weights_bwd", _p(Wd), _p(bd), _p(Wihd), _p(dev(dwf.float())), _p(dev(dbf.float())), D, _p(gW), _p(gb), _p(gWih), st())
+    for got, ref in ((gW, W.grad), (gb, b.grad), (gWih, Wih.grad)):
+        assert (got.cpu().double() - 1.0 - ref).abs().max() < 1e-3 * max(1.0, float(ref.abs().max()) / 10)
+
+
+def _gru_reference(s, h, deg, wf, bf, bih, whh, bhh):
+    D = h.shape[1]
+    gi = s @ wf.t() + deg[:, None] * bf[None, :] + bih
+    gh = h @ whh.t() + bhh
+    r = torch.sigmoid(gi[:, :D] + gh[:, :D]); z = torch.sigmoid(gi[:, D:2 * D] + gh[:, D:2 * D])
+    n = torch.tanh(gi[:, 2 * D:] + r * gh[:, 2 * D:])
+    return (1 - z) * n + z * h, r, z, n, gh[:, 2 * D:]
+
+
+@pytest.mark.parametrize("D", [32, 128, 256])
+def test_gru_step_fwd_bwd(D):
+    g = synth.make_batch(24, 60, seed=2, variable=True)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    torch.manual_seed(D)
+    k = 1.0 / D ** 0.5
+    mk = lambda *sh: (torch.rand(*sh, dtype=torch.float64) * 2 - 1) * k
+    wf, bf, bih, whh, bhh = mk(3 * D, D) * 1.5, mk(3 * D), mk(3 * D), mk(3 * D, D), mk(3 * D)
+    s = torch.randn(N, D, dtype=torch.float64) * 2; h = torch.tanh(torch.randn(N, D, dtype=torch.float64))
+    deg = torch.bincount(g.edges()[1], minlength=N).double()
+    leaves = [t.requires_grad_(True) for t in (s, h, wf, bf, bih, whh, bhh)]
+    h_ref, r_ref, z_ref, n_ref, ghn_ref = _gru_reference(*leaves[:2], deg, *leaves[2:])
+    dh_out = torch.randn(N, D, dtype=torch.float64)
+    (h_ref * dh_out).sum().backward()
+    f32 = [dev(t.detach().float()) for t in leaves]
+    sd, hd, wfd, bfd, bihd, whhd, bhhd = f32
+    for engine in engines_for(D):
+        L = lib()
+        wsb = max(L.call("ddfa_gru_step_workspace_bytes", N, D, engine), 4 * 2 * N * 3 * D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        h_out = torch.empty(N, D, device=DEV); gates = torch.empty(4, N, D, device=DEV)
+        L.call("ddfa_gru_step_fwd", _p(sd), _p(hd), _p(dg.indptr), _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), N, D, _p(h_out),
+               _p(gates), _p(ws), wsb, engine, st())
+        assert (h_out.cpu().double() - h_ref.detach()).abs().max() < 2e-5, f"engine {engine}"
+        for got, ref in zip(gates.cpu().double(), (r_ref, z_ref, n_ref, ghn_ref)):
+            assert (got - ref.detach()).abs().max() < 5e-5
+        # without gate saving
+        h_out2 = torch.empty(N, D, device=DEV)
+        L.call("ddfa_gru_step_fwd", _p(sd), _p(hd), _p(dg.indptr), _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), N, D, _p(h_out2),
+               None, _p(ws), wsb, engine, st())
+        assert torch.equal(h_out, h_out2)
+        # backward
+        ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
+        acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
+        L.call("ddfa_gru_step_bwd", _p(dev(dh_out.float())), _p(hd), _p(sd), _p(gates), _p(dg.indptr), _p(wfd), _p(whhd), N, D, _p(ds), _p(dh),
+               _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]), _p(ws), wsb, engine, st())
+        checks = [(ds, s.grad), (dh, h.grad), (acc["dwf"], wf.grad), (acc["dbf"], bf.grad), (acc["dbih"], bih.grad), (acc["dwhh"], whh.grad), (acc["dbhh"], bhh.grad)]
+        for got, ref in checks:
+            scale = max(1.0, float(ref.abs().max()))
+            assert (got.cpu().double() - ref).abs().max() < 2e-4 * scale, f"engine {engine}"
+    with pytest.raises(DdfaError, match="tcgen05"):
+        lib().call("ddfa_gru_step_fwd", _p(sd), _p(hd), _p(dg.indptr), _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), N, 64 if D != 64 else 32,
+                   _p(h_out), None, _p(ws), wsb, ENGINE_TCGEN05, st())
+
+
+@pytest.mark.parametrize("D,L", [(128, 3), (128, 1), (32, 2), (64, 0), (256, 2)])
+def test_readout_mlp_fwd_bwd(D, L):
+    sizes = [1, 2, 300, 40, 5, 0, 17]          # includes an EMPTY graph (pooled = 0) and a 1-node graph
+    g = synth.make_batch(sizes=[s for s in sizes if s > 0], input_dim=50, seed=D)
+    bnn = torch.tensor(sizes)
+    N, B, D2 = int(bnn.sum()), len(sizes), 2 * D
+    torch.manual_seed(D + L)
+    h = torch.randn(N, D, dtype=torch.float64, requires_grad=True); x = torch.randn(N, D, dtype=torch.float64, requires_grad=True)
+    gate = torch.nn.Linear(D2, 1).double()
+    layers = []
+    for i in range(L):
+        layers.append(torch.nn.Linear(D2, 1 if i == L - 1 else D2).double())
+        if i != L - 1:
+            layers.append(torch.nn.ReLU())
+    mlp = torch.nn.Sequential(*layers)
+
+    class _G:  # minimal graph for the oracle pooling
+        def batch_num_nodes(self):
+            return bnn
+    pool = O.GlobalAttentionPoolingRestated(gate)
+    pooled_ref = pool(_G(), torch.cat([h, x], 1))
+    out_ref = mlp(pooled_ref).squeeze(-1) if L else pooled_ref
+    dout = torch.randn_like(out_ref)
+    (out_ref * dout).sum().backward()
+
+    graph_ptr = dev(torch.cat([torch.zeros(1, dtype=torch.int64), bnn.cumsum(0)]).to(torch.int32))
+    hd, xd = dev(h.detach().float()), dev(x.detach().float())
+    wg, bg = dev(gate.weight.detach().float().reshape(-1)), dev(gate.bias.detach().float())
+    lins = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+    mw, mb = [dev(m.weight.detach().float()) for m in lins], [dev(m.bias.detach().float()) for m in lins]
+    pooled = torch.empty(B, D2, device=DEV); logits = torch.empty(B, device=DEV)
+    gl = torch.empty(N, device=DEV); smax = torch.empty(B, device=DEV); ssum = torch.empty(B, device=DEV)
+    act = torch.empty(max(L - 1, 1), B, D2, device=DEV)
+    Lb = lib()
+    Lb.call("ddfa_readout_mlp_fwd", _p(hd), _p(xd), _p(graph_ptr), B, D, _p(wg), _p(bg), ptr_array([_p(t) for t in mw]) if L else None,
+            ptr_array([_p(t) for t in mb]) if L else None, L, _p(pooled), _p(logits) if L else None, _p(gl), _p(smax), _p(ssum), _p(act), st())
+    assert (pooled.cpu().double() - pooled_ref.detach()).abs().max() < 1e-5
+    assert float(pooled[5].abs().max()) == 0.0
+    if L:
+        assert (logits.cpu().double() - out_ref.detach()).abs().max() < 2e-5
+        dpooled = torch.empty(B, D2, device=DEV); scratch = torch.empty(2, B, D2, device=DEV)
+        gw, gb = [torch.zeros_like(t) for t in mw], [torch.zeros_like(t) for t in mb]
+        Lb.call("ddfa_mlp_bwd", _p(dev(dout.float())), _p(pooled), _p(act), ptr_array([_p(t) for t in mw]), B, D, L, _p(dpooled),
+                ptr_array([_p(t) for t in gw]), ptr_array([_p(t) for t in gb]), _p(scratch), st())
+        for got, m in zip(gw, lins):
+            assert (got.cpu().double() - m.weight.grad).abs().max() < 1e-4 * max(1.0, float(m.weight.grad.abs().max()))
+        for got, m in zip(gb, lins):
+            assert (got.cpu().double() - m.bias.grad).abs().max() < 1e-4 * max(1.0, float(m.bias.grad.abs().max()))
+    else:
+        dpooled = dev(dout.float())
+    dh, dx = torch.zeros(N, D, device=DEV), torch.zeros(N, D, device=DEV)
+    dwg, dbg = torch.zeros(D2, device=DEV), torch.zeros(1, device=DEV)
+    Lb.call("ddfa_readout_bwd", _p(dpooled), _p(pooled), _p(hd), _p(xd), _p(graph_ptr), B, D, _p(wg), _p(gl), _p(smax), _p(ssum), _p(dh), _p(dx),
+            _p(dwg), _p(dbg), st())
+    assert (dh.cpu().double() - h.grad).abs().max() < 1e-4 * max(1.0, float(h.grad.abs().max()))
+    assert (dx.cpu().double() - x.grad).abs().max() < 1e-4 * max(1.0, float(x.grad.abs().max()))
+    assert (dwg.cpu().double() - gate.weight.grad.reshape(-1)).abs().max() < 2e-4 * max(1.0, float(gate.weight.grad.abs().max()))
+    assert abs(float(dbg) - float(gate.bias.grad)) < 1e-4
+
+
+@pytest.mark.parametrize("pw", [1.0, 2.5])
+def test_graph_label_bce(pw):
+    g = synth.make_batch(300, 20, seed=3, variable=True, vuln_rate=0.4)
+    dg = prepare_graph(g, DEV)
+    B = g.batch_size
+    torch.manual_seed(1)
+    logits = (torch.randn(B, dtype=torch.float64) * 4).requires_grad_(True)
+    m = O.OracleFlowGNNGGNN("_ABS_DATAFLOW", 10, 4, 1, 1, positive_weight=pw)
+    labels_ref = m.get_label(g)
+    loss_ref = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw], dtype=torch.float64))(logits, labels_ref.double())
+    loss_ref.backward()
+    labels = torch.empty(B, device=DEV); loss = torch.full((1,), 7.0, device=DEV); dl = torch.empty(B, device=DEV)
+    lib().call("ddfa_graph_label_bce", _p(dev(logits.detach().float())), _p(dev(g.ndata["_VULN"])), _p(dg.graph_ptr), B, pw, 1.0 / B, 1.0 / B,
+               _p(labels), _p(loss), _p(dl), st())
+    assert torch.equal(labels.cpu(), labels_ref) and labels_ref.sum() > 10
+    assert abs(float(loss) - float(loss_ref)) < 1e-5
+    assert (dl.cpu().double() - logits.grad).abs().max() < 1e-7
+    # labels only
+    lib().call("ddfa_graph_label_bce", None, _p(dev(g.ndata["_VULN"])), _p(dg.graph_ptr), B, 1.0, 0.0, 0.0, _p(labels), None, None, st())
+    assert torch.equal(labels.cpu(), labels_ref)
+
+
+def test_adam_flat_matches_torch_adam():
+    torch.manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-2)        # config_default.yaml:43-47
+    p, m, v = dev(p0), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for i in range(6):
+        g = torch.randn(n) * (0.1 if i % 2 else 3.0)
+        ref.grad = g.clone(); opt.step()
+        lib().call("ddfa_adam_flat", _p(p), _p(dev(g)), _p(m), _p(v), _p(step), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, st())
+    assert int(step) == 6
+    assert (p.cpu() - ref.detach()).abs().max() < 2e-6

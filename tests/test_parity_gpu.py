@@ -1,0 +1,246 @@
+"""GPU: end-to-end parity of the reference-facing module (deepdfa_b200.FlowGNNGGNNModule, which
+calls the C ABI) against the oracle — golden fixtures, live oracle on the same seeded inputs,
+gradients, optimisation steps, and the size-independent properties at BASELINE's full sizes.
+
+Bar (BASELINE.json north_star): logits within 1e-3 of the fp32 reference, identical labels
+(sign of the logit == decision at the 0.5 sigmoid threshold, base_module.py:186,364)."""
+import copy
+
+import pytest
+import torch
+
+import deepdfa_b200 as D
+from deepdfa_b200 import batched_graph as G
+from deepdfa_b200 import synth
+from oracle import ggnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FEAT = "_ABS_DATAFLOW_api_all_limitall_1000_limitsubkeys_1000"
+TOL = 1e-3
+
+
+def graph_of(case):
+    b = case["graph"]
+    return G.BatchedCFG(b["src"], b["dst"], b["batch_num_nodes"], b["ndata"])
+
+
+def module_of(case, engine):
+    torch.manual_seed(case["seed"])
+    m = D.FlowGNNGGNNModule(**case["ctor"], engine=engine)
+    for k, (s, a) in case["checksums"].items():
+        assert abs(float(m.state_dict()[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(a)), "RNG drift: regenerate goldens"
+    return m.to(DEV)
+
+
+def tc_available():
+    from deepdfa_b200._lib import ENGINE_TCGEN05, lib
+    return lib().call("ddfa_engine_available", ENGINE_TCGEN05) == 1
+
+
+def engines_of(case):
+    d = case["ctor"]["hidden_dim"] * (4 if case["ctor"]["concat_all_absdf"] else 1)
+    return ["simt", "tcgen05"] if (d == 128 and tc_available()) else ["simt"]
+
+
+@pytest.fixture(autouse=True)
+def _skip_unbuilt_engine(request):
+    engine = request.node.callspec.params.get("engine") if hasattr(request.node, "callspec") else None
+    if engine == "tcgen05" and not tc_available():
+        pytest.skip("tcgen05 engine not compiled into libddfa_b200.so")
+
+
+def assert_logits_close(got, ref64, tol=TOL):
+    got = got.detach().cpu().double().reshape(ref64.shape)
+    err = float((got - ref64).abs().max())
+    assert err <= tol, f"max |dlogit| = {err:.3e} > {tol}"
+    if ref64.dim() == 1:
+        decisive = ref64.abs() > 10 * max(err, 1e-7)
+        assert torch.equal((got > 0)[decisive], (ref64 > 0)[decisive])
+    return err
+
+
+def test_golden_forward_both_engines(golden):
+    worst = {}
+    for case in golden["cases"]:
+        g = graph_of(case)
+        for engine in engines_of(case):
+            m = module_of(case, engine)
+            with torch.no_grad():
+                out = m(g.to(DEV), {})
+            assert out.shape == case["out_fp64"].shape
+            err = assert_logits_close(out, case["out_fp64"])
+            worst[engine] = max(worst.get(engine, 0.0), err)
+            labels = m.get_label(g.to(DEV))
+            assert torch.equal(labels.cpu(), case["labels"])
+    print("worst |dlogit| vs fp64 oracle per engine:", worst)
+    assert worst["simt"] < 5e-5          # fp32 FFMA engine sits at the fp32 noise floor
+
+
+def test_golden_gradients(golden):
+    for case in golden["cases"]:
+        if "grad_norm_fp64" not in case:
+            continue
+        g = graph_of(case).to(DEV)
+        for engine in engines_of(case):
+            m = module_of(case, engine)
+            loss = m.training_step((g, {}), 0)
+            assert abs(float(loss) - case["loss_fp64"]) < 1e-5
+            loss.backward()
+            for name, p in m.named_parameters():
+                ref_norm = case["grad_norm_fp64"][name]
+                got_norm = float(p.grad.double().norm())
+                assert abs(got_norm - ref_norm) <= 2e-3 * max(ref_norm, 1e-4) + 1e-7, (case["name"], engine, name, got_norm, ref_norm)
+                if case.get("grads_fp64"):
+                    ref = case["grads_fp64"][name]
+                    assert (p.grad.cpu().double() - ref).abs().max() <= 1e-4 * max(1.0, float(ref.abs().max())) + 1e-7, (case["name"], name)
+
+
+def test_encoder_mode_backward_through_pooled(golden):
+    case = next(c for c in golden["cases"] if c["name"] == "tiny_encoder_T2")
+    g = graph_of(case)
+    torch.manual_seed(case["seed"])
+    o = O.OracleFlowGNNGGNN(**case["ctor"]).double()
+    m = module_of(case, "simt")
+    w = torch.randn(g.batch_size, m.out_dim, dtype=torch.float64)
+    (o(g) * w).sum().backward()
+    out = m(g.to(DEV), {})
+    assert out.shape == (g.batch_size, m.out_dim)
+    (out * w.float().to(DEV)).sum().backward()
+    for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
+        assert (p.grad.cpu().double() - q.grad).abs().max() <= 1e-4 * max(1.0, float(q.grad.abs().max())) + 1e-7, name
+
+
+def test_tiny_adam_steps_autograd_path_and_fused_trainer(golden):
+    case = next(c for c in golden["cases"] if c["name"] == "tiny_T3_L2")
+    g = graph_of(case).to(DEV)
+    # (a) reference-style loop: module.training_step + stock torch Adam (config_default.yaml:43-47)
+    m = module_of(case, "simt")
+    opt = m.configure_optimizers()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = m.training_step((g, {}), 0)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses == pytest.approx(case["adam_losses"], abs=2e-5)
+    for k, v in case["state_after_adam"].items():
+        assert (m.state_dict()[k].cpu() - v).abs().max() < 2e-5, k
+    # (b) fused trainer: flat buffers + ddfa_adam_flat
+    m2 = module_of(case, "simt")
+    tr = D.FusedTrainer(m2)
+    losses2 = [float(tr.step(g)) for _ in range(3)]
+    assert losses2 == pytest.approx(case["adam_losses"], abs=2e-5)
+    for k, v in case["state_after_adam"].items():
+        assert (m2.state_dict()[k].cpu() - v).abs().max() < 2e-5, k
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("T,L", [(8, 2), (5, 3)])
+def test_full_size_c0_against_live_oracle(engine, T, L):
+    """BASELINE config 1/2: 256 CFGs x 150 nodes / 300 edges, 128-d, T steps — logits vs the CPU oracle."""
+    g = synth.make_batch(256, 150, seed=0)
+    torch.manual_seed(0)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, T, L, concat_all_absdf=True)
+    for p in o.parameters():           # trained-scale weights (SURVEY.md §7 hard part 1): x2
+        p.data.mul_(2.0)
+    with torch.no_grad():
+        ref = o(g).double()
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, T, L, concat_all_absdf=True, engine=engine)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV)
+    with torch.no_grad():
+        out = m(g, {})                  # CPU graph: moved to the module's device by the module
+    err = assert_logits_close(out, ref)
+    print(f"C0 T={T} L={L} engine={engine}: max|dlogit|={err:.2e}, |logit| range {float(ref.abs().max()):.2f}")
+    assert torch.equal(m.get_label(g).cpu(), o.get_label(g))
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_full_size_gradients_against_live_oracle(engine):
+    g = synth.make_batch(64, 150, seed=5, variable=True, vuln_rate=0.3)
+    torch.manual_seed(1)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, positive_weight=4.0)
+    loss_ref, _ = o.training_loss(g)
+    loss_ref.backward()
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, positive_weight=4.0, engine=engine)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV)
+    loss = m.training_step((g.to(DEV), {}), 0)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-4
+    for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
+        ref = q.grad
+        scale = max(float(ref.abs().max()), 1e-6)
+        rel = float((p.grad.cpu() - ref).abs().max()) / scale
+        assert rel < (2e-3 if engine == "simt" else 2e-2), (name, rel)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_properties_at_c1_size(engine):
+    """Batch 1024 (BASELINE config 3 shape): determinism, batch-composition invariance (graphs never
+    exchange messages), and sharding over 2 'ranks' reproducing the unsharded logits."""
+    g = synth.make_batch(1024, 150, seed=7, variable=True)
+    torch.manual_seed(3)
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, engine=engine).to(DEV)
+    with torch.no_grad():
+        a = m(g.to(DEV), {})
+        b = m(g.to(DEV), {})
+        assert torch.equal(a, b)
+        parts = G.split_batch(g, 2)
+        pa = torch.cat([m(p.to(DEV), {}) for p in parts])
+    assert (a - pa).abs().max() < 1e-5
+    assert a.shape == (1024,) and torch.isfinite(a).all()
+
+
+def test_single_graph_squeeze_and_duck_typed_dgl_graph():
+    m = D.FlowGNNGGNNModule(FEAT, 60, 8, 3, 2, concat_all_absdf=True).to(DEV)
+    g = synth.make_batch(sizes=[9], input_dim=60, seed=1)
+    out = m(g.to(DEV), {})
+    assert out.dim() == 0                          # logits.squeeze() (ggnn.py:107)
+
+    class FakeDGL:                                  # anything exposing the DGL subset is accepted
+        def __init__(self, g):
+            self._g, self.ndata = g, g.ndata
+        def edges(self):
+            return self._g.edges()
+        def batch_num_nodes(self):
+            return self._g.batch_num_nodes()
+    g3 = synth.make_batch(sizes=[4, 9, 2], input_dim=60, seed=2)
+    with torch.no_grad():
+        assert torch.equal(m(FakeDGL(g3), {}), m(g3, {}))
+
+
+def test_index_validation_raises():
+    m = D.FlowGNNGGNNModule(FEAT, 60, 8, 2, 1, concat_all_absdf=True).to(DEV)
+    m.validate_inputs = True
+    g = synth.make_batch(sizes=[6, 3], input_dim=60, seed=1)
+    g.ndata["_ABS_DATAFLOW_api"][2] = 60
+    with pytest.raises(IndexError):
+        m(g, {})
+
+
+def test_fused_trainer_tracks_oracle_training():
+    """Config-3 style check at reduced size: 10 optimisation steps on a stream of batches; the loss
+    curve and the final decisions follow the oracle trained on the identical stream."""
+    torch.manual_seed(0)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, positive_weight=8.0)
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, positive_weight=8.0, engine="simt")
+    m.load_state_dict(copy.deepcopy(o.state_dict()))
+    m.to(DEV)
+    tr = D.FusedTrainer(m)
+    opt = O.make_optimizer(o)
+    batches = [synth.make_batch(32, 60, seed=50 + i, variable=True, vuln_rate=0.3) for i in range(5)]
+    for step in range(10):
+        b = batches[step % 5]
+        opt.zero_grad()
+        loss_ref, _ = o.training_loss(b)
+        loss_ref.backward()
+        opt.step()
+        loss = float(tr.step(b))
+        assert abs(loss - float(loss_ref)) < 2e-3 * max(1.0, abs(float(loss_ref))), (step, loss, float(loss_ref))
+    with torch.no_grad():
+        ref = o(batches[0]).double()
+        out = m(batches[0], {})
+    assert (out.cpu().double() - ref).abs().max() < 5e-3
