@@ -254,7 +254,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also builds + caches the device CSR of every resident batch) -------------------
-    for i in range(max(args.warmup, 3)):
+    min_warm = int(os.environ.get("DDFA_BENCH_MIN_WARMUP", "3"))   # 1 only for profiler runs (never a bench value)
+    for i in range(max(args.warmup, min_warm)):
         trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
     torch.cuda.synchronize()
     l0 = L.call("ddfa_launch_count")
@@ -339,7 +340,10 @@ def run_ours(args):
     gru["frac_fwd"] = gru["fwd_achieved"] / gru["peak"]
 
     # ---- cpu baseline on this box's host cores (bounded sample) ----------------------------------------
-    cpu_val, cpu_s, cpu_done, cpu_threads = cpu_train_steps(args.graphs, 12, 2, budget_s=20.0)
+    if os.environ.get("DDFA_BENCH_SKIP_CPU") == "1":     # profiler runs only
+        cpu_val, cpu_s, cpu_done, cpu_threads = None, None, 0, 0
+    else:
+        cpu_val, cpu_s, cpu_done, cpu_threads = cpu_train_steps(args.graphs, 12, 2, budget_s=20.0)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
