@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ddfa_fold_weights_fwd": (_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "ddfa_fold_weights_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ddfa_gru_step_workspace_bytes": (_sz, [_i32, _i32, _int]),
+    "ddfa_gru_step_prepare": (_int, [_vp] * 5 + [_i32, _int, _vp, _sz, _vp]),
     "ddfa_gru_step_fwd": (_int, [_vp] * 8 + [_i32, _i32, _vp, _vp, _vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd": (_int, [_vp] * 7 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_readout_mlp_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32] + [_vp] * 6 + [_vp]),

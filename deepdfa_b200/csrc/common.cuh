@@ -50,6 +50,8 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
 // gru_tc.cu — tcgen05 engine entry points (D == 128)
 bool gru_tc_available();
 size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
+int gru_tc_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, int32_t D,
+                   void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
                     const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,
                     float *save_gates, void *workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -210,6 +210,16 @@ static int check_step_args(const char *who, int32_t N, int32_t D, int engine) {
   return DDFA_OK;
 }
 
+int ddfa_gru_step_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
+                          int32_t D, int engine, void *workspace, size_t workspace_bytes, void *stream_) {
+  using namespace ddfa;
+  int rc = check_step_args("ddfa_gru_step_prepare", 0, D, engine);
+  if (rc) return rc;
+  if (engine == DDFA_ENGINE_SIMT) return DDFA_OK;  // nothing to pre-pack
+  DDFA_REQUIRE(w_fold && b_fold && b_ih && w_hh && b_hh, "ddfa_gru_step_prepare: NULL pointer");
+  return gru_tc_prepare(w_fold, b_fold, b_ih, w_hh, b_hh, D, workspace, workspace_bytes, as_stream(stream_));
+}
+
 int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
                       const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,
                       float *save_gates, void *workspace, size_t workspace_bytes, int engine, void *stream_) {

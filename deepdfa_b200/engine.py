@@ -231,6 +231,8 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
 
     ws_bytes = L.call("ddfa_gru_step_workspace_bytes", N, D, engine)
     ws = alloc.get("gru_ws", (max(ws_bytes, 16),), torch.uint8)
+    L.call("ddfa_gru_step_prepare", _p(w_fold), _p(b_fold), _p(params.b_ih), _p(params.w_hh), _p(params.b_hh), D, engine,
+           _p(ws), ws_bytes, st)
     hs, ss, gs = [x], [], []
     h_cur = x
     for t in range(T):

@@ -117,6 +117,12 @@ int ddfa_fold_weights_bwd(const float *w_msg, const float *b_msg, const float *w
  * workspace: engine-dependent scratch (ddfa_gru_step_workspace_bytes).
  * ------------------------------------------------------------------------------------- */
 size_t ddfa_gru_step_workspace_bytes(int32_t num_nodes, int32_t dim, int engine);
+/* Once per forward (weights are constant over the T steps): engine-specific pre-packing of the
+ * step's weights into `workspace` (tcgen05: bf16 hi/lo split, UMMA swizzled smem images; SIMT:
+ * no-op).  The same workspace must then be passed to every ddfa_gru_step_fwd of that forward. */
+int ddfa_gru_step_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
+                          const float *w_hh, const float *b_hh, int32_t dim, int engine,
+                          void *workspace, size_t workspace_bytes, void *stream);
 int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold,
                       const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                       int32_t num_nodes, int32_t dim, float *h_out, float *save_gates,
