@@ -45,6 +45,7 @@ _SIGNATURES = {
     "ddfa_embed_concat_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "ddfa_embed_concat_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _int, _vp]),
+    "ddfa_gather_sum_variant": (_int, [_int, _vp, _vp, _vp, _i32, _i32, _vp, _int, _vp]),
     "ddfa_fold_weights_fwd": (_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "ddfa_fold_weights_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ddfa_gru_step_workspace_bytes": (_sz, [_i32, _i32, _int]),

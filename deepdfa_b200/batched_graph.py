@@ -29,7 +29,7 @@ class BatchedCFG:
 
     def __init__(self, src: torch.Tensor, dst: torch.Tensor, batch_num_nodes: torch.Tensor,
                  ndata: Optional[Dict[str, torch.Tensor]] = None,
-                 batch_num_edges: Optional[torch.Tensor] = None):
+                 batch_num_edges: Optional[torch.Tensor] = None, num_nodes: Optional[int] = None):
         if src.shape != dst.shape or src.dim() != 1:
             raise ValueError("src and dst must be 1-D tensors of equal length")
         self._src = src
@@ -37,7 +37,12 @@ class BatchedCFG:
         self._bnn = batch_num_nodes.to(torch.int64)
         self._bne = batch_num_edges
         self.ndata: Dict[str, torch.Tensor] = dict(ndata or {})
-        self._n = int(self._bnn.sum().item()) if self._bnn.numel() else 0
+        if num_nodes is not None:
+            self._n = int(num_nodes)              # known by the caller: no reduction (and no device sync)
+        elif self._bnn.is_cuda and self.ndata:
+            self._n = int(next(iter(self.ndata.values())).shape[0])   # avoid a device reduction + sync
+        else:
+            self._n = int(self._bnn.sum().item()) if self._bnn.numel() else 0
         for k, v in self.ndata.items():
             if v.shape[0] != self._n:
                 raise ValueError(f"ndata[{k!r}] has {v.shape[0]} rows, graph has {self._n} nodes")
@@ -91,14 +96,14 @@ class BatchedCFG:
             self._bnn.to(device, non_blocking=non_blocking),
             {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()},
             None if self._bne is None else self._bne.to(device, non_blocking=non_blocking),
+            num_nodes=self._n,
         )
-        g._n = self._n
         return g
 
     def pin_memory(self) -> "BatchedCFG":
         g = BatchedCFG(self._src.pin_memory(), self._dst.pin_memory(), self._bnn.pin_memory(),
                        {k: v.pin_memory() for k, v in self.ndata.items()},
-                       None if self._bne is None else self._bne.pin_memory())
+                       None if self._bne is None else self._bne.pin_memory(), num_nodes=self._n)
         return g
 
     def __repr__(self):

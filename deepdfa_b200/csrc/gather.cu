@@ -7,61 +7,81 @@
 // Bound: HBM bandwidth (zero FLOPs).  Algorithmic bytes per launch:
 //     E*D*4 (source rows) + N*D*4 (write) + E*4 (indices) + (N+1)*4 (indptr)
 //
-// Mapping: a group of G = min(32, D/4) lanes owns RW consecutive destination rows; one lane
+// Mapping: a group of G = min(32, D/4) lanes owns RW*PASSES consecutive destination rows; one lane
 // holds one 16-byte column chunk, so a D=128 fp32 row (512 B) is exactly one warp-wide
-// ld.global.nc.v4.  Per group: one coalesced load of the RW+1 row pointers, one coalesced load
-// of the (<=32 per pass) neighbour ids, then the neighbour-row loads are issued in batches of
-// UNROLL independent 128-bit loads (memory-level parallelism) and folded into the per-row
-// accumulators by a uniform segmented reduction (row boundaries broadcast with shuffles).
+// ld.global.nc.v4.  The kernel is latency-bound (ncu r01a: long-scoreboard stalls dominate: the
+// chain indptr -> indices -> rows is three dependent DRAM/L2 round trips), so the index side is
+// hoisted: ONE coalesced load fetches all RW*PASSES+1 row pointers of the group, then up to
+// NIDX*G neighbour ids are prefetched into registers, and only then the row phase starts: the
+// neighbour rows are fetched in batches of UNROLL independent 128-bit loads (memory-level
+// parallelism) and folded into per-row accumulators by a warp-uniform segmented reduction (row
+// boundaries broadcast with shuffles), RW rows per pass.  No atomics; neighbour lists are sorted,
+// so the fp32 summation order — and the result — is deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ddfa {
 
-template <int G, int CH, int RW, int UNROLL>
-__global__ void __launch_bounds__(256) gather_sum_kernel(const int32_t *__restrict__ indptr,
-                                                         const int32_t *__restrict__ indices,
-                                                         const float *__restrict__ h, int32_t N, int32_t D,
-                                                         float *__restrict__ out, int accumulate) {
+template <int G, int CH, int RW, int UNROLL, int PASSES, int NIDX, int THREADS>
+__global__ void __launch_bounds__(THREADS) gather_sum_kernel(const int32_t *__restrict__ indptr,
+                                                             const int32_t *__restrict__ indices,
+                                                             const float *__restrict__ h, int32_t N, int32_t D,
+                                                             float *__restrict__ out, int accumulate) {
   constexpr int GROUPS_PER_WARP = 32 / G;
+  constexpr int ROWS = RW * PASSES;
+  static_assert(ROWS + 1 <= G, "row pointers of a group must fit its lanes");
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;                 // lane inside the group
   const int gbase = lane - gl;             // first lane of the group inside the warp
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t group = warp_global * GROUPS_PER_WARP + (lane / G);
-  const int64_t v0 = group * RW;
+  const int64_t v0 = group * ROWS;
   if (v0 >= N) return;
-  const int nrows = (int)min((int64_t)RW, (int64_t)N - v0);
+  const int nrows = (int)min((int64_t)ROWS, (int64_t)N - v0);
 
-  // row pointers of this chunk: lane i holds indptr[v0+i], i <= nrows
+  // row pointers of the whole group: lane i holds indptr[v0+i], i <= nrows
   int32_t myptr = 0;
   if (gl <= nrows) myptr = __ldg(indptr + v0 + gl);
   const int32_t beg0 = __shfl_sync(gmask, myptr, gbase);
-  int32_t rend[RW];  // row end offsets relative to beg0
+  const int32_t total = __shfl_sync(gmask, myptr, gbase + nrows) - beg0;
+  // prefetch the first NIDX*G neighbour ids of the group (coalesced)
+  int32_t pre[NIDX];
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    int32_t e = __shfl_sync(gmask, myptr, gbase + min(r + 1, nrows));
-    rend[r] = e - beg0;
-  }
-  const int32_t total = rend[RW - 1];
+  for (int b = 0; b < NIDX; ++b) pre[b] = (b * G + gl < total) ? __ldg(indices + beg0 + b * G + gl) : 0;
 
-  float4 acc[RW][CH];
+#pragma unroll 1
+  for (int p = 0; p < PASSES; ++p) {
+    const int r0 = p * RW;
+    if (r0 >= nrows) break;
+    int32_t rend[RW];  // row end offsets (relative to beg0) of this pass's rows
 #pragma unroll
-  for (int r = 0; r < RW; ++r)
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < RW; ++r) rend[r] = __shfl_sync(gmask, myptr, gbase + min(r0 + r + 1, nrows)) - beg0;
+    const int32_t pbeg = __shfl_sync(gmask, myptr, gbase + r0) - beg0;
+    const int32_t pend = rend[RW - 1];
 
-  for (int32_t pbase = 0; pbase < total; pbase += G) {
-    // coalesced load of up to G neighbour ids of this chunk
-    int32_t myidx = 0;
-    if (pbase + gl < total) myidx = __ldg(indices + beg0 + pbase + gl);
-    const int32_t cnt = min((int32_t)G, total - pbase);
-    for (int32_t b = 0; b < cnt; b += UNROLL) {
+    float4 acc[RW][CH];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int32_t b = pbeg; b < pend; b += UNROLL) {
       float4 v[UNROLL][CH];
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
-        const int32_t u = __shfl_sync(gmask, myidx, gbase + min(b + j, cnt - 1));
-        if (b + j < cnt) {
+        const int32_t pos = min(b + j, pend - 1);  // clamp: every lane runs the shuffles
+        const int blk = pos / G, l = pos - blk * G;
+        int32_t u = 0;
+        bool found = false;
+#pragma unroll
+        for (int q = 0; q < NIDX; ++q) {
+          const int32_t t = __shfl_sync(gmask, pre[q], gbase + l);
+          if (blk == q) { u = t; found = true; }
+        }
+        if (!found) u = __ldg(indices + beg0 + pos);  // very long neighbour lists: direct (uniform) load
+        if (b + j < pend) {
           const float *row = h + (int64_t)u * D;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
@@ -75,11 +95,11 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(const int32_t *__restri
       }
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
-        const int32_t pos = pbase + b + j;  // position inside the chunk's edge list
+        const int32_t pos = b + j;
         // uniform (per group) segmented accumulate: edge `pos` belongs to the first row with rend > pos
 #pragma unroll
         for (int r = 0; r < RW; ++r) {
-          const bool mine = (pos < rend[r]) && (r == 0 || pos >= rend[r - 1]);
+          const bool mine = (pos < rend[r]) && (r == 0 ? true : pos >= rend[r - 1]);
           if (mine) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) f4_add(acc[r][c], v[j][c]);
@@ -87,54 +107,104 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(const int32_t *__restri
         }
       }
     }
-  }
 
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    if (r < nrows) {
-      float *orow = out + (v0 + r) * D;
+    for (int r = 0; r < RW; ++r) {
+      if (r0 + r < nrows) {
+        float *orow = out + (v0 + r0 + r) * D;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int col = (gl + c * G) * 4;
-        if (col < D) {
-          float4 a = acc[r][c];
-          if (accumulate) f4_add(a, *reinterpret_cast<const float4 *>(orow + col));
-          *reinterpret_cast<float4 *>(orow + col) = a;
+        for (int c = 0; c < CH; ++c) {
+          const int col = (gl + c * G) * 4;
+          if (col < D) {
+            float4 a = acc[r][c];
+            if (accumulate) f4_add(a, *reinterpret_cast<const float4 *>(orow + col));
+            *reinterpret_cast<float4 *>(orow + col) = a;
+          }
         }
       }
     }
   }
 }
 
-template <int G, int CH, int RW, int UNROLL>
+template <int G, int CH, int RW, int UNROLL, int PASSES, int NIDX, int THREADS>
 static int launch_gather(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, int32_t D,
                          float *out, int accumulate, cudaStream_t stream) {
   constexpr int GROUPS_PER_WARP = 32 / G;
-  const int64_t groups = ((int64_t)N + RW - 1) / RW;
+  constexpr int ROWS = RW * PASSES;
+  const int64_t groups = ((int64_t)N + ROWS - 1) / ROWS;
   const int64_t warps = (groups + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;
-  const int threads = 256;
-  const int64_t blocks = (warps * 32 + threads - 1) / threads;
-  gather_sum_kernel<G, CH, RW, UNROLL><<<(unsigned)blocks, threads, 0, stream>>>(indptr, indices, h, N, D, out, accumulate);
+  const int64_t blocks = (warps * 32 + THREADS - 1) / THREADS;
+  gather_sum_kernel<G, CH, RW, UNROLL, PASSES, NIDX, THREADS><<<(unsigned)blocks, THREADS, 0, stream>>>(indptr, indices, h, N, D, out, accumulate);
   DDFA_CHECK_LAUNCH("gather_sum_kernel");
   return DDFA_OK;
 }
 
-}  // namespace ddfa
+// Tuning variants for the D=128 case (selected by ddfa_gather_sum_variant / $DDFA_GATHER_VARIANT):
+//   id : RW UNROLL PASSES NIDX THREADS
+static int launch_d128_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,
+                               float *out, int accumulate, cudaStream_t stream) {
+  switch (variant) {
+    case 0: return launch_gather<32, 1, 4, 8, 1, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 1: return launch_gather<32, 1, 4, 8, 2, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 2: return launch_gather<32, 1, 4, 8, 4, 2, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 3: return launch_gather<32, 1, 4, 8, 4, 2, 128>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 4: return launch_gather<32, 1, 2, 4, 4, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 5: return launch_gather<32, 1, 2, 4, 8, 2, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 6: return launch_gather<32, 1, 2, 8, 4, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 7: return launch_gather<32, 1, 1, 4, 8, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 8: return launch_gather<32, 1, 4, 4, 2, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 9: return launch_gather<32, 1, 2, 4, 2, 1, 128>(indptr, indices, h, N, 128, out, accumulate, stream);
+    default:
+      set_error("ddfa_gather_sum_variant: unknown variant %d (0..9)", variant);
+      return DDFA_ERR_INVALID_ARG;
+  }
+}
 
-extern "C" int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,
-                               int32_t D, float *out, int accumulate, void *stream_) {
-  using namespace ddfa;
+static int default_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("DDFA_GATHER_VARIANT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+static int check_gather_args(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, int32_t D, float *out) {
   DDFA_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && D <= 1024, "ddfa_gather_sum: unsupported shape N=%d D=%d (need D%%4==0, D<=1024)", N, D);
   if (N == 0) return DDFA_OK;
   DDFA_REQUIRE(indptr && indices && h && out, "ddfa_gather_sum: NULL pointer");
   DDFA_REQUIRE(aligned16(h) && aligned16(out), "ddfa_gather_sum: h/out must be 16-byte aligned");
   DDFA_REQUIRE(h != out, "ddfa_gather_sum: in-place gather is not supported");
+  return DDFA_OK;
+}
+
+}  // namespace ddfa
+
+extern "C" {
+
+int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, int32_t D, float *out,
+                    int accumulate, void *stream_) {
+  using namespace ddfa;
+  int rc = check_gather_args(indptr, indices, h, N, D, out);
+  if (rc || N == 0) return rc;
   cudaStream_t stream = as_stream(stream_);
   const int chunks = D / 4;  // 16-byte chunks per row
-  if (chunks <= 8) return launch_gather<8, 1, 4, 8>(indptr, indices, h, N, D, out, accumulate, stream);
-  if (chunks <= 16) return launch_gather<16, 1, 4, 8>(indptr, indices, h, N, D, out, accumulate, stream);
-  if (chunks <= 32) return launch_gather<32, 1, 4, 8>(indptr, indices, h, N, D, out, accumulate, stream);
-  if (chunks <= 64) return launch_gather<32, 2, 2, 8>(indptr, indices, h, N, D, out, accumulate, stream);
-  if (chunks <= 128) return launch_gather<32, 4, 2, 4>(indptr, indices, h, N, D, out, accumulate, stream);
-  return launch_gather<32, 8, 1, 4>(indptr, indices, h, N, D, out, accumulate, stream);
+  if (D == 128) return launch_d128_variant(default_variant(), indptr, indices, h, N, out, accumulate, stream);
+  if (chunks <= 8) return launch_gather<8, 1, 4, 8, 1, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+  if (chunks <= 16) return launch_gather<16, 1, 4, 8, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+  if (chunks <= 32) return launch_gather<32, 1, 4, 8, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+  if (chunks <= 64) return launch_gather<32, 2, 2, 8, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+  if (chunks <= 128) return launch_gather<32, 4, 2, 4, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+  return launch_gather<32, 8, 1, 4, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
 }
+
+int ddfa_gather_sum_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,
+                            int32_t D, float *out, int accumulate, void *stream_) {
+  using namespace ddfa;
+  int rc = check_gather_args(indptr, indices, h, N, D, out);
+  if (rc || N == 0) return rc;
+  DDFA_REQUIRE(D == 128, "ddfa_gather_sum_variant: tuning variants exist for D == 128 only (got %d)", D);
+  return launch_d128_variant(variant, indptr, indices, h, N, out, accumulate, as_stream(stream_));
+}
+
+}  // extern "C"

@@ -58,7 +58,7 @@ class FusedTrainer:
         self.loss_slot = self.flat_g[total:total + 1]
         self.ws = E.Workspace(self.device)
         self._graphs = {}
-        self.launches_per_step = None
+        self._warm_shapes = set()
 
     # ------------------------------------------------------------------------------------
     def _enqueue(self, g, dg, idx, vuln, global_batch: int):
@@ -93,22 +93,20 @@ class FusedTrainer:
         if global_batch is None:
             global_batch = dg.batch_size * self.world
         with torch.cuda.device(self.device):
-            if not self.use_cuda_graph:
+            shape_key = (dg.num_nodes, dg.num_edges, dg.batch_size)
+            if not self.use_cuda_graph or shape_key not in self._warm_shapes:
+                # eager step; also the warm-up (workspace growth, lazy CUDA module init) before any capture
                 self._enqueue(g, dg, idx, vuln, global_batch)
+                self._warm_shapes.add(shape_key)
             else:
-                key = id(g)
-                graph = self._graphs.get(key)
-                if graph is None:
-                    # warm the workspace outside capture, then capture this batch's step
-                    self._enqueue(g, dg, idx, vuln, global_batch)
+                # one captured CUDA graph per resident batch object (its device pointers are baked in)
+                entry = self._graphs.get(id(g))
+                if entry is None:
                     torch.cuda.synchronize(self.device)
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
                         self._enqueue(g, dg, idx, vuln, global_batch)
-                    self._graphs[key] = (graph, g)
-                else:
-                    graph = graph[0]
-                if isinstance(graph, tuple):
-                    graph = graph[0]
-                graph.replay()
+                    entry = (cg, g, idx, vuln)     # keep the captured tensors alive
+                    self._graphs[id(g)] = entry
+                entry[0].replay()
         return self.loss_slot

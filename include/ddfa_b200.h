@@ -95,6 +95,9 @@ int ddfa_embed_concat_bwd(const int64_t *const *idx, const float *dx, const floa
  * ------------------------------------------------------------------------------------- */
 int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *h,
                     int32_t num_nodes, int32_t dim, float *out, int accumulate, void *stream);
+/* Tuning entry (scripts/gather_bench.py): same contract, explicit launch-shape variant (D == 128). */
+int ddfa_gather_sum_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h,
+                            int32_t num_nodes, int32_t dim, float *out, int accumulate, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Weight folding (done once per forward): w_fold = W_ih @ W  [3D,D], b_fold = W_ih @ b [3D]

@@ -17,6 +17,20 @@ def dev(t):
     return t.to(DEV).contiguous()
 
 
+_KEEP = []
+
+
+def dk(t):
+    """dev() for tensors passed inline as pointers: keeps the device tensor alive so two temporaries in one call
+    can never alias through the caching allocator."""
+    x = dev(t)
+    _KEEP.append(x)
+    if len(_KEEP) > 64:
+        torch.cuda.synchronize()
+        del _KEEP[:32]
+    return x
+
+
 def st():
     return _stream_ptr()
 
@@ -149,17 +163,18 @@ def test_embed_concat_fwd_bwd(K, H):
     lib().call("ddfa_embed_concat_fwd", ptr_array([_p(i) for i in idd]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
     assert torch.equal(x.cpu(), ref) and int(oob) == 0
     dx, dx2 = torch.randn(N, K * H), torch.randn(N, K * H)
+    dx_d, dx2_d = dev(dx), dev(dx2)          # keep the device tensors alive across the call (no aliasing temporaries)
     for second in (None, dx2):
         tot = dx + (second if second is not None else 0)
         ref_g = [torch.zeros(V, H, dtype=torch.float64).index_add_(0, i, tot[:, k * H:(k + 1) * H].double()) for k, i in enumerate(idx)]
         gd = [torch.zeros(V, H, device=DEV) for _ in range(K)]
-        lib().call("ddfa_embed_concat_bwd", ptr_array([_p(i) for i in idd]), _p(dev(dx)), _p(dev(second)) if second is not None else None,
+        lib().call("ddfa_embed_concat_bwd", ptr_array([_p(i) for i in idd]), _p(dx_d), _p(dx2_d) if second is not None else None,
                    K, V, H, N, ptr_array([_p(t) for t in gd]), st())
         for a, b in zip(gd, ref_g):
             assert (a.cpu().double() - b).abs().max() < 2e-4 * max(1.0, float(b.abs().max()))
     # out-of-range indices are clamped and counted
     bad = [i.clone() for i in idx]; bad[0][5] = V + 3; bad[0][6] = -2
-    lib().call("ddfa_embed_concat_fwd", ptr_array([_p(dev(i)) for i in bad]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
+    lib().call("ddfa_embed_concat_fwd", ptr_array([_p(dk(i)) for i in bad]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
     assert int(oob) == 2
 
 
@@ -176,7 +191,7 @@ def test_fold_weights_fwd_bwd():
     lib().call("ddfa_fold_weights_fwd", _p(Wd), _p(bd), _p(Wihd), D, _p(wfd), _p(bfd), st())
     assert (wfd.cpu().double() - wf.detach()).abs().max() < 1e-3 and (bfd.cpu().double() - bf.detach()).abs().max() < 1e-3
     gW, gb, gWih = torch.ones(D, D, device=DEV), torch.ones(D, device=DEV), torch.ones(3 * D, D, device=DEV)   # += semantics
-    lib().call("ddfa_fold_weights_bwd", _p(Wd), _p(bd), _p(Wihd), _p(dev(dwf.float())), _p(dev(dbf.float())), D, _p(gW), _p(gb), _p(gWih), st())
+    lib().call("ddfa_fold_weights_bwd", _p(Wd), _p(bd), _p(Wihd), _p(dk(dwf.float())), _p(dk(dbf.float())), D, _p(gW), _p(gb), _p(gWih), st())
     for got, ref in ((gW, W.grad), (gb, b.grad), (gWih, Wih.grad)):
         assert (got.cpu().double() - 1.0 - ref).abs().max() < 1e-3 * max(1.0, float(ref.abs().max()) / 10)
 
@@ -225,7 +240,7 @@ def test_gru_step_fwd_bwd(D):
         # backward
         ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
         acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
-        L.call("ddfa_gru_step_bwd", _p(dev(dh_out.float())), _p(hd), _p(sd), _p(gates), _p(dg.indptr), _p(wfd), _p(whhd), N, D, _p(ds), _p(dh),
+        L.call("ddfa_gru_step_bwd", _p(dk(dh_out.float())), _p(hd), _p(sd), _p(gates), _p(dg.indptr), _p(wfd), _p(whhd), N, D, _p(ds), _p(dh),
                _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]), _p(ws), wsb, engine, st())
         checks = [(ds, s.grad), (dh, h.grad), (acc["dwf"], wf.grad), (acc["dbf"], bf.grad), (acc["dbih"], bih.grad), (acc["dwhh"], whh.grad), (acc["dbhh"], bhh.grad)]
         for got, ref in checks:
@@ -278,7 +293,7 @@ def test_readout_mlp_fwd_bwd(D, L):
         assert (logits.cpu().double() - out_ref.detach()).abs().max() < 2e-5
         dpooled = torch.empty(B, D2, device=DEV); scratch = torch.empty(2, B, D2, device=DEV)
         gw, gb = [torch.zeros_like(t) for t in mw], [torch.zeros_like(t) for t in mb]
-        Lb.call("ddfa_mlp_bwd", _p(dev(dout.float())), _p(pooled), _p(act), ptr_array([_p(t) for t in mw]), B, D, L, _p(dpooled),
+        Lb.call("ddfa_mlp_bwd", _p(dk(dout.float())), _p(pooled), _p(act), ptr_array([_p(t) for t in mw]), B, D, L, _p(dpooled),
                 ptr_array([_p(t) for t in gw]), ptr_array([_p(t) for t in gb]), _p(scratch), st())
         for got, m in zip(gw, lins):
             assert (got.cpu().double() - m.weight.grad).abs().max() < 1e-4 * max(1.0, float(m.weight.grad.abs().max()))
@@ -308,13 +323,13 @@ def test_graph_label_bce(pw):
     loss_ref = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw], dtype=torch.float64))(logits, labels_ref.double())
     loss_ref.backward()
     labels = torch.empty(B, device=DEV); loss = torch.full((1,), 7.0, device=DEV); dl = torch.empty(B, device=DEV)
-    lib().call("ddfa_graph_label_bce", _p(dev(logits.detach().float())), _p(dev(g.ndata["_VULN"])), _p(dg.graph_ptr), B, pw, 1.0 / B, 1.0 / B,
+    lib().call("ddfa_graph_label_bce", _p(dk(logits.detach().float())), _p(dk(g.ndata["_VULN"])), _p(dg.graph_ptr), B, pw, 1.0 / B, 1.0 / B,
                _p(labels), _p(loss), _p(dl), st())
     assert torch.equal(labels.cpu(), labels_ref) and labels_ref.sum() > 10
     assert abs(float(loss) - float(loss_ref)) < 1e-5
     assert (dl.cpu().double() - logits.grad).abs().max() < 1e-7
     # labels only
-    lib().call("ddfa_graph_label_bce", None, _p(dev(g.ndata["_VULN"])), _p(dg.graph_ptr), B, 1.0, 0.0, 0.0, _p(labels), None, None, st())
+    lib().call("ddfa_graph_label_bce", None, _p(dk(g.ndata["_VULN"])), _p(dg.graph_ptr), B, 1.0, 0.0, 0.0, _p(labels), None, None, st())
     assert torch.equal(labels.cpu(), labels_ref)
 
 
@@ -329,6 +344,6 @@ def test_adam_flat_matches_torch_adam():
     for i in range(6):
         g = torch.randn(n) * (0.1 if i % 2 else 3.0)
         ref.grad = g.clone(); opt.step()
-        lib().call("ddfa_adam_flat", _p(p), _p(dev(g)), _p(m), _p(v), _p(step), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, st())
+        lib().call("ddfa_adam_flat", _p(p), _p(dk(g)), _p(m), _p(v), _p(step), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, st())
     assert int(step) == 6
     assert (p.cpu() - ref.detach()).abs().max() < 2e-6
