@@ -52,6 +52,12 @@ bool gru_tc_available();
 size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
 int gru_tc_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, int32_t D,
                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gru_tc_bwd_workspace_bytes(int32_t N, int32_t D);
+int gru_tc_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, void *workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
+int gru_tc_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates, const int32_t *indptr, int32_t N,
+                    int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
                     const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,
                     float *save_gates, void *workspace, size_t workspace_bytes, cudaStream_t stream);

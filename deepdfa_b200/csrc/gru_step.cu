@@ -247,6 +247,22 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
   return DDFA_OK;
 }
 
+size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
+  if (N < 0 || D <= 0) return 0;
+  if (engine == DDFA_ENGINE_TCGEN05) return ddfa::gru_tc_bwd_workspace_bytes(N, D);
+  return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // dgi | dgh
+}
+
+int ddfa_gru_step_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, int engine, void *workspace,
+                              size_t workspace_bytes, void *stream_) {
+  using namespace ddfa;
+  int rc = check_step_args("ddfa_gru_step_prepare_bwd", 0, D, engine);
+  if (rc) return rc;
+  if (engine == DDFA_ENGINE_SIMT) return DDFA_OK;
+  DDFA_REQUIRE(w_fold && w_hh, "ddfa_gru_step_prepare_bwd: NULL pointer");
+  return gru_tc_prepare_bwd(w_fold, w_hh, D, workspace, workspace_bytes, as_stream(stream_));
+}
+
 int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates, const int32_t *indptr,
                       const float *w_fold, const float *w_hh, int32_t N, int32_t D, float *ds, float *dh,
                       float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
@@ -259,12 +275,14 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
                "ddfa_gru_step_bwd: NULL pointer");
   DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd: dh must not alias dh_out");
   cudaStream_t stream = as_stream(stream_);
-  const size_t need = sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;
+  const size_t need = ddfa_gru_step_bwd_workspace_bytes(N, D, engine);
   if (workspace_bytes < need || workspace == nullptr) {
     set_error("ddfa_gru_step_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     return DDFA_ERR_WORKSPACE;
   }
-  // Round 1: the backward GEMMs run on the SIMT engine for both engine selections.
+  if (engine == DDFA_ENGINE_TCGEN05)
+    return gru_tc_step_bwd(dh_out, h, s, gates, indptr, N, D, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+                           workspace_bytes, stream);
   float *dgi = static_cast<float *>(workspace);
   float *dgh = dgi + (size_t)N * 3 * D;
   dim3 block(D / 4, 256 / (D / 4) > 0 ? 256 / (D / 4) : 1);

@@ -349,6 +349,430 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const float *__
   }
 }
 
+// =================================================================================================
+// Backward, part 1 — gate backward fused with the two data-gradient GEMMs (K = 3D):
+//     q_r, q_z, q_n, q_nr  (elementwise from dh', h, r, z, n, gh_n)           dgi = [q_r|q_z|q_n]
+//     ds = dgi  W'      (= q_r W'_r + q_z W'_z + q_n  W'_n)                   dgh = [q_r|q_z|q_nr]
+//     dh = dh' * z + dgh Whh (= q_r Whh_r + q_z Whh_z + q_nr Whh_n)
+// Also writes the four q planes (inputs of the weight-gradient kernel) and the bias gradients.
+// Same CTA organisation as the forward kernel; the A operand cycles the four q matrices through
+// two 64 KB slots (a_full / a_empty mbarriers), accumulators ds | dh = 2 x 128 TMEM columns.
+// Weight chunks (B operands, [n = output col][k = gate col] K-major, i.e. the TRANSPOSED weights) are
+// pre-packed by gru_tc_pack_bwd_kernel in consumption order:
+//   c in [ 0, 8): A = q_r : target ds (W'_r^T)  c<4, target dh (Whh_r^T) c>=4 ; kb = (c>>1)&1 ; v = c&1
+//   c in [ 8,16): A = q_z : likewise with gate z
+//   c in [16,20): A = q_n : ds (W'_n^T) ;  c in [20,24): A = q_nr : dh (Whh_n^T)
+// =================================================================================================
+__host__ __device__ __forceinline__ void bwd_chunk_decode(int c, int &m, int &target, int &kb, int &v) {
+  if (c < 16) { m = c >> 3; target = (c >> 2) & 1; }
+  else        { m = 2 + ((c - 16) >> 2); target = m - 2; }
+  kb = (c >> 1) & 1;
+  v = c & 1;
+}
+
+__global__ void __launch_bounds__(256) gru_tc_pack_bwd_kernel(const float *__restrict__ w_fold, const float *__restrict__ w_hh,
+                                                              uint8_t *__restrict__ packed) {
+  // one thread = (chunk pair cp (hi+lo), k8, n): 8 consecutive k of output column n
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 12 * 8 * 128) return;
+  const int n = t & 127, k8 = (t >> 7) & 7, cp = t >> 10;
+  int m, target, kb, v;
+  bwd_chunk_decode(cp * 2, m, target, kb, v);
+  const int gate = (m < 2) ? m : 2;
+  const float *W = (target == 0) ? w_fold : w_hh;
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float x = W[(size_t)(gate * 128 + kb * 64 + k8 * 8 + i) * kD + n];   // B[n][k] = W[gate*128 + k][n]
+    split_bf16(x, hi[i], lo[i]);
+  }
+  const uint32_t off = sw128_offset(n, k8 * 8);
+  *reinterpret_cast<uint4 *>(packed + (size_t)(cp * 2 + 0) * kChunkBytes + off) = *reinterpret_cast<const uint4 *>(hi);
+  *reinterpret_cast<uint4 *>(packed + (size_t)(cp * 2 + 1) * kChunkBytes + off) = *reinterpret_cast<const uint4 *>(lo);
+}
+
+constexpr int kBwdSlotBytes = 4 * kATileBytes;        // one q matrix: [hi|lo][kblock] = 64 KB
+constexpr int kBwdOffB = 2 * kBwdSlotBytes;           // 128 KB
+constexpr int kBwdOffBias = kBwdOffB + kSmemB;
+constexpr int kBwdOffBar = kBwdOffBias + kBiasFloats * 4;
+constexpr int kBwdNumBars = 2 * kStages + 5;          // full[5], empty[5], a_full[2], a_empty[2], acc
+constexpr int kBwdOffTmemPtr = kBwdOffBar + kBwdNumBars * 8;
+constexpr int kBwdSmemAlloc = kBwdOffTmemPtr + 16 + 1024;
+
+__device__ __forceinline__ void store_split_row(uint8_t *slot, int kb, uint32_t off, const float4 &x) {
+  __nv_bfloat16 hi[4], lo[4];
+  split_bf16(x.x, hi[0], lo[0]); split_bf16(x.y, hi[1], lo[1]);
+  split_bf16(x.z, hi[2], lo[2]); split_bf16(x.w, hi[3], lo[3]);
+  uint2 ph, pl;
+  ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+  ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+  pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+  pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+  *reinterpret_cast<uint2 *>(slot + (0 * 2 + kb) * kATileBytes + off) = ph;   // variant hi
+  *reinterpret_cast<uint2 *>(slot + (1 * 2 + kb) * kATileBytes + off) = pl;   // variant lo
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gru_tc_dgrad_kernel(
+    const float *__restrict__ dh_out, const float *__restrict__ h, const float *__restrict__ gates,
+    const int32_t *__restrict__ indptr, const uint8_t *__restrict__ packed, int32_t N, float *__restrict__ ds,
+    float *__restrict__ dh, float *__restrict__ q, float *__restrict__ db_fold, float *__restrict__ db_ih,
+    float *__restrict__ db_hh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kBwdOffBar;
+  auto full_bar = [&](int i) { return bar0 + 8u * i; };
+  auto empty_bar = [&](int i) { return bar0 + 8u * (kStages + i); };
+  auto afull_bar = [&](int s_) { return bar0 + 8u * (2 * kStages + s_); };
+  auto aempty_bar = [&](int s_) { return bar0 + 8u * (2 * kStages + 2 + s_); };
+  const uint32_t acc_bar = bar0 + 8u * (2 * kStages + 4);
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kBwdOffTmemPtr);
+  float *bias_s = reinterpret_cast<float *>(smem + kBwdOffBias);   // 7 x 128 column sums of this tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile0 = blockIdx.x * kTileM;
+  const size_t plane = (size_t)N * kD;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(afull_bar(i), kLoaderThreads); mbar_init(aempty_bar(i), 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_ptr_smem)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads) bias_s[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < kNumChunks; ++c) {
+        const int stage = c % kStages, use = c / kStages;
+        if (use > 0) mbar_wait(empty_bar(stage), (use - 1) & 1);
+        mbar_arrive_expect_tx(full_bar(stage), kChunkBytes);
+        bulk_g2s(sbase + kBwdOffB + stage * kChunkBytes, packed + (size_t)c * kChunkBytes, kChunkBytes, full_bar(stage));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t started = 0;  // bit per accumulator (ds, dh)
+      for (int c = 0; c < kNumChunks; ++c) {
+        int m, target, kb, v;
+        bwd_chunk_decode(c, m, target, kb, v);
+        const int slot = m & 1;
+        const bool first_of_m = (c == 0) || (c == 8) || (c == 16) || (c == 20);
+        const bool last_of_m = (c == 7) || (c == 15) || (c == 19) || (c == 23);
+        if (first_of_m) mbar_wait(afull_bar(slot), (m >> 1) & 1);
+        const int stage = c % kStages, use = c / kStages;
+        mbar_wait(full_bar(stage), use & 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)target * 128u;
+        const uint32_t b_addr = sbase + kBwdOffB + stage * kChunkBytes;
+        const int n_av = (v == 0) ? 2 : 1;
+        for (int av = 0; av < n_av; ++av) {
+          const uint32_t a_addr = sbase + (uint32_t)(slot * kBwdSlotBytes + (av * 2 + kb) * kATileBytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_f16(d_addr, make_desc(a_addr + k4 * 32), make_desc(b_addr + k4 * 32), kIdesc, (started >> target) & 1u);
+            started |= 1u << target;
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (last_of_m) umma_commit(aempty_bar(slot));   // this q matrix has been fully consumed
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    const int lw = warp - 2;
+    const int kb = lane >> 4, kin = (lane & 15) * 4;
+    const int col = lane * 4;
+    float4 sum[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- sweep 1: q_r -> slot 0, q_z -> slot 1; all four q planes to global ----
+#pragma unroll 2
+    for (int r = 0; r < 16; ++r) {
+      const int row = lw * 16 + r;
+      const int node = tile0 + row;
+      float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr;
+      if (node < N) {
+        const size_t off = (size_t)node * kD + col;
+        const float4 d = ldg_nc_f4(dh_out + off);
+        const float4 hv = ldg_nc_f4(h + off);
+        const float4 rr = ldg_nc_f4(gates + off);
+        const float4 zz = ldg_nc_f4(gates + plane + off);
+        const float4 nn = ldg_nc_f4(gates + 2 * plane + off);
+        const float4 gh = ldg_nc_f4(gates + 3 * plane + off);
+        const float deg = (float)(indptr[node + 1] - indptr[node]);
+#define BWDQ(f)                                                  \
+  {                                                              \
+    const float dz_ = d.f * (hv.f - nn.f);                       \
+    const float dn_ = d.f * (1.f - zz.f);                        \
+    qn.f = dn_ * (1.f - nn.f * nn.f);                            \
+    qz.f = dz_ * zz.f * (1.f - zz.f);                            \
+    qr.f = qn.f * gh.f * rr.f * (1.f - rr.f);                    \
+    qnr.f = qn.f * rr.f;                                         \
+  }
+        BWDQ(x) BWDQ(y) BWDQ(z) BWDQ(w)
+#undef BWDQ
+        *reinterpret_cast<float4 *>(q + off) = qr;
+        *reinterpret_cast<float4 *>(q + plane + off) = qz;
+        *reinterpret_cast<float4 *>(q + 2 * plane + off) = qn;
+        *reinterpret_cast<float4 *>(q + 3 * plane + off) = qnr;
+        f4_add(sum[0], qr); f4_add(sum[1], qz); f4_add(sum[2], qn); f4_add(sum[3], qnr);
+        f4_fma(sum[4], deg, qr); f4_fma(sum[5], deg, qz); f4_fma(sum[6], deg, qn);
+      }
+      const uint32_t off_s = sw128_offset(row, kin);
+      store_split_row(smem + 0 * kBwdSlotBytes, kb, off_s, qr);
+      store_split_row(smem + 1 * kBwdSlotBytes, kb, off_s, qz);
+    }
+    fence_async_smem();
+    mbar_arrive(afull_bar(0));
+    mbar_arrive(afull_bar(1));
+    // column sums of this tile -> shared (8 warps contend per address), later one RED per column per CTA
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      atomicAdd(&bias_s[i * kD + col + 0], sum[i].x); atomicAdd(&bias_s[i * kD + col + 1], sum[i].y);
+      atomicAdd(&bias_s[i * kD + col + 2], sum[i].z); atomicAdd(&bias_s[i * kD + col + 3], sum[i].w);
+    }
+    // ---- sweep 2: q_n -> slot 0, q_nr -> slot 1 (re-read this thread's own q values) ----
+#pragma unroll 1
+    for (int m = 2; m < 4; ++m) {
+      const int slot = m & 1;
+      mbar_wait(aempty_bar(slot), 0);
+      const float *qp = q + (size_t)m * plane;
+#pragma unroll 4
+      for (int r = 0; r < 16; ++r) {
+        const int row = lw * 16 + r;
+        const int node = tile0 + row;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (node < N) x = *reinterpret_cast<const float4 *>(qp + (size_t)node * kD + col);
+        store_split_row(smem + slot * kBwdSlotBytes, kb, sw128_offset(row, kin), x);
+      }
+      fence_async_smem();
+      mbar_arrive(afull_bar(slot));
+    }
+    // bias gradients: the 256 loader threads flush the CTA's column sums
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = threadIdx.x - 64; i < kBiasFloats; i += kLoaderThreads) {
+      const float v_ = bias_s[i];
+      const int which = i >> 7, c_ = i & 127;
+      // 0:S(q_r) 1:S(q_z) 2:S(q_n) 3:S(q_nr) 4:S(deg q_r) 5:S(deg q_z) 6:S(deg q_n)
+      if (which == 0) { atomicAdd(db_ih + c_, v_); atomicAdd(db_hh + c_, v_); }
+      else if (which == 1) { atomicAdd(db_ih + kD + c_, v_); atomicAdd(db_hh + kD + c_, v_); }
+      else if (which == 2) atomicAdd(db_ih + 2 * kD + c_, v_);
+      else if (which == 3) atomicAdd(db_hh + 2 * kD + c_, v_);
+      else atomicAdd(db_fold + (which - 4) * kD + c_, v_);
+    }
+    // ---- epilogue: ds = acc_ds ; dh = acc_dh + dh' * z ----
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int qd = warp & 3, chalf = lw >> 2;
+    const int row = qd * 32 + lane;
+    const int node = tile0 + row;
+    const bool valid = node < N;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col0 = chalf * 64 + cc * 16;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0;
+      float a_ds[16], a_dh[16];
+      tmem_ld16(taddr + 0, a_ds);
+      tmem_ld16(taddr + 128, a_dh);
+      float dv[16], zv[16];
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(dh_out + (size_t)node * kD + col0 + i * 4);
+          const float4 z4 = *reinterpret_cast<const float4 *>(gates + plane + (size_t)node * kD + col0 + i * 4);
+          dv[i * 4 + 0] = t4.x; dv[i * 4 + 1] = t4.y; dv[i * 4 + 2] = t4.z; dv[i * 4 + 3] = t4.w;
+          zv[i * 4 + 0] = z4.x; zv[i * 4 + 1] = z4.y; zv[i * 4 + 2] = z4.z; zv[i * 4 + 3] = z4.w;
+        }
+      }
+      tmem_ld_wait();
+      if (valid) {
+        float *pds = ds + (size_t)node * kD + col0;
+        float *pdh = dh + (size_t)node * kD + col0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4 *>(pds + i * 4) = make_float4(a_ds[i * 4], a_ds[i * 4 + 1], a_ds[i * 4 + 2], a_ds[i * 4 + 3]);
+          *reinterpret_cast<float4 *>(pdh + i * 4) =
+              make_float4(fmaf(dv[i * 4], zv[i * 4], a_dh[i * 4]), fmaf(dv[i * 4 + 1], zv[i * 4 + 1], a_dh[i * 4 + 1]),
+                          fmaf(dv[i * 4 + 2], zv[i * 4 + 2], a_dh[i * 4 + 2]), fmaf(dv[i * 4 + 3], zv[i * 4 + 3], a_dh[i * 4 + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// =================================================================================================
+// Backward, part 2 — weight gradients (K = nodes):  dW'[3D,D] += dgi^T s ,  dWhh[3D,D] += dgh^T h.
+// Both operands are "MN-major" (for one node k the 128 gate / feature columns are contiguous): the
+// same swizzled [node][64 cols] tiles the other kernels use, read through MN-major UMMA descriptors
+// (LBO = stride between the two 64-column blocks, SBO = stride between 8-node groups).
+// grid = (ctas, 2): blockIdx.y = role (0: A in {q_r,q_z,q_n}, B = s -> dW' ; 1: A in {q_r,q_z,q_nr}, B = h
+// -> dWhh).  A CTA is persistent over 64-node tiles and keeps its three [128 x 128] fp32 accumulator
+// blocks (384 TMEM columns) across all of them; the operands stream through a 6-slot ring (B_t, A_0, A_1,
+// A_2 per tile; B_t is released after A_2).  At the end every CTA adds its partial sums with RED.ADD.
+// =================================================================================================
+constexpr int kWgTileK = 64;                          // nodes per tile
+constexpr int kWgSlotBytes = 2 * 2 * kWgTileK * 128;  // [hi|lo][col block][64 nodes x 128 B] = 32 KB
+constexpr int kWgSlots = 6;
+constexpr int kWgOffBar = kWgSlots * kWgSlotBytes;    // 192 KB
+constexpr int kWgNumBars = 2 * kWgSlots + 1;
+constexpr int kWgOffTmemPtr = kWgOffBar + kWgNumBars * 8;
+constexpr int kWgSmemAlloc = kWgOffTmemPtr + 16 + 1024;
+// both operands MN-major: bit 15 (A) and bit 16 (B)
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  // start>>4 | LBO (between 64-element MN blocks) = 8192 B | SBO (between 8-row K groups) = 1024 B | v1 | SW128
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((kWgTileK * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gru_tc_wgrad_kernel(const float *__restrict__ q, const float *__restrict__ s,
+                                                                   const float *__restrict__ h, int32_t N,
+                                                                   float *__restrict__ dw_fold, float *__restrict__ dw_hh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kWgOffBar;
+  auto full_bar = [&](int i) { return bar0 + 8u * i; };
+  auto empty_bar = [&](int i) { return bar0 + 8u * (kWgSlots + i); };
+  const uint32_t acc_bar = bar0 + 8u * (2 * kWgSlots);
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kWgOffTmemPtr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = blockIdx.y;
+  const int num_tiles = (N + kWgTileK - 1) / kWgTileK;
+  const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const size_t plane = (size_t)N * kD;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgSlots; ++i) { mbar_init(full_bar(i), kLoaderThreads); mbar_init(empty_bar(i), 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_ptr_smem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int jb = 4 * i;                       // operand sequence number of B_t
+        const int slot_b = jb % kWgSlots;
+        mbar_wait(full_bar(slot_b), (jb / kWgSlots) & 1);
+        for (int g = 0; g < 3; ++g) {
+          const int ja = jb + 1 + g, slot_a = ja % kWgSlots;
+          mbar_wait(full_bar(slot_a), (ja / kWgSlots) & 1);
+          tc_fence_after();
+          const uint32_t a0 = sbase + slot_a * kWgSlotBytes, b0 = sbase + slot_b * kWgSlotBytes;
+          const uint32_t d_addr = tmem_base + (uint32_t)g * 128u;
+#pragma unroll
+          for (int k16 = 0; k16 < kWgTileK / 16; ++k16) {
+            const uint32_t koff = (uint32_t)k16 * 2048u;   // 16 nodes = two 8-node groups of 1024 B
+            const uint32_t vstride = 2 * kWgTileK * 128;   // hi -> lo variant
+            const uint32_t acc = (i > 0 || k16 > 0) ? 1u : 0u;
+            umma_f16(d_addr, make_desc_mn(a0 + koff), make_desc_mn(b0 + koff), kIdescMN, acc);                     // a_hi b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + vstride + koff), make_desc_mn(b0 + koff), kIdescMN, 1u);            // a_lo b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + koff), make_desc_mn(b0 + vstride + koff), kIdescMN, 1u);            // a_hi b_lo
+          }
+          umma_commit(empty_bar(slot_a));
+        }
+        umma_commit(empty_bar(slot_b));
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (warp >= 2) {
+    const int lw = warp - 2;
+    const int kb = lane >> 4, kin = (lane & 15) * 4;
+    const int col = lane * 4;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int node0 = tile * kWgTileK;
+      for (int w = 0; w < 4; ++w) {
+        const int j = 4 * i + w, slot = j % kWgSlots;
+        if (j >= kWgSlots) mbar_wait(empty_bar(slot), ((j / kWgSlots) - 1) & 1);
+        const float *src;
+        if (w == 0) src = (role == 0) ? s : h;
+        else {
+          const int pl = (w == 3) ? (role == 0 ? 2 : 3) : (w - 1);   // q planes: r, z, then n (role 0) or nr (role 1)
+          src = q + (size_t)pl * plane;
+        }
+        uint8_t *dst = smem + slot * kWgSlotBytes;
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int node = node0 + lw * 8 + r;
+          v[r] = (node < N) ? ldg_nc_f4(src + (size_t)node * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int row = lw * 8 + r;
+          __nv_bfloat16 hi[4], lo[4];
+          split_bf16(v[r].x, hi[0], lo[0]); split_bf16(v[r].y, hi[1], lo[1]);
+          split_bf16(v[r].z, hi[2], lo[2]); split_bf16(v[r].w, hi[3], lo[3]);
+          uint2 ph, pl2;
+          ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+          ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+          pl2.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+          pl2.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+          const uint32_t off = sw128_offset(row, kin);
+          *reinterpret_cast<uint2 *>(dst + (0 * 2 + kb) * (kWgTileK * 128) + off) = ph;
+          *reinterpret_cast<uint2 *>(dst + (1 * 2 + kb) * (kWgTileK * 128) + off) = pl2;
+        }
+        fence_async_smem();
+        mbar_arrive(full_bar(slot));
+      }
+    }
+    if (my_tiles > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+      const int qd = warp & 3, chalf = lw >> 2;
+      const int m = qd * 32 + lane;                      // row inside the 128-row gate block
+      float *dW = (role == 0) ? dw_fold : dw_hh;
+#pragma unroll 1
+      for (int g = 0; g < 3; ++g) {
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = chalf * 64 + cc * 16;
+          float a[16];
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + col0), a);
+          tmem_ld_wait();
+          float *dst = dW + (size_t)(g * 128 + m) * kD + col0;
+#pragma unroll
+          for (int x = 0; x < 16; ++x) atomicAdd(dst + x, a[x]);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 }  // namespace tc
 
 bool gru_tc_available() { return true; }
@@ -371,6 +795,56 @@ int gru_tc_prepare(const float *w_fold, const float *b_fold, const float *b_ih, 
   const int total = 2 * 2 * 3 * 128 * 8;
   tc::gru_tc_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, b_fold, b_ih, b_hh, static_cast<uint8_t *>(workspace));
   DDFA_CHECK_LAUNCH("gru_tc_pack_kernel");
+  return DDFA_OK;
+}
+
+// ---- backward host side --------------------------------------------------------------------------
+// workspace = [24 x 16 KB packed transposed weights][q planes: 4 x N x 128 fp32]
+size_t gru_tc_bwd_workspace_bytes(int32_t N, int32_t D) {
+  if (D != tc::kD) return 16;
+  return (size_t)tc::kNumChunks * tc::kChunkBytes + (size_t)4 * (size_t)N * tc::kD * sizeof(float);
+}
+
+int gru_tc_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, void *workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  if (D != tc::kD) {
+    set_error("tcgen05 engine: D must be 128, got %d", D);
+    return DDFA_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < (size_t)tc::kNumChunks * tc::kChunkBytes) {
+    set_error("tcgen05 engine (bwd): workspace too small");
+    return DDFA_ERR_WORKSPACE;
+  }
+  tc::gru_tc_pack_bwd_kernel<<<(12 * 8 * 128 + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, static_cast<uint8_t *>(workspace));
+  DDFA_CHECK_LAUNCH("gru_tc_pack_bwd_kernel");
+  return DDFA_OK;
+}
+
+int gru_tc_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates, const int32_t *indptr, int32_t N,
+                    int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (D != tc::kD) {
+    set_error("tcgen05 engine: D must be 128, got %d", D);
+    return DDFA_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < gru_tc_bwd_workspace_bytes(N, D)) {
+    set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc_bwd_workspace_bytes(N, D));
+    return DDFA_ERR_WORKSPACE;
+  }
+  uint8_t *packed = static_cast<uint8_t *>(workspace);
+  float *q = reinterpret_cast<float *>(packed + (size_t)tc::kNumChunks * tc::kChunkBytes);
+  DDFA_CUDA(cudaFuncSetAttribute(tc::gru_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kBwdSmemAlloc));
+  DDFA_CUDA(cudaFuncSetAttribute(tc::gru_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemAlloc));
+  const int tiles = (N + tc::kTileM - 1) / tc::kTileM;
+  tc::gru_tc_dgrad_kernel<<<tiles, tc::kThreads, tc::kBwdSmemAlloc, stream>>>(dh_out, h, gates, indptr, packed, N, ds, dh, q, db_fold,
+                                                                            db_ih, db_hh);
+  DDFA_CHECK_LAUNCH("gru_tc_dgrad_kernel");
+  const int wtiles = (N + tc::kWgTileK - 1) / tc::kWgTileK;
+  int ctas = kNumSMs / 2;
+  if (ctas > wtiles) ctas = wtiles;
+  dim3 grid(ctas, 2);
+  tc::gru_tc_wgrad_kernel<<<grid, tc::kThreads, tc::kWgSmemAlloc, stream>>>(q, s, h, N, dw_fold, dw_hh);
+  DDFA_CHECK_LAUNCH("gru_tc_wgrad_kernel");
   return DDFA_OK;
 }
 

@@ -306,8 +306,9 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     dw_fold.zero_()
     db_fold.zero_()
     ds = alloc.get("ds", (N, D))
-    ws_bytes = 4 * 2 * N * 3 * D
+    ws_bytes = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, engine)
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
+    L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
         _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
                _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),

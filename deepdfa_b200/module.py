@@ -139,6 +139,11 @@ class FlowGNNGGNNModule(nn.Module):
             encoder_mode=encoder_mode, undersample_node_on_loss_factor=undersample_node_on_loss_factor,
             test_every=test_every, tune_nni=tune_nni, positive_weight=positive_weight, profile=profile, time=time)
         self.class_threshold = 0.5  # base_module.py:32
+        # base_module.py:72-74: the reference keeps BCEWithLogitsLoss(pos_weight) as a submodule, so a checkpoint
+        # saved with positive_weight carries the buffer "loss_fn.pos_weight"; keep the same container/key.  The loss
+        # itself is computed by ddfa_graph_label_bce.
+        self.loss_fn = nn.BCEWithLogitsLoss(
+            pos_weight=None if positive_weight is None else torch.tensor([positive_weight]))
 
         if "_ABS_DATAFLOW" in feat:  # ggnn.py:36-37
             feat = "_ABS_DATAFLOW"

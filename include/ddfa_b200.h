@@ -132,7 +132,13 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
                       void *workspace, size_t workspace_bytes, int engine, void *stream);
 /* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
  * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
- * Accumulated (+=): dw_fold[3D,D], db_fold[3D], db_ih[3D], dw_hh[3D,D], db_hh[3D]. */
+ * Accumulated (+=): dw_fold[3D,D], db_fold[3D], db_ih[3D], dw_hh[3D,D], db_hh[3D].
+ * workspace: ddfa_gru_step_bwd_workspace_bytes(); with the tcgen05 engine it must first be
+ * prepared once per backward pass by ddfa_gru_step_prepare_bwd (transposed bf16 hi/lo weight
+ * images) and is then reused by every step of that pass. */
+size_t ddfa_gru_step_bwd_workspace_bytes(int32_t num_nodes, int32_t dim, int engine);
+int ddfa_gru_step_prepare_bwd(const float *w_fold, const float *w_hh, int32_t dim, int engine,
+                              void *workspace, size_t workspace_bytes, void *stream);
 int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates,
                       const int32_t *indptr, const float *w_fold, const float *w_hh,
                       int32_t num_nodes, int32_t dim, float *ds, float *dh, float *dw_fold,

@@ -10,7 +10,7 @@ for STAGE in "$@"; do
   echo "=================== stage: $STAGE"
   case $STAGE in
     tests)
-      timeout 1800 python -m pytest tests -m gpu -q --timeout 300 -s > $OUT/${TAG}_pytest.log 2>&1
+      timeout 900 python -m pytest tests -m gpu -q --timeout 120 -s > $OUT/${TAG}_pytest.log 2>&1
       echo "pytest exit: $?"; grep -E "passed|failed|error" $OUT/${TAG}_pytest.log | tail -n 5
       grep -E "^(FAILED|ERROR)|worst|max\|dlogit" $OUT/${TAG}_pytest.log | head -n 40 ;;
     tcdebug)

@@ -82,7 +82,49 @@ def main():
     errmap("T4 h_out simt    vs fp64", ho_si, ref)
     errmap("T4 gh_n  tcgen05 vs fp64", g_tc[3], gh[:, 2 * D:])
     errmap("T4 gh_n  simt    vs fp64", g_si[3], gh[:, 2 * D:])
+    # --- test 5: backward, tcgen05 vs SIMT engine (the SIMT backward is pinned against fp64 autograd in tests/)
+    def run_bwd(engine, N_, dh_o, h_, s_, gates_, ip_):
+        L = lib()
+        wsb = max(L.call("ddfa_gru_step_bwd_workspace_bytes", N_, D, engine), 16)
+        ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_gru_step_prepare_bwd", _p(wf4), _p(whh4), D, engine, _p(ws), wsb, _stream_ptr())
+        outs = {"ds": torch.full((N_, D), float("nan"), device=DEV), "dh": torch.full((N_, D), float("nan"), device=DEV),
+                "dwf": torch.zeros(3 * D, D, device=DEV), "dbf": torch.zeros(3 * D, device=DEV), "dbih": torch.zeros(3 * D, device=DEV),
+                "dwhh": torch.zeros(3 * D, D, device=DEV), "dbhh": torch.zeros(3 * D, device=DEV)}
+        def call():
+            L.call("ddfa_gru_step_bwd", _p(dh_o), _p(h_), _p(s_), _p(gates_), _p(ip_), _p(wf4), _p(whh4), N_, D, _p(outs["ds"]), _p(outs["dh"]),
+                   _p(outs["dwf"]), _p(outs["dbf"]), _p(outs["dbih"]), _p(outs["dwhh"]), _p(outs["dbhh"]), _p(ws), wsb, engine, _stream_ptr())
+        call()
+        torch.cuda.synchronize()
+        return outs, call
+    dh_o = torch.randn(N, D, device=DEV)
+    o_tc, _ = run_bwd(ENGINE_TCGEN05, N, dh_o, h4, s4, g_si, indptr)
+    o_si, _ = run_bwd(ENGINE_SIMT, N, dh_o, h4, s4, g_si, indptr)
+    for k in o_tc:
+        if o_tc[k].dim() == 2 and o_tc[k].shape[0] == N:
+            errmap(f"T5 bwd {k} tcgen05 vs simt", o_tc[k], o_si[k])
+        else:
+            e = float((o_tc[k].double() - o_si[k].double()).abs().max()); sc = float(o_si[k].abs().max())
+            print(f"T5 bwd {k}: max err {e:.3e} (ref max {sc:.3e}), nan {int(torch.isnan(o_tc[k]).sum())}")
+            if o_tc[k].dim() == 2 and e > 1e-3 * max(sc, 1):
+                err = (o_tc[k] - o_si[k]).abs().reshape(3, 4, 32, 4, 32).amax(dim=(2, 4))
+                print("   block map [gate][row32][col32]:", [[f"{float(x):.1e}" for x in r_.flatten()] for r_ in err])
     # timing
+    N2 = 38400
+    s5 = torch.randn(N2, D, device=DEV); h5 = torch.tanh(torch.randn(N2, D, device=DEV)); d5 = torch.randn(N2, D, device=DEV)
+    g5 = torch.rand(4, N2, D, device=DEV)
+    ip5 = torch.arange(N2 + 1, dtype=torch.int32, device=DEV) * 2
+    for eng, name in ((ENGINE_TCGEN05, "tcgen05"), (ENGINE_SIMT, "simt")):
+        _, call = run_bwd(eng, N2, d5, h5, s5, g5, ip5)
+        for _ in range(3):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 10 * 1e3
+        print(f"timing bwd {name} N={N2}: {us:.1f} us/step ({2 * 2.0 * N2 * 6 * D * D / us / 1e6:.1f} TFLOP/s algorithmic)")
     for eng, name in ((ENGINE_TCGEN05, "tcgen05"), (ENGINE_SIMT, "simt")):
         N2 = 38400
         s5 = torch.randn(N2, D, device=DEV); h5 = torch.tanh(torch.randn(N2, D, device=DEV))

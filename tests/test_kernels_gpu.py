@@ -224,14 +224,20 @@ def test_gru_step_fwd_bwd(D):
     sd, hd, wfd, bfd, bihd, whhd, bhhd = f32
     for engine in engines_for(D):
         L = lib()
-        wsb = max(L.call("ddfa_gru_step_workspace_bytes", N, D, engine), 4 * 2 * N * 3 * D)
+        wsb = max(L.call("ddfa_gru_step_workspace_bytes", N, D, engine), 16)
         ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_gru_step_prepare", _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), D, engine, _p(ws), wsb, st())
+        wsb_b = max(L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, engine), 16)
+        ws_b = torch.empty(wsb_b, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_gru_step_prepare_bwd", _p(wfd), _p(whhd), D, engine, _p(ws_b), wsb_b, st())
         h_out = torch.empty(N, D, device=DEV); gates = torch.empty(4, N, D, device=DEV)
         L.call("ddfa_gru_step_fwd", _p(sd), _p(hd), _p(dg.indptr), _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), N, D, _p(h_out),
                _p(gates), _p(ws), wsb, engine, st())
-        assert (h_out.cpu().double() - h_ref.detach()).abs().max() < 2e-5, f"engine {engine}"
+        # SIMT: fp32 FFMA + accurate expf/tanhf; tcgen05: bf16x3 operands (~2^-16 rel.) + ex2.approx gate math
+        tol_h = 2e-5 if engine == ENGINE_SIMT else 1e-4
+        assert (h_out.cpu().double() - h_ref.detach()).abs().max() < tol_h, f"engine {engine}"
         for got, ref in zip(gates.cpu().double(), (r_ref, z_ref, n_ref, ghn_ref)):
-            assert (got - ref.detach()).abs().max() < 5e-5
+            assert (got - ref.detach()).abs().max() < 2.5 * tol_h
         # without gate saving
         h_out2 = torch.empty(N, D, device=DEV)
         L.call("ddfa_gru_step_fwd", _p(sd), _p(hd), _p(dg.indptr), _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), N, D, _p(h_out2),
@@ -241,7 +247,7 @@ def test_gru_step_fwd_bwd(D):
         ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
         acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
         L.call("ddfa_gru_step_bwd", _p(dk(dh_out.float())), _p(hd), _p(sd), _p(gates), _p(dg.indptr), _p(wfd), _p(whhd), N, D, _p(ds), _p(dh),
-               _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]), _p(ws), wsb, engine, st())
+               _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]), _p(ws_b), wsb_b, engine, st())
         checks = [(ds, s.grad), (dh, h.grad), (acc["dwf"], wf.grad), (acc["dbf"], bf.grad), (acc["dbih"], bih.grad), (acc["dwhh"], whh.grad), (acc["dbhh"], bhh.grad)]
         for got, ref in checks:
             scale = max(1.0, float(ref.abs().max()))
