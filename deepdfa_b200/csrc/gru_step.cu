@@ -146,13 +146,22 @@ __global__ void fold_bias_bwd_outer_kernel(const float *__restrict__ db_fold, co
   const int j = (int)(t / D), k = (int)(t % D);
   dw_ih[t] = fmaf(db_fold[j], b[k], dw_ih[t]);
 }
-// db[k] += sum_j w_ih[j,k] db_fold[j]
-__global__ void fold_bias_bwd_vec_kernel(const float *__restrict__ w_ih, const float *__restrict__ db_fold, int32_t D, float *__restrict__ db) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= D) return;
+// db[k] += sum_j w_ih[j,k] db_fold[j]     block = (32 columns) x (8 row partitions), coalesced along k
+__global__ void __launch_bounds__(256) fold_bias_bwd_vec_kernel(const float *__restrict__ w_ih, const float *__restrict__ db_fold,
+                                                                int32_t D, float *__restrict__ db) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int j = 0; j < 3 * D; ++j) s = fmaf(w_ih[(int64_t)j * D + k], db_fold[j], s);
-  db[k] += s;
+  if (k < D)
+    for (int j = threadIdx.y; j < 3 * D; j += 8) s = fmaf(w_ih[(int64_t)j * D + k], db_fold[j], s);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    db[k] += t;
+  }
 }
 
 }  // namespace ddfa
@@ -188,7 +197,7 @@ int ddfa_fold_weights_bwd(const float *w_msg, const float *b_msg, const float *w
   const int64_t tot = (int64_t)3 * D * D;
   fold_bias_bwd_outer_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(db_fold, b_msg, D, dw_ih);
   DDFA_CHECK_LAUNCH("fold_bias_bwd_outer_kernel");
-  fold_bias_bwd_vec_kernel<<<(D + 127) / 128, 128, 0, stream>>>(w_ih, db_fold, D, db_msg);
+  fold_bias_bwd_vec_kernel<<<(D + 31) / 32, dim3(32, 8), 0, stream>>>(w_ih, db_fold, D, db_msg);
   DDFA_CHECK_LAUNCH("fold_bias_bwd_vec_kernel");
   return DDFA_OK;
 }

@@ -250,12 +250,21 @@ __global__ void relu_mask_kernel(const float *in, const float *__restrict__ mask
   if (i < total) out[i] = (mask[i] > 0.f) ? in[i] : 0.f;
 }
 // out[n] += sum_m X[m,n]   (M small: one thread per column, coalesced across threads)
-__global__ void colsum_accum_kernel(const float *__restrict__ X, int32_t M, int32_t N, float *__restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// block = (32 columns) x (8 row partitions); one block owns its 32 columns, so the += needs no atomics
+__global__ void __launch_bounds__(256) colsum_accum_kernel(const float *__restrict__ X, int32_t M, int32_t N, float *__restrict__ out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) s += X[(int64_t)m * N + n];
-  out[n] += s;
+  if (n < N)
+    for (int m = threadIdx.y; m < M; m += 8) s += X[(int64_t)m * N + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[n] += t;
+  }
 }
 
 }  // namespace ddfa
@@ -313,7 +322,7 @@ int ddfa_mlp_bwd(const float *dlogits, const float *pooled, const float *mlp_act
     // dW_i[out,2D] += dOut^T[out,B] @ in[B,2D]
     int rc = sgemm(1, 0, out_dim, D2, B, 1.f, dout, out_dim, in, D2, 1.f, dmlp_w[i], D2, 1, stream);
     if (rc) return rc;
-    colsum_accum_kernel<<<(out_dim + 127) / 128, 128, 0, stream>>>(dout, B, out_dim, dmlp_b[i]);
+    colsum_accum_kernel<<<(out_dim + 31) / 32, dim3(32, 8), 0, stream>>>(dout, B, out_dim, dmlp_b[i]);
     DDFA_CHECK_LAUNCH("colsum_accum_kernel");
     // dIn[B,2D] = dOut[B,out] @ W_i[out,2D]
     float *din = (i == 0) ? dpooled : (dout == buf0 ? buf1 : buf0);
