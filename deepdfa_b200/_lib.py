@@ -51,6 +51,10 @@ _SIGNATURES = {
     "ddfa_gru_step_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "ddfa_gru_step_prepare": (_int, [_vp] * 5 + [_i32, _int, _vp, _sz, _vp]),
     "ddfa_gru_step_fwd": (_int, [_vp] * 8 + [_i32, _i32, _vp, _vp, _vp, _sz, _int, _vp]),
+    "ddfa_act_image_bytes": (_sz, [_i64]),
+    "ddfa_act_to_image": (_int, [_vp, _i32, _i32, _vp, _vp]),
+    "ddfa_gather_sum_image": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ddfa_gru_step_fwd_image": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "ddfa_gru_step_prepare_bwd": (_int, [_vp, _vp, _i32, _int, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd": (_int, [_vp] * 7 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
@@ -63,7 +67,8 @@ _SIGNATURES = {
 }
 
 _NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
-              "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes"}
+              "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes",
+              "ddfa_act_image_bytes"}
 
 
 class _Lib:

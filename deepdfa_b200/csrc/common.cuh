@@ -52,6 +52,14 @@ bool gru_tc_available();
 size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
 int gru_tc_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, int32_t D,
                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
+// gru_tc_fwd.cu — forward v2 (weight-stationary, activation images)
+size_t act_image_bytes(int64_t n);
+int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
+size_t gru_tc2_workspace_bytes();
+int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
+                     void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gru_tc_bwd_workspace_bytes(int32_t N, int32_t D);
 int gru_tc_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, void *workspace, size_t workspace_bytes,
                        cudaStream_t stream);

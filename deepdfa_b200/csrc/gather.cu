@@ -17,6 +17,7 @@
 // parallelism) and folded into per-row accumulators by a warp-uniform segmented reduction (row
 // boundaries broadcast with shuffles), RW rows per pass.  No atomics; neighbour lists are sorted,
 // so the fp32 summation order — and the result — is deterministic.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -139,6 +140,85 @@ static int launch_gather(const int32_t *indptr, const int32_t *indices, const fl
   return DDFA_OK;
 }
 
+// ---- D = 128, output as an activation image (tc_common.cuh) for the tcgen05 engine --------------------
+// Same mapping as variant 9 (2 rows per pass, 2 passes, 4 row loads in flight, 128-thread CTAs); the sum of a
+// row is split into bf16 hi/lo and stored as 8-byte pieces of the swizzled image (16 lanes fill one 128-byte
+// image row).  Rows N .. ceil128(N)-1 are written as zeros (the weight-gradient GEMM sums over all 128 rows).
+__global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__restrict__ indptr,
+                                                               const int32_t *__restrict__ indices,
+                                                               const float *__restrict__ h, int32_t N,
+                                                               uint8_t *__restrict__ out_img, float *__restrict__ out_f32) {
+  constexpr int RW = 2, PASSES = 2, ROWS = RW * PASSES, UNROLL = 4, D = 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t v0 = warp_global * ROWS;
+  const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
+  if (v0 >= Npad) return;
+  const int nrows = (int)min((int64_t)ROWS, Npad - v0);
+  int32_t myptr = 0;
+  if (lane <= nrows) myptr = __ldg(indptr + min(v0 + lane, (int64_t)N));   // padded rows: empty neighbour list
+  const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
+  const int32_t total = __shfl_sync(0xffffffffu, myptr, nrows) - beg0;
+  const int32_t pre = (lane < total) ? __ldg(indices + beg0 + lane) : 0;
+#pragma unroll 1
+  for (int p = 0; p < PASSES; ++p) {
+    const int r0 = p * RW;
+    if (r0 >= nrows) break;
+    int32_t rend[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) rend[r] = __shfl_sync(0xffffffffu, myptr, min(r0 + r + 1, nrows)) - beg0;
+    const int32_t pbeg = __shfl_sync(0xffffffffu, myptr, r0) - beg0;
+    const int32_t pend = rend[RW - 1];
+    float4 acc[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t b = pbeg; b < pend; b += UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const int32_t pos = min(b + j, pend - 1);
+        int32_t u = __shfl_sync(0xffffffffu, pre, pos & 31);
+        if (pos >= 32) u = __ldg(indices + beg0 + pos);
+        v[j] = (b + j < pend) ? ldg_nc_f4(h + (int64_t)u * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const int32_t pos = b + j;
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const bool mine = (pos < rend[r]) && (r == 0 ? true : pos >= rend[r - 1]);
+          if (mine) f4_add(acc[r], v[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (r0 + r < nrows) {
+        const int64_t node = v0 + r0 + r;
+        // bf16 hi/lo split of 4 consecutive columns -> two 8-byte stores into the swizzled image
+        __nv_bfloat16 hi[4], lo[4];
+        const float xs[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hi[i] = __float2bfloat16_rn(xs[i]);
+          lo[i] = __float2bfloat16_rn(xs[i] - __bfloat162float(hi[i]));
+        }
+        uint2 ph, pl;
+        ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+        ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+        pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+        pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+        const int col = lane * 4, row = (int)(node & 127);
+        const size_t tile_off = (size_t)(node >> 7) * 65536;
+        const uint32_t sw = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((((col & 63) >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
+        *reinterpret_cast<uint2 *>(out_img + tile_off + (size_t)((0 * 2 + (col >> 6)) * 16384) + sw) = ph;
+        *reinterpret_cast<uint2 *>(out_img + tile_off + (size_t)((1 * 2 + (col >> 6)) * 16384) + sw) = pl;
+        if (out_f32 && node < N) *reinterpret_cast<float4 *>(out_f32 + node * D + col) = acc[r];
+      }
+    }
+  }
+}
+
 // Tuning variants for the D=128 case (selected by ddfa_gather_sum_variant / $DDFA_GATHER_VARIANT):
 //   id : RW UNROLL PASSES NIDX THREADS
 static int launch_d128_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,
@@ -196,6 +276,20 @@ int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *
   if (chunks <= 64) return launch_gather<32, 2, 2, 8, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
   if (chunks <= 128) return launch_gather<32, 4, 2, 4, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
   return launch_gather<32, 8, 1, 4, 2, 1, 256>(indptr, indices, h, N, D, out, accumulate, stream);
+}
+
+int ddfa_gather_sum_image(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, int32_t D,
+                          void *out_image, float *out_f32, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gather_sum_image: activation images exist for D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(indptr && indices && h && out_image && aligned16(h) && aligned16(out_image), "ddfa_gather_sum_image: NULL or unaligned pointer");
+  const int64_t rows = ((int64_t)N + 127) / 128 * 128;
+  const int64_t warps = (rows + 3) / 4;
+  const int64_t blocks = (warps * 32 + 127) / 128;
+  gather_sum_image_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream_)>>>(indptr, indices, h, N, static_cast<uint8_t *>(out_image), out_f32);
+  DDFA_CHECK_LAUNCH("gather_sum_image_kernel");
+  return DDFA_OK;
 }
 
 int ddfa_gather_sum_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,

@@ -204,8 +204,31 @@ int ddfa_fold_weights_bwd(const float *w_msg, const float *b_msg, const float *w
 
 size_t ddfa_gru_step_workspace_bytes(int32_t N, int32_t D, int engine) {
   if (N < 0 || D <= 0) return 0;
-  if (engine == DDFA_ENGINE_TCGEN05) return ddfa::gru_tc_workspace_bytes(N, D);
-  return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // gi|gh (fwd) or dgi|dgh (bwd)
+  // tcgen05: [packed per-slice weight images + biases][s image][h image]; the two images are only used by the
+  // fp32-in/fp32-out entry ddfa_gru_step_fwd (N = 0 gives the size ddfa_gru_step_fwd_image needs).
+  if (engine == DDFA_ENGINE_TCGEN05) return D == 128 ? ddfa::gru_tc2_workspace_bytes() + 2 * ddfa::act_image_bytes(N) : 16;
+  return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // gi|gh
+}
+
+size_t ddfa_act_image_bytes(int64_t num_nodes) { return num_nodes < 0 ? 0 : ddfa::act_image_bytes(num_nodes); }
+
+int ddfa_act_to_image(const float *x, int32_t N, int32_t D, void *image, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_act_to_image: activation images exist for D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(x && image && aligned16(x) && aligned16(image), "ddfa_act_to_image: NULL or unaligned pointer");
+  return act_to_image(x, N, image, as_stream(stream_));
+}
+
+int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const float *h, const int32_t *indptr, int32_t N,
+                            int32_t D, float *h_out, void *h_out_image, float *save_gates, const void *workspace,
+                            size_t workspace_bytes, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_fwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(s_image && h_image && h && indptr && h_out, "ddfa_gru_step_fwd_image: NULL pointer");
+  return gru_tc2_step_fwd(s_image, h_image, h, indptr, N, h_out, h_out_image, save_gates, workspace, workspace_bytes,
+                          as_stream(stream_));
 }
 
 static int check_step_args(const char *who, int32_t N, int32_t D, int engine) {
@@ -226,7 +249,7 @@ int ddfa_gru_step_prepare(const float *w_fold, const float *b_fold, const float 
   if (rc) return rc;
   if (engine == DDFA_ENGINE_SIMT) return DDFA_OK;  // nothing to pre-pack
   DDFA_REQUIRE(w_fold && b_fold && b_ih && w_hh && b_hh, "ddfa_gru_step_prepare: NULL pointer");
-  return gru_tc_prepare(w_fold, b_fold, b_ih, w_hh, b_hh, D, workspace, workspace_bytes, as_stream(stream_));
+  return gru_tc2_prepare(w_fold, b_fold, b_ih, w_hh, b_hh, workspace, workspace_bytes, as_stream(stream_));
 }
 
 int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
@@ -242,8 +265,18 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
     set_error("ddfa_gru_step_fwd: workspace too small (%zu < %zu)", workspace_bytes, ddfa_gru_step_workspace_bytes(N, D, engine));
     return DDFA_ERR_WORKSPACE;
   }
-  if (engine == DDFA_ENGINE_TCGEN05)
-    return gru_tc_step_fwd(s, h, indptr, w_fold, b_fold, b_ih, w_hh, b_hh, N, D, h_out, save_gates, workspace, workspace_bytes, stream);
+  if (engine == DDFA_ENGINE_TCGEN05) {
+    // fp32-in / fp32-out convenience path (tests, tools): build the two operand images in the workspace, then run the
+    // image kernel.  The training driver calls ddfa_gru_step_fwd_image with images written by the producer kernels.
+    uint8_t *ws8 = static_cast<uint8_t *>(workspace);
+    void *s_img = ws8 + gru_tc2_workspace_bytes();
+    void *h_img = ws8 + gru_tc2_workspace_bytes() + act_image_bytes(N);
+    rc = act_to_image(s, N, s_img, stream);
+    if (rc) return rc;
+    rc = act_to_image(h, N, h_img, stream);
+    if (rc) return rc;
+    return gru_tc2_step_fwd(s_img, h_img, h, indptr, N, h_out, nullptr, save_gates, workspace, workspace_bytes, stream);
+  }
   float *gi = static_cast<float *>(workspace);
   float *gh = gi + (size_t)N * 3 * D;
   rc = sgemm(0, 1, N, 3 * D, D, 1.f, s, D, w_fold, D, 0.f, gi, 3 * D, 1, stream);

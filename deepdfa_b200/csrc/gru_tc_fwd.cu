@@ -1,0 +1,331 @@
+// tcgen05 engine, forward GRU step v2 (D == 128) — weight-stationary, persistent, TMA-fed.
+//
+//   acc_r = s W'_r^T + h Whh_r^T    acc_z = s W'_z^T + h Whh_z^T    acc_gin = s W'_n^T    acc_ghn = h Whh_n^T
+//   r,z = sigmoid(acc + indeg b' + b_ih + b_hh) ; n = tanh(gin + r * ghn) ; h' = n + z (h - n)
+//
+// Why this shape (r01c ncu: the first tcgen05 kernel kept the tensor pipe busy only 7-10 % of the time —
+// every CTA re-streamed all 384 KB of split weights per 128-node tile and converted its A operand itself,
+// with load / MMA / epilogue phases serialised):
+//   * WEIGHT-STATIONARY: a CTA owns a 32-column slice of the 128 hidden columns for the whole launch; the
+//     bf16 hi/lo images of the 96 weight rows it needs (3 gates x 32 columns, K = 128, two matrices) are
+//     96 KB and are loaded into shared memory ONCE per CTA.
+//   * The A operands (s and h) arrive as "activation images" (tc_common.cuh) written by the producer
+//     kernels, so the GEMM kernel has no conversion pass: one elected thread streams 16 KB chunks through a
+//     7-stage ring with cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) + mbarrier complete_tx.
+//   * The accumulators of one 128-node tile are only 4 x 32 = 128 TMEM columns, so FOUR tiles are in flight
+//     in the 512-column TMEM: the epilogue of tile k overlaps the MMAs of tiles k+1..k+3.
+//   * PERSISTENT: grid = 4 slices x up to 37 tile groups (148 SMs); group g walks tiles g, g+G, g+2G, ...
+//     The four slice-CTAs of a group read the same A chunks at the same time (L2 hits).
+// Precision: bf16x3 (a_hi w_hi + a_hi w_lo + a_lo w_hi, fp32 accumulate in TMEM), gate math with ex2.approx.
+// Warp roles: warp 0 = TMEM alloc + TMA producer, warp 1 = MMA issuer (one lane), warps 2..9 = epilogue
+// (thread = node row, 16 of the slice's 32 columns each).
+#include "tc_common.cuh"
+
+namespace ddfa {
+namespace tc2 {
+using namespace tcc;
+
+constexpr int kSlices = 4;
+constexpr int kSliceCols = kD / kSlices;                 // 32
+constexpr int kWRows = 3 * kSliceCols;                   // 96 weight rows per slice: [r | z | n]
+constexpr int kWImgBytes = kWRows * 128;                 // 12 KB: one (matrix p, kblock, variant) image
+constexpr int kWSliceBytes = 8 * kWImgBytes;             // 96 KB per slice, index (p*2 + kb)*2 + v
+constexpr int kBiasSlice = 7 * kSliceCols;               // floats per slice
+constexpr int kAStages = 7;
+constexpr int kAccBufs = 4;
+constexpr int kOffA = kWSliceBytes;
+constexpr int kOffBias = kOffA + kAStages * kChunkBytes;
+constexpr int kOffBar = kOffBias + kBiasSlice * 4;
+constexpr int kNumBars = 1 + 2 * kAStages + 2 * kAccBufs;
+constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr int kSmemAlloc = kOffTmemPtr + 16 + 1024;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr size_t kPackedBytes = (size_t)kSlices * kWSliceBytes + (size_t)kSlices * kBiasSlice * 4;
+
+// ---- fp32 [N,128] -> activation image (zero tail rows) ----------------------------------------
+__global__ void __launch_bounds__(256) to_image_kernel(const float *__restrict__ x, int32_t N, uint8_t *__restrict__ image) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread = 8 consecutive columns of a row
+  const int64_t rows = ((int64_t)N + kTileM - 1) / kTileM * kTileM;
+  if (t >= rows * 16) return;
+  const int64_t node = t >> 4;
+  const int col = (int)(t & 15) * 8;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (node < N) {
+    const float4 a = ldg_nc_f4(x + node * kD + col), b = ldg_nc_f4(x + node * kD + col + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  uint4 ph, pl;
+  split8(v, ph, pl);
+  *reinterpret_cast<uint4 *>(image + image_offset(node, col, 0)) = ph;
+  *reinterpret_cast<uint4 *>(image + image_offset(node, col, 1)) = pl;
+}
+
+// ---- per-slice weight images + biases ----------------------------------------------------------
+// packed = [slice j][ (p*2+kb)*2+v ][96 rows x 64 k swizzled]  then  [slice j][7][32] biases
+// local row lr = gate*32 + c  <->  weight row gate*128 + 32 j + c ; p: 0 = w_fold (s part), 1 = w_hh (h part)
+__global__ void __launch_bounds__(256) pack_kernel(const float *__restrict__ w_fold, const float *__restrict__ w_hh,
+                                                   const float *__restrict__ b_fold, const float *__restrict__ b_ih,
+                                                   const float *__restrict__ b_hh, uint8_t *__restrict__ packed) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = kSlices * 2 * 2 * kWRows * 8;  // (j, p, kb, lr, k8)
+  if (t < total) {
+    const int k8 = t & 7;
+    const int lr = (t >> 3) % kWRows;
+    const int rest = (t >> 3) / kWRows;  // (j*2 + p)*2 + kb
+    const int kb = rest & 1, p = (rest >> 1) & 1, j = rest >> 2;
+    const int gate = lr / kSliceCols, c = lr % kSliceCols;
+    const float *W = (p == 0 ? w_fold : w_hh) + (size_t)(gate * kD + j * kSliceCols + c) * kD + kb * 64 + k8 * 8;
+    const float4 a = *reinterpret_cast<const float4 *>(W), b = *reinterpret_cast<const float4 *>(W + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 ph, pl;
+    split8(x, ph, pl);
+    uint8_t *base = packed + (size_t)j * kWSliceBytes + (size_t)((p * 2 + kb) * 2) * kWImgBytes + sw128_offset(lr, k8 * 8);
+    *reinterpret_cast<uint4 *>(base) = ph;
+    *reinterpret_cast<uint4 *>(base + kWImgBytes) = pl;
+  }
+  if (t < kD) {
+    const int j = t / kSliceCols, c = t % kSliceCols;
+    float *bias = reinterpret_cast<float *>(packed + (size_t)kSlices * kWSliceBytes) + j * kBiasSlice;
+    bias[0 * kSliceCols + c] = b_ih[t] + b_hh[t];
+    bias[1 * kSliceCols + c] = b_ih[kD + t] + b_hh[kD + t];
+    bias[2 * kSliceCols + c] = b_ih[2 * kD + t];
+    bias[3 * kSliceCols + c] = b_hh[2 * kD + t];
+    bias[4 * kSliceCols + c] = b_fold[t];
+    bias[5 * kSliceCols + c] = b_fold[kD + t];
+    bias[6 * kSliceCols + c] = b_fold[2 * kD + t];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
+                                                              const float *__restrict__ h, const int32_t *__restrict__ indptr,
+                                                              const uint8_t *__restrict__ packed, int32_t N,
+                                                              float *__restrict__ h_out, uint8_t *__restrict__ h_out_img,
+                                                              float *__restrict__ gates) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kOffBar;
+  const uint32_t w_full = bar0;
+  auto a_full = [&](int i) { return bar0 + 8u * (1 + i); };
+  auto a_empty = [&](int i) { return bar0 + 8u * (1 + kAStages + i); };
+  auto acc_full = [&](int i) { return bar0 + 8u * (1 + 2 * kAStages + i); };
+  auto acc_empty = [&](int i) { return bar0 + 8u * (1 + 2 * kAStages + kAccBufs + i); };
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemPtr);
+  float *bias_s = reinterpret_cast<float *>(smem + kOffBias);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % kSlices;
+  const int group = blockIdx.x / kSlices, num_groups = gridDim.x / kSlices;
+  const int num_tiles = (N + kTileM - 1) / kTileM;
+  const int my_tiles = (num_tiles > group) ? (num_tiles - 1 - group) / num_groups + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < kAccBufs; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 512);
+  }
+  {
+    const float *bias_g = reinterpret_cast<const float *>(packed + (size_t)kSlices * kWSliceBytes) + slice * kBiasSlice;
+    for (int i = threadIdx.x; i < kBiasSlice; i += kThreads) bias_s[i] = bias_g[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer: resident weights once, then the A chunks of every tile =====
+    if (lane == 0 && my_tiles > 0) {
+      mbar_arrive_expect_tx(w_full, kWSliceBytes);
+      for (int i = 0; i < 8; ++i)
+        bulk_g2s(sbase + i * kWImgBytes, packed + (size_t)slice * kWSliceBytes + (size_t)i * kWImgBytes, kWImgBytes, w_full);
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int tile = group + k * num_groups;
+        for (int ci = 0; ci < 8; ++ci, ++cc) {
+          const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+          const int stage = cc % kAStages, use = cc / kAStages;
+          if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          mbar_arrive_expect_tx(a_full(stage), kChunkBytes);
+          const uint8_t *src = (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)(v * 2 + kb) * kChunkBytes;
+          bulk_g2s(sbase + kOffA + stage * kChunkBytes, src, kChunkBytes, a_full(stage));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t kIdesc96 = make_idesc(96), kIdesc64 = make_idesc(64), kIdesc32 = make_idesc(32);
+      mbar_wait(w_full, 0);
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int buf = k % kAccBufs, buse = k / kAccBufs;
+        if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [r 0-31 | z 32-63 | gin 64-95 | ghn 96-127]
+        for (int ci = 0; ci < 8; ++ci, ++cc) {
+          const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+          const int stage = cc % kAStages, use = cc / kAStages;
+          mbar_wait(a_full(stage), use & 1);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + kOffA + stage * kChunkBytes;
+          const int n_wv = (v == 0) ? 2 : 1;   // a_hi pairs with w_hi and w_lo; a_lo with w_hi only
+          for (int wv = 0; wv < n_wv; ++wv) {
+            const uint32_t w_addr = sbase + (uint32_t)(((p * 2 + kb) * 2 + wv) * kWImgBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t ad = make_desc(a_addr + k4 * 32);
+              const bool first = (kb == 0 && v == 0 && wv == 0 && k4 == 0);
+              if (p == 0) {
+                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc96, first ? 0u : 1u);            // r | z | gin
+              } else {
+                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, 1u);                          // r | z
+                umma_f16(d_base + 96, ad, make_desc(w_addr + 64 * 128 + k4 * 32), kIdesc32, first ? 0u : 1u);  // ghn
+              }
+            }
+          }
+          umma_commit(a_empty(stage));
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int lw = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter
+    const int csub = lw >> 2;        // which 16 of the slice's 32 columns
+    const int row = q * 32 + lane;
+    const int gc0 = slice * kSliceCols + csub * 16;   // first global column of this thread
+    const int lc0 = csub * 16;                         // first column inside the slice
+    const size_t plane = (size_t)N * kD;
+    for (int k = 0; k < my_tiles; ++k) {
+      const int tile = group + k * num_groups;
+      const int buf = k % kAccBufs, buse = k / kAccBufs;
+      const int64_t node = (int64_t)tile * kTileM + row;
+      const bool valid = node < N;
+      float hv[16];
+      float deg = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = ldg_nc_f4(h + node * kD + gc0 + i * 4);
+          hv[i * 4 + 0] = t4.x; hv[i * 4 + 1] = t4.y; hv[i * 4 + 2] = t4.z; hv[i * 4 + 3] = t4.w;
+        }
+        deg = (float)(indptr[node + 1] - indptr[node]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = 0.f;
+      }
+      mbar_wait(acc_full(buf), buse & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + lc0);
+      float ar[16], az[16], agi[16], agh[16];
+      tmem_ld16(taddr + 0, ar);
+      tmem_ld16(taddr + 32, az);
+      tmem_ld16(taddr + 64, agi);
+      tmem_ld16(taddr + 96, agh);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has drained its part of the buffer
+      float o_r[16], o_z[16], o_n[16], o_g[16], o_h[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = lc0 + i;
+        const float r = fast_sigmoid(ar[i] + fmaf(deg, bias_s[4 * kSliceCols + c], bias_s[0 * kSliceCols + c]));
+        const float z = fast_sigmoid(az[i] + fmaf(deg, bias_s[5 * kSliceCols + c], bias_s[1 * kSliceCols + c]));
+        const float ghn = agh[i] + bias_s[3 * kSliceCols + c];
+        const float nn = fast_tanh(agi[i] + fmaf(deg, bias_s[6 * kSliceCols + c], bias_s[2 * kSliceCols + c]) + r * ghn);
+        o_r[i] = r; o_z[i] = z; o_n[i] = nn; o_g[i] = ghn;
+        o_h[i] = valid ? fmaf(z, hv[i] - nn, nn) : 0.f;
+      }
+      // h' image (all 128 rows of the tile: rows past N are zero — the weight-gradient GEMM sums over nodes)
+      if (h_out_img) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float x8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x8[i] = o_h[u * 8 + i];
+          uint4 ph, pl;
+          split8(x8, ph, pl);
+          *reinterpret_cast<uint4 *>(h_out_img + image_offset(node, gc0 + u * 8, 0)) = ph;
+          *reinterpret_cast<uint4 *>(h_out_img + image_offset(node, gc0 + u * 8, 1)) = pl;
+        }
+      }
+      if (valid) {
+        float *dst = h_out + node * kD + gc0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4 *>(dst + i * 4) = make_float4(o_h[i * 4], o_h[i * 4 + 1], o_h[i * 4 + 2], o_h[i * 4 + 3]);
+        if (gates) {
+          float *gd = gates + node * kD + gc0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<float4 *>(gd + i * 4) = make_float4(o_r[i * 4], o_r[i * 4 + 1], o_r[i * 4 + 2], o_r[i * 4 + 3]);
+            *reinterpret_cast<float4 *>(gd + plane + i * 4) = make_float4(o_z[i * 4], o_z[i * 4 + 1], o_z[i * 4 + 2], o_z[i * 4 + 3]);
+            *reinterpret_cast<float4 *>(gd + 2 * plane + i * 4) = make_float4(o_n[i * 4], o_n[i * 4 + 1], o_n[i * 4 + 2], o_n[i * 4 + 3]);
+            *reinterpret_cast<float4 *>(gd + 3 * plane + i * 4) = make_float4(o_g[i * 4], o_g[i * 4 + 1], o_g[i * 4 + 2], o_g[i * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc2
+
+size_t act_image_bytes(int64_t n) { return tcc::image_bytes(n); }
+
+int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream) {
+  const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
+  const int64_t total = rows * 16;
+  if (total == 0) return DDFA_OK;
+  tc2::to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, N, static_cast<uint8_t *>(image));
+  DDFA_CHECK_LAUNCH("to_image_kernel");
+  return DDFA_OK;
+}
+
+size_t gru_tc2_workspace_bytes() { return tc2::kPackedBytes; }
+
+int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < tc2::kPackedBytes) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, tc2::kPackedBytes);
+    return DDFA_ERR_WORKSPACE;
+  }
+  const int total = tc2::kSlices * 2 * 2 * tc2::kWRows * 8;
+  tc2::pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, b_fold, b_ih, b_hh, static_cast<uint8_t *>(workspace));
+  DDFA_CHECK_LAUNCH("tc2::pack_kernel");
+  return DDFA_OK;
+}
+
+int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
+                     void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < tc2::kPackedBytes) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, tc2::kPackedBytes);
+    return DDFA_ERR_WORKSPACE;
+  }
+  DDFA_CUDA(cudaFuncSetAttribute(tc2::gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemAlloc));
+  const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
+  int groups = kNumSMs / tc2::kSlices;
+  if (groups > tiles) groups = tiles;
+  tc2::gru_fwd_kernel<<<groups * tc2::kSlices, tc2::kThreads, tc2::kSmemAlloc, stream>>>(
+      static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr, static_cast<const uint8_t *>(workspace), N,
+      h_out, static_cast<uint8_t *>(h_out_img), save_gates);
+  DDFA_CHECK_LAUNCH("tc2::gru_fwd_kernel");
+  return DDFA_OK;
+}
+
+}  // namespace ddfa

@@ -1,0 +1,149 @@
+// Shared device helpers for the tcgen05 kernels: mbarrier, TMA bulk copy, UMMA descriptors, TMEM access,
+// the bf16 hi/lo operand split and the "activation image" layout.
+//
+// Activation image (tcgen05 engine only): an [N,128] fp32 matrix X is also kept as MMA-ready operands:
+//   image[tile = node/128][variant v: 0 = hi, 1 = lo][kblock kb: cols 0-63 | 64-127] = one 16 KB chunk,
+//   chunk = [128 rows x 64 bf16], rows 128 B apart, 16-byte units XOR-swizzled by (row & 7)
+//   (the UMMA canonical K-major SWIZZLE_128B layout; read as "MN-major" it is the [col][node] operand of the
+//   weight-gradient GEMM).  hi = bf16(x), lo = bf16(x - hi).  Rows past N are zero.  64 KB per 128-node tile —
+//   exactly the bytes of the fp32 matrix — so producer kernels write it instead of / next to fp32 and the GEMM
+//   kernels stream it with plain 1-D TMA bulk copies (no in-kernel conversion pass).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ddfa {
+namespace tcc {
+
+constexpr int kD = 128;
+constexpr int kTileM = 128;
+constexpr int kChunkBytes = 128 * 128;        // one [128 x 64] bf16 chunk
+constexpr int kImageTileBytes = 4 * kChunkBytes;  // [hi|lo][kb0|kb1] = 64 KB per 128-node tile
+
+__host__ __device__ __forceinline__ size_t image_bytes(int64_t n) { return (size_t)((n + kTileM - 1) / kTileM) * kImageTileBytes; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+
+// Instruction descriptor, kind::f16: D = f32, A = B = bf16, M = 128; N and operand majors as given.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major = false, bool b_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: start>>4 | LBO=1 | SBO = 1024 B | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 64-element MN blocks, SBO = 1024 B between 8-row K groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B chunk
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+// byte offset of element (node, col) variant v inside an activation image
+__host__ __device__ __forceinline__ size_t image_offset(int64_t node, int col, int v) {
+  return (size_t)(node / kTileM) * kImageTileBytes + (size_t)((v * 2 + (col >> 6)) * kChunkBytes) +
+         sw128_offset((int)(node % kTileM), col & 63);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// 4 consecutive fp32 -> packed 4 x bf16 hi and 4 x bf16 lo (8 bytes each)
+__device__ __forceinline__ void split4(const float4 &x, uint2 &ph, uint2 &pl) {
+  __nv_bfloat16 hi[4], lo[4];
+  split_bf16(x.x, hi[0], lo[0]); split_bf16(x.y, hi[1], lo[1]);
+  split_bf16(x.z, hi[2], lo[2]); split_bf16(x.w, hi[3], lo[3]);
+  ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+  ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+  pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+  pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+}
+// 8 consecutive fp32 (one 16-byte bf16 unit) -> hi / lo uint4
+__device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl) {
+  uint2 h0, l0, h1, l1;
+  split4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
+  split4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
+  ph = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  pl = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.f * x);  // inf for large x -> 1 - 0 = 1 ; 0 for very negative x -> -1
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+}  // namespace tcc
+}  // namespace ddfa

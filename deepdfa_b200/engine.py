@@ -179,6 +179,18 @@ class Workspace:
             self._bufs[name] = buf
         return buf[:numel].view(*shape)
 
+    def get_zeroed(self, name, shape, dtype=torch.float32):
+        """Like get(), but the backing store is zero-filled when it is (re)allocated — activation images rely
+        on never containing non-finite garbage in their padding rows."""
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.zeros(max(numel, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = buf
+        return buf[:numel].view(*shape)
+
 
 class _FreshAlloc:
     """Allocation policy of the autograd path: every buffer is a fresh tensor (caching allocator)."""
@@ -188,6 +200,9 @@ class _FreshAlloc:
 
     def get(self, name, shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def get_zeroed(self, name, shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
 
 
 def node_indices(g: BatchedCFG, concat_all_absdf: bool, feature_key: str, device) -> List[torch.Tensor]:
@@ -229,24 +244,36 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     b_fold = alloc.get("b_fold", (3 * D,))
     L.call("ddfa_fold_weights_fwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), D, _p(w_fold), _p(b_fold), st)
 
-    ws_bytes = L.call("ddfa_gru_step_workspace_bytes", N, D, engine)
+    use_images = engine == ENGINE_TCGEN05     # activations travel as MMA-ready bf16 hi/lo images (include/ddfa_b200.h)
+    ws_bytes = L.call("ddfa_gru_step_workspace_bytes", 0 if use_images else N, D, engine)
     ws = alloc.get("gru_ws", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare", _p(w_fold), _p(b_fold), _p(params.b_ih), _p(params.w_hh), _p(params.b_hh), D, engine,
            _p(ws), ws_bytes, st)
     hs, ss, gs = [x], [], []
     h_cur = x
+    if use_images:
+        img_bytes = L.call("ddfa_act_image_bytes", N)
+        s_img = alloc.get_zeroed("s_img", (img_bytes,), torch.uint8)
+        h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(2)]
+        L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
     for t in range(T):
         if training:
             s_t = alloc.get(f"s{t}", (N, D))
             h_next = alloc.get(f"h{t + 1}", (N, D))
             g_t = alloc.get(f"gates{t}", (4, N, D))
         else:
-            s_t = alloc.get("s", (N, D))
+            s_t = None if use_images else alloc.get("s", (N, D))
             h_next = alloc.get(f"hpp{t % 2}", (N, D))
             g_t = None
-        _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
-        _call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
-               _p(params.w_hh), _p(params.b_hh), N, D, _p(h_next), _p(g_t), _p(ws), ws_bytes, engine, st)
+        if use_images:
+            # round 1: the weight-gradient kernel still reads fp32 s, so training keeps the fp32 copy next to the image
+            _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_img), _p(s_t), st, tag="gather_fwd")
+            _call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_imgs[t % 2]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
+                  _p(h_imgs[(t + 1) % 2]) if t + 1 < T else None, _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
+        else:
+            _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
+            _call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
+                  _p(params.w_hh), _p(params.b_hh), N, D, _p(h_next), _p(g_t), _p(ws), ws_bytes, engine, st)
         if training:
             hs.append(h_next); ss.append(s_t); gs.append(g_t)
         h_cur = h_next

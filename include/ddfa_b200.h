@@ -130,6 +130,25 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
                       const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                       int32_t num_nodes, int32_t dim, float *h_out, float *save_gates,
                       void *workspace, size_t workspace_bytes, int engine, void *stream);
+/* ---- tcgen05 engine: activation images -------------------------------------------------------
+ * With the tcgen05 engine (D == 128) activations travel between kernels as MMA-ready operands next to /
+ * instead of fp32: image[node/128][hi|lo][cols 0-63 | 64-127] = 16 KB chunks of [128 rows x 64 bf16] in the
+ * UMMA K-major SWIZZLE_128B layout, hi = bf16(x), lo = bf16(x - hi); rows past N are zero; the image has
+ * exactly the size of the fp32 matrix rounded up to 128 rows (ddfa_act_image_bytes).  Producers:
+ * ddfa_act_to_image (from fp32, used for h_0 = x), ddfa_gather_sum_image (s_t), ddfa_gru_step_fwd_image
+ * (h_{t+1}).  Allocate images zero-initialised. */
+size_t ddfa_act_image_bytes(int64_t num_nodes);
+int ddfa_act_to_image(const float *x, int32_t num_nodes, int32_t dim, void *image, void *stream);
+/* K3 writing the image of s (and, when out_f32 != NULL, also the fp32 matrix). */
+int ddfa_gather_sum_image(const int32_t *indptr, const int32_t *indices, const float *h,
+                          int32_t num_nodes, int32_t dim, void *out_image, float *out_f32, void *stream);
+/* K4 on images: s_image / h_image in, h (fp32, for the z*h term) in; h_out fp32 and (optional) its image out.
+ * workspace = the buffer prepared by ddfa_gru_step_prepare(engine = TCGEN05). */
+int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const float *h,
+                            const int32_t *indptr, int32_t num_nodes, int32_t dim, float *h_out,
+                            void *h_out_image, float *save_gates, const void *workspace,
+                            size_t workspace_bytes, void *stream);
+
 /* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
  * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
  * Accumulated (+=): dw_fold[3D,D], db_fold[3D], db_ih[3D], dw_hh[3D,D], db_hh[3D].

@@ -125,6 +125,48 @@ def main():
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 10 * 1e3
         print(f"timing bwd {name} N={N2}: {us:.1f} us/step ({2 * 2.0 * N2 * 6 * D * D / us / 1e6:.1f} TFLOP/s algorithmic)")
+    # image-path kernels alone (what the training driver calls)
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+    from deepdfa_b200 import synth
+    from deepdfa_b200.engine import prepare_graph
+    for graphs in (256, 1024):
+        gb = synth.make_batch(graphs, 150, seed=1)
+        dgb = prepare_graph(gb, DEV)
+        Nb = gb.num_nodes()
+        L = lib()
+        hb = torch.tanh(torch.randn(Nb, D, device=DEV)); ob = torch.empty(Nb, D, device=DEV); gt = torch.empty(4, Nb, D, device=DEV)
+        ib = L.call("ddfa_act_image_bytes", Nb)
+        s_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); h_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+        o_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); s_f = torch.empty(Nb, D, device=DEV)
+        wsb = L.call("ddfa_gru_step_workspace_bytes", 0, D, ENGINE_TCGEN05)
+        ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_gru_step_prepare", _p(wf4), _p(bf4), _p(bih4), _p(whh4), _p(bhh4), D, ENGINE_TCGEN05, _p(ws), wsb, _stream_ptr())
+        L.call("ddfa_act_to_image", _p(hb), Nb, D, _p(h_img), _stream_ptr())
+        t_g = timeit(lambda: L.call("ddfa_gather_sum", _p(dgb.indptr), _p(dgb.indices), _p(hb), Nb, D, _p(s_f), 0, _stream_ptr()))
+        t_gi = timeit(lambda: L.call("ddfa_gather_sum_image", _p(dgb.indptr), _p(dgb.indices), _p(hb), Nb, D, _p(s_img), None, _stream_ptr()))
+        t_gif = timeit(lambda: L.call("ddfa_gather_sum_image", _p(dgb.indptr), _p(dgb.indices), _p(hb), Nb, D, _p(s_img), _p(s_f), _stream_ptr()))
+        # check the image against the fp32 gather through the fp32-input reference path
+        t_ti = timeit(lambda: L.call("ddfa_act_to_image", _p(hb), Nb, D, _p(h_img), _stream_ptr()))
+        t_f0 = timeit(lambda: L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hb), _p(dgb.indptr), Nb, D, _p(ob), None, None, _p(ws), wsb, _stream_ptr()))
+        t_f1 = timeit(lambda: L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hb), _p(dgb.indptr), Nb, D, _p(ob), _p(o_img), _p(gt), _p(ws), wsb, _stream_ptr()))
+        fl = 2.0 * Nb * 6 * D * D
+        print(f"image path N={Nb}: gather fp32 {t_g:.1f} us | gather->image {t_gi:.1f} us | gather->image+fp32 {t_gif:.1f} us | to_image {t_ti:.1f} us | "
+              f"gru_fwd_image infer {t_f0:.1f} us ({fl / t_f0 / 1e6:.0f} TFLOP/s alg) | train(+img+gates) {t_f1:.1f} us ({fl / t_f1 / 1e6:.0f} TFLOP/s alg)")
+        # correctness of the image chain vs the fp32-in entry point
+        ref_out = torch.empty(Nb, D, device=DEV)
+        wsb2 = L.call("ddfa_gru_step_workspace_bytes", Nb, D, ENGINE_TCGEN05); ws2 = torch.zeros(wsb2, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_gru_step_prepare", _p(wf4), _p(bf4), _p(bih4), _p(whh4), _p(bhh4), D, ENGINE_TCGEN05, _p(ws2), wsb2, _stream_ptr())
+        L.call("ddfa_gru_step_fwd", _p(s_f), _p(hb), _p(dgb.indptr), _p(wf4), _p(bf4), _p(bih4), _p(whh4), _p(bhh4), Nb, D, _p(ref_out), None, _p(ws2), wsb2, ENGINE_TCGEN05, _stream_ptr())
+        torch.cuda.synchronize()
+        print(f"   image chain vs fp32-in entry: max diff {float((ob - ref_out).abs().max()):.3e}")
     for eng, name in ((ENGINE_TCGEN05, "tcgen05"), (ENGINE_SIMT, "simt")):
         N2 = 38400
         s5 = torch.randn(N2, D, device=DEV); h5 = torch.tanh(torch.randn(N2, D, device=DEV))
