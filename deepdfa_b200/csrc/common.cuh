@@ -47,12 +47,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // sgemm.cu — SIMT fp32 GEMM, C = alpha*op(A)op(B) + beta*C (row-major)
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
           float beta, float *C, int ldc, int split_k, cudaStream_t stream);
-// gru_tc.cu — tcgen05 engine entry points (D == 128)
-bool gru_tc_available();
-size_t gru_tc_workspace_bytes(int32_t N, int32_t D);
-int gru_tc_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, int32_t D,
-                   void *workspace, size_t workspace_bytes, cudaStream_t stream);
-// gru_tc_fwd.cu — forward v2 (weight-stationary, activation images)
+// gru_tc_fwd.cu — tcgen05 engine, forward (D == 128; weight-stationary, activation images)
 size_t act_image_bytes(int64_t n);
 int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
 size_t gru_tc2_workspace_bytes();
@@ -60,15 +55,12 @@ int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
                      void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream);
-size_t gru_tc_bwd_workspace_bytes(int32_t N, int32_t D);
-int gru_tc_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, void *workspace, size_t workspace_bytes,
-                       cudaStream_t stream);
-int gru_tc_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates, const int32_t *indptr, int32_t N,
-                    int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
-                    void *workspace, size_t workspace_bytes, cudaStream_t stream);
-int gru_tc_step_fwd(const float *s, const float *h, const int32_t *indptr, const float *w_fold, const float *b_fold,
-                    const float *b_ih, const float *w_hh, const float *b_hh, int32_t N, int32_t D, float *h_out,
-                    float *save_gates, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+// gru_tc_bwd.cu — tcgen05 engine, backward (gate backward -> q images, dgrad, wgrad)
+size_t gru_tc2_bwd_workspace_bytes(int32_t N);
+int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
+                     float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
   float4 v;

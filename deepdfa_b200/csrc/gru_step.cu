@@ -7,7 +7,7 @@
 // which equals GRUCell(a, h) for a_v = sum_{u->v} (W h_u + b).
 //
 // This file holds the engine dispatch, the SIMT engine (fp32 FFMA GEMMs from sgemm.cu + fused
-// gate kernels) and the weight-folding helpers.  The tcgen05 engine lives in gru_tc.cu.
+// gate kernels) and the weight-folding helpers.  The tcgen05 engine lives in gru_tc_fwd.cu / gru_tc_bwd.cu.
 #include "common.cuh"
 
 namespace ddfa {
@@ -291,8 +291,22 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
 
 size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
   if (N < 0 || D <= 0) return 0;
-  if (engine == DDFA_ENGINE_TCGEN05) return ddfa::gru_tc_bwd_workspace_bytes(N, D);
+  // tcgen05: [transposed weight images][q images x4][h image] + [s image] (the last one only for the fp32-s entry)
+  if (engine == DDFA_ENGINE_TCGEN05) return D == 128 ? ddfa::gru_tc2_bwd_workspace_bytes(N) + ddfa::act_image_bytes(N) : 16;
   return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // dgi | dgh
+}
+
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates, const int32_t *indptr,
+                            int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+                            float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_bwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(dh_out && h && s_image && gates && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
+               "ddfa_gru_step_bwd_image: NULL pointer");
+  DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image: dh must not alias dh_out");
+  return gru_tc2_step_bwd(dh_out, h, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+                          workspace_bytes, as_stream(stream_));
 }
 
 int ddfa_gru_step_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, int engine, void *workspace,
@@ -302,7 +316,7 @@ int ddfa_gru_step_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D,
   if (rc) return rc;
   if (engine == DDFA_ENGINE_SIMT) return DDFA_OK;
   DDFA_REQUIRE(w_fold && w_hh, "ddfa_gru_step_prepare_bwd: NULL pointer");
-  return gru_tc_prepare_bwd(w_fold, w_hh, D, workspace, workspace_bytes, as_stream(stream_));
+  return gru_tc2_prepare_bwd(w_fold, w_hh, workspace, workspace_bytes, as_stream(stream_));
 }
 
 int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const float *gates, const int32_t *indptr,
@@ -322,9 +336,14 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
     set_error("ddfa_gru_step_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     return DDFA_ERR_WORKSPACE;
   }
-  if (engine == DDFA_ENGINE_TCGEN05)
-    return gru_tc_step_bwd(dh_out, h, s, gates, indptr, N, D, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
-                           workspace_bytes, stream);
+  if (engine == DDFA_ENGINE_TCGEN05) {
+    // fp32-s convenience path (tests, tools): build the s image at the end of the workspace, then the image kernels
+    void *s_img = static_cast<uint8_t *>(workspace) + gru_tc2_bwd_workspace_bytes(N);
+    rc = act_to_image(s, N, s_img, stream);
+    if (rc) return rc;
+    return gru_tc2_step_bwd(dh_out, h, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+                            workspace_bytes, stream);
+  }
   float *dgi = static_cast<float *>(workspace);
   float *dgh = dgi + (size_t)N * 3 * D;
   dim3 block(D / 4, 256 / (D / 4) > 0 ? 256 / (D / 4) : 1);

@@ -1,0 +1,448 @@
+// tcgen05 engine, backward of one GRU step (D == 128), v2 — activation images in, TMA-fed, persistent.
+//
+//   (1) gate_bwd_image_kernel   q_r, q_z, q_n, q_nr  <-  (dh', h, r, z, n, gh_n)      elementwise, HBM-bound
+//         writes the four q matrices and h_t as activation IMAGES + the bias gradients (column sums)
+//   (2) dgrad_kernel            ds = [q_r q_z q_n] W' ;  dh = dh' * z + [q_r q_z q_nr] Whh      K = 3D
+//         weight-stationary like the forward kernel: a CTA owns 32 output columns of ds AND dh; the bf16 hi/lo
+//         images of the transposed weight slices (96 KB) stay in shared memory, the q images stream through a
+//         TMA ring, accumulators [ds | dh] = 64 TMEM columns per tile, four tiles in flight.
+//   (3) wgrad_kernel            dW' += [q_r q_z q_n]^T s ;  dWhh += [q_r q_z q_nr]^T h            K = nodes
+//         both operands are read "MN-major" straight from the images (64-node half tiles, 32 KB per operand,
+//         6-slot TMA ring); a CTA keeps its [384 x 128] fp32 partial sum in TMEM over all its tiles and adds it to
+//         the global gradient with RED.ADD at the end.
+// Precision: bf16x3 everywhere (hi*hi + hi*lo + lo*hi), fp32 accumulate.
+#include "tc_common.cuh"
+
+namespace ddfa {
+namespace tc2b {
+using namespace tcc;
+
+constexpr int kSlices = 4, kSliceCols = 32;
+constexpr int kThreads = 320, kEpiWarps = 8;
+
+// =================================================================================================
+// (1) gate backward -> q images, h image, bias gradients
+// =================================================================================================
+constexpr int kGbRows = 64;  // node rows per CTA (8 warps x 8 rows)
+__global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
+                                                             const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                                             int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
+                                                             uint8_t *__restrict__ h_img, float *__restrict__ db_fold,
+                                                             float *__restrict__ db_ih, float *__restrict__ db_hh) {
+  __shared__ float red[7 * kD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = lane * 4;
+  const size_t plane = (size_t)N * kD;
+  for (int i = threadIdx.x; i < 7 * kD; i += 256) red[i] = 0.f;
+  __syncthreads();
+  float4 sum[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t row0 = (int64_t)blockIdx.x * kGbRows + warp * 8;
+  const int64_t Npad = ((int64_t)N + kTileM - 1) / kTileM * kTileM;
+#pragma unroll 2
+  for (int r = 0; r < 8; ++r) {
+    const int64_t node = row0 + r;
+    if (node >= Npad) break;
+    float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr, hv = qr;
+    if (node < N) {
+      const size_t off = (size_t)node * kD + col;
+      const float4 d = ldg_nc_f4(dh_out + off);
+      hv = ldg_nc_f4(h + off);
+      const float4 rr = ldg_nc_f4(gates + off);
+      const float4 zz = ldg_nc_f4(gates + plane + off);
+      const float4 nn = ldg_nc_f4(gates + 2 * plane + off);
+      const float4 gh = ldg_nc_f4(gates + 3 * plane + off);
+      const float deg = (float)(indptr[node + 1] - indptr[node]);
+#define BWDQ(f)                                                  \
+  {                                                              \
+    const float dz_ = d.f * (hv.f - nn.f);                       \
+    const float dn_ = d.f * (1.f - zz.f);                        \
+    qn.f = dn_ * (1.f - nn.f * nn.f);                            \
+    qz.f = dz_ * zz.f * (1.f - zz.f);                            \
+    qr.f = qn.f * gh.f * rr.f * (1.f - rr.f);                    \
+    qnr.f = qn.f * rr.f;                                         \
+  }
+      BWDQ(x) BWDQ(y) BWDQ(z) BWDQ(w)
+#undef BWDQ
+      f4_add(sum[0], qr); f4_add(sum[1], qz); f4_add(sum[2], qn); f4_add(sum[3], qnr);
+      f4_fma(sum[4], deg, qr); f4_fma(sum[5], deg, qz); f4_fma(sum[6], deg, qn);
+    }
+    // images: rows N..Npad-1 are written as zeros (the weight-gradient GEMM sums over all 128 rows of a tile)
+    const size_t o_hi = image_offset(node, col, 0), o_lo = image_offset(node, col, 1);
+    uint2 ph, pl;
+    split4(qr, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 0 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 0 * img_stride + o_lo) = pl;
+    split4(qz, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_lo) = pl;
+    split4(qn, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_lo) = pl;
+    split4(qnr, ph, pl); *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_lo) = pl;
+    split4(hv, ph, pl);  *reinterpret_cast<uint2 *>(h_img + o_hi) = ph;                  *reinterpret_cast<uint2 *>(h_img + o_lo) = pl;
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    atomicAdd(&red[i * kD + col + 0], sum[i].x); atomicAdd(&red[i * kD + col + 1], sum[i].y);
+    atomicAdd(&red[i * kD + col + 2], sum[i].z); atomicAdd(&red[i * kD + col + 3], sum[i].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 7 * kD; i += 256) {
+    const float v_ = red[i];
+    const int which = i >> 7, c_ = i & 127;
+    // 0:S(q_r) 1:S(q_z) 2:S(q_n) 3:S(q_nr) 4:S(deg q_r) 5:S(deg q_z) 6:S(deg q_n)
+    if (which == 0) { atomicAdd(db_ih + c_, v_); atomicAdd(db_hh + c_, v_); }
+    else if (which == 1) { atomicAdd(db_ih + kD + c_, v_); atomicAdd(db_hh + kD + c_, v_); }
+    else if (which == 2) atomicAdd(db_ih + 2 * kD + c_, v_);
+    else if (which == 3) atomicAdd(db_hh + 2 * kD + c_, v_);
+    else atomicAdd(db_fold + (which - 4) * kD + c_, v_);
+  }
+}
+
+// =================================================================================================
+// (2) dgrad
+// =================================================================================================
+constexpr int kDgWImgBytes = 64 * 128;                  // [rows 0-31: W'^T slice | rows 32-63: Whh^T slice] x 64 k = 8 KB
+constexpr int kDgWSliceBytes = 12 * kDgWImgBytes;       // (gate*2 + kb)*2 + v  -> 96 KB
+constexpr int kDgAStages = 7;
+constexpr int kDgAccBufs = 4;
+constexpr int kDgOffA = kDgWSliceBytes;
+constexpr int kDgOffBar = kDgOffA + kDgAStages * kChunkBytes;
+constexpr int kDgNumBars = 1 + 2 * kDgAStages + 2 * kDgAccBufs;
+constexpr int kDgOffTmemPtr = kDgOffBar + kDgNumBars * 8;
+constexpr int kDgSmemAlloc = kDgOffTmemPtr + 16 + 1024;
+constexpr size_t kDgPackedBytes = (size_t)kSlices * kDgWSliceBytes;
+
+// packed[j][(g*2+kb)*2+v][64 rows x 64 k]: row n < 32: w_fold[g*128 + kb*64 + k][32j + n] ; row 32+n: w_hh[...][32j + n]
+__global__ void __launch_bounds__(256) dgrad_pack_kernel(const float *__restrict__ w_fold, const float *__restrict__ w_hh,
+                                                         uint8_t *__restrict__ packed) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = kSlices * 3 * 2 * 8 * 64;   // (j, g, kb, k8, row): row fastest -> coalesced source reads
+  if (t >= total) return;
+  const int row = t & 63, k8 = (t >> 6) & 7, kb = (t >> 9) & 1;
+  const int g = (t >> 10) % 3, j = (t >> 10) / 3;
+  const float *W = (row < 32) ? w_fold : w_hh;
+  const int n = row & 31;
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = W[(size_t)(g * kD + kb * 64 + k8 * 8 + i) * kD + j * kSliceCols + n];
+  uint4 ph, pl;
+  split8(x, ph, pl);
+  uint8_t *base = packed + (size_t)j * kDgWSliceBytes + (size_t)((g * 2 + kb) * 2) * kDgWImgBytes + sw128_offset(row, k8 * 8);
+  *reinterpret_cast<uint4 *>(base) = ph;
+  *reinterpret_cast<uint4 *>(base + kDgWImgBytes) = pl;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
+                                                            const float *__restrict__ dh_out, const float *__restrict__ gates,
+                                                            const uint8_t *__restrict__ packed, int32_t N,
+                                                            float *__restrict__ ds, float *__restrict__ dh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kDgOffBar;
+  const uint32_t w_full = bar0;
+  auto a_full = [&](int i) { return bar0 + 8u * (1 + i); };
+  auto a_empty = [&](int i) { return bar0 + 8u * (1 + kDgAStages + i); };
+  auto acc_full = [&](int i) { return bar0 + 8u * (1 + 2 * kDgAStages + i); };
+  auto acc_empty = [&](int i) { return bar0 + 8u * (1 + 2 * kDgAStages + kDgAccBufs + i); };
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kDgOffTmemPtr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % kSlices;
+  const int group = blockIdx.x / kSlices, num_groups = gridDim.x / kSlices;
+  const int num_tiles = (N + kTileM - 1) / kTileM;
+  const int my_tiles = (num_tiles > group) ? (num_tiles - 1 - group) / num_groups + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < kDgAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < kDgAccBufs; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0 && my_tiles > 0) {
+      mbar_arrive_expect_tx(w_full, kDgWSliceBytes);
+      for (int i = 0; i < 12; ++i)
+        bulk_g2s(sbase + i * kDgWImgBytes, packed + (size_t)slice * kDgWSliceBytes + (size_t)i * kDgWImgBytes, kDgWImgBytes, w_full);
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int tile = group + k * num_groups;
+        for (int ci = 0; ci < 16; ++ci, ++cc) {       // ci = (m*2 + kb)*2 + v ; m: q_r, q_z, q_n, q_nr
+          const int m = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+          const int stage = cc % kDgAStages, use = cc / kDgAStages;
+          if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          mbar_arrive_expect_tx(a_full(stage), kChunkBytes);
+          const uint8_t *src = q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes + (size_t)(v * 2 + kb) * kChunkBytes;
+          bulk_g2s(sbase + kDgOffA + stage * kChunkBytes, src, kChunkBytes, a_full(stage));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t kIdesc64 = make_idesc(64), kIdesc32 = make_idesc(32);
+      mbar_wait(w_full, 0);
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
+        if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)buf * 64u;   // [ds 0-31 | dh 32-63]
+        for (int ci = 0; ci < 16; ++ci, ++cc) {
+          const int m = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+          const int g = m < 2 ? m : 2;
+          const int stage = cc % kDgAStages, use = cc / kDgAStages;
+          mbar_wait(a_full(stage), use & 1);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + kDgOffA + stage * kChunkBytes;
+          const int n_wv = (v == 0) ? 2 : 1;
+          for (int wv = 0; wv < n_wv; ++wv) {
+            const uint32_t w_addr = sbase + (uint32_t)(((g * 2 + kb) * 2 + wv) * kDgWImgBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t ad = make_desc(a_addr + k4 * 32);
+              if (m < 2) {        // q_r, q_z feed both ds and dh: one N = 64 MMA
+                const bool first = (ci == 0 && wv == 0 && k4 == 0);
+                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, first ? 0u : 1u);
+              } else if (m == 2)  // q_n -> ds only (rows 0..31 of the image)
+                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc32, 1u);
+              else                // q_nr -> dh only (rows 32..63)
+                umma_f16(d_base + 32, ad, make_desc(w_addr + 32 * 128 + k4 * 32), kIdesc32, 1u);
+            }
+          }
+          umma_commit(a_empty(stage));
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    const int lw = warp - 2, q = warp & 3, csub = lw >> 2;
+    const int row = q * 32 + lane;
+    const int gc0 = slice * kSliceCols + csub * 16, lc0 = csub * 16;
+    const size_t plane = (size_t)N * kD;
+    float4 dn[4], zn[4];
+    auto prefetch = [&](int kk) {
+      const int64_t nd = (int64_t)(group + kk * num_groups) * kTileM + row;
+      if (kk < my_tiles && nd < N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dn[i] = ldg_nc_f4(dh_out + nd * kD + gc0 + i * 4);
+          zn[i] = ldg_nc_f4(gates + plane + nd * kD + gc0 + i * 4);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dn[i] = zn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    prefetch(0);
+    for (int k = 0; k < my_tiles; ++k) {
+      const int tile = group + k * num_groups;
+      const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
+      const int64_t node = (int64_t)tile * kTileM + row;
+      float4 dv[4], zv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dv[i] = dn[i]; zv[i] = zn[i]; }
+      prefetch(k + 1);
+      mbar_wait(acc_full(buf), buse & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + lc0);
+      float a_ds[16], a_dh[16];
+      tmem_ld16(taddr + 0, a_ds);
+      tmem_ld16(taddr + 32, a_dh);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (node < N) {
+        float *pds = ds + node * kD + gc0;
+        float *pdh = dh + node * kD + gc0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4 *>(pds + i * 4) = make_float4(a_ds[i * 4], a_ds[i * 4 + 1], a_ds[i * 4 + 2], a_ds[i * 4 + 3]);
+          *reinterpret_cast<float4 *>(pdh + i * 4) =
+              make_float4(fmaf(dv[i].x, zv[i].x, a_dh[i * 4]), fmaf(dv[i].y, zv[i].y, a_dh[i * 4 + 1]),
+                          fmaf(dv[i].z, zv[i].z, a_dh[i * 4 + 2]), fmaf(dv[i].w, zv[i].w, a_dh[i * 4 + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =================================================================================================
+// (3) wgrad
+// =================================================================================================
+constexpr int kWgTileK = 64;                              // nodes per half tile
+constexpr int kWgPiece = kWgTileK * 128;                  // 8 KB: rows 0-63 or 64-127 of one image chunk
+constexpr int kWgSlotBytes = 4 * kWgPiece;                // [hi|lo][col block] = 32 KB per operand
+constexpr int kWgSlots = 6;
+constexpr int kWgOffBar = kWgSlots * kWgSlotBytes;        // 192 KB
+constexpr int kWgNumBars = 2 * kWgSlots + 1;
+constexpr int kWgOffTmemPtr = kWgOffBar + kWgNumBars * 8;
+constexpr int kWgSmemAlloc = kWgOffTmemPtr + 16 + 1024;
+
+// grid = (ctas, 2): blockIdx.y = role: 0: A in {q_r,q_z,q_n}, B = s image -> dW' ; 1: A in {q_r,q_z,q_nr}, B = h image -> dWhh
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
+                                                            const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
+                                                            int32_t N, float *__restrict__ dw_fold, float *__restrict__ dw_hh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kWgOffBar;
+  auto full_bar = [&](int i) { return bar0 + 8u * i; };
+  auto empty_bar = [&](int i) { return bar0 + 8u * (kWgSlots + i); };
+  const uint32_t acc_bar = bar0 + 8u * (2 * kWgSlots);
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kWgOffTmemPtr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = blockIdx.y;
+  const int num_tiles = 2 * ((N + kTileM - 1) / kTileM);   // 64-node half tiles (images are padded to 128 rows with zeros)
+  const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgSlots; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    mbar_init(acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // TMA producer: per half tile the operand sequence B_t, A_0, A_1, A_2 (each 4 x 8 KB pieces of an image tile)
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int ht = (int)blockIdx.x + i * (int)gridDim.x;
+        const size_t tile_off = (size_t)(ht >> 1) * kImageTileBytes + (size_t)(ht & 1) * kWgPiece;
+        for (int w = 0; w < 4; ++w) {
+          const int j = 4 * i + w, slot = j % kWgSlots;
+          if (j >= kWgSlots) mbar_wait(empty_bar(slot), ((j / kWgSlots) - 1) & 1);
+          const uint8_t *src;
+          if (w == 0) src = (role == 0) ? s_img : h_img;
+          else {
+            const int pl = (w == 3) ? (role == 0 ? 2 : 3) : (w - 1);
+            src = q_img + (size_t)pl * img_stride;
+          }
+          mbar_arrive_expect_tx(full_bar(slot), kWgSlotBytes);
+          for (int c = 0; c < 4; ++c)   // c = v*2 + kb
+            bulk_g2s(sbase + slot * kWgSlotBytes + c * kWgPiece, src + tile_off + (size_t)c * kChunkBytes, kWgPiece, full_bar(slot));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t kIdescMN = make_idesc(128, true, true);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int jb = 4 * i, slot_b = jb % kWgSlots;
+        mbar_wait(full_bar(slot_b), (jb / kWgSlots) & 1);
+        for (int g = 0; g < 3; ++g) {
+          const int ja = jb + 1 + g, slot_a = ja % kWgSlots;
+          mbar_wait(full_bar(slot_a), (ja / kWgSlots) & 1);
+          tc_fence_after();
+          const uint32_t a0 = sbase + slot_a * kWgSlotBytes, b0 = sbase + slot_b * kWgSlotBytes;
+          const uint32_t d_addr = tmem_base + (uint32_t)g * 128u;
+#pragma unroll
+          for (int k16 = 0; k16 < kWgTileK / 16; ++k16) {
+            const uint32_t koff = (uint32_t)k16 * 2048u;     // 16 nodes = two 8-node groups of 1024 B
+            const uint32_t vs = 2 * kWgPiece;                // hi -> lo variant
+            const uint32_t acc = (i > 0 || k16 > 0) ? 1u : 0u;
+            umma_f16(d_addr, make_desc_mn(a0 + koff, kWgPiece), make_desc_mn(b0 + koff, kWgPiece), kIdescMN, acc);            // a_hi b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + vs + koff, kWgPiece), make_desc_mn(b0 + koff, kWgPiece), kIdescMN, 1u);        // a_lo b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + koff, kWgPiece), make_desc_mn(b0 + vs + koff, kWgPiece), kIdescMN, 1u);        // a_hi b_lo
+          }
+          umma_commit(empty_bar(slot_a));
+        }
+        umma_commit(empty_bar(slot_b));
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (my_tiles > 0) {
+    const int lw = warp - 2, qd = warp & 3, chalf = lw >> 2;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int m = qd * 32 + lane;
+    float *dW = (role == 0) ? dw_fold : dw_hh;
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col0 = chalf * 64 + cc * 16;
+        float a[16];
+        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + col0), a);
+        tmem_ld_wait();
+        float *dst = dW + (size_t)(g * 128 + m) * kD + col0;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) atomicAdd(dst + x, a[x]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc2b
+
+// workspace = [dgrad per-slice transposed weight images (384 KB)][q images x4][h image]
+size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N); }
+
+int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < tc2b::kDgPackedBytes) {
+    set_error("tcgen05 engine (bwd): workspace too small");
+    return DDFA_ERR_WORKSPACE;
+  }
+  const int total = tc2b::kSlices * 3 * 2 * 8 * 64;
+  tc2b::dgrad_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, static_cast<uint8_t *>(workspace));
+  DDFA_CHECK_LAUNCH("tc2b::dgrad_pack_kernel");
+  return DDFA_OK;
+}
+
+int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
+                     float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
+    set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N));
+    return DDFA_ERR_WORKSPACE;
+  }
+  uint8_t *packed = static_cast<uint8_t *>(workspace);
+  const size_t img = tcc::image_bytes(N);
+  uint8_t *q_img = packed + tc2b::kDgPackedBytes;
+  uint8_t *h_img = q_img + 4 * img;
+  const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
+  tc2b::gate_bwd_image_kernel<<<(unsigned)((rows + tc2b::kGbRows - 1) / tc2b::kGbRows), 256, 0, stream>>>(
+      dh_out, h, gates, indptr, N, q_img, img, h_img, db_fold, db_ih, db_hh);
+  DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
+  DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kDgSmemAlloc));
+  DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
+  const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
+  int groups = kNumSMs / tc2b::kSlices;
+  if (groups > tiles) groups = tiles;
+  tc2b::dgrad_kernel<<<groups * tc2b::kSlices, tc2b::kThreads, tc2b::kDgSmemAlloc, stream>>>(q_img, img, dh_out, gates, packed, N, ds, dh);
+  DDFA_CHECK_LAUNCH("tc2b::dgrad_kernel");
+  int ctas = kNumSMs / 2;
+  if (ctas > 2 * tiles) ctas = 2 * tiles;
+  tc2b::wgrad_kernel<<<dim3(ctas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,
+                                                                                   dw_fold, dw_hh);
+  DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
+  return DDFA_OK;
+}
+
+}  // namespace ddfa

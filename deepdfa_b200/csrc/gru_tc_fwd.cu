@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const float *__restrict__ w_f
     const int lr = (t >> 3) % kWRows;
     const int rest = (t >> 3) / kWRows;  // (j*2 + p)*2 + kb
     const int kb = rest & 1, p = (rest >> 1) & 1, j = rest >> 2;
-    const int gate = lr / kSliceCols, c = lr % kSliceCols;
+    // row order inside an image: s part (p = 0) [n | r | z], h part (p = 1) [r | z | n] — so that each part is ONE
+    // N = 96 MMA into the TMEM column layout [gi_n | r | z | gh_n] (p = 0 -> columns 0..95, p = 1 -> columns 32..127)
+    const int blk = lr / kSliceCols, c = lr % kSliceCols;
+    const int gate = (p == 0) ? (blk == 0 ? 2 : blk - 1) : blk;
     const float *W = (p == 0 ? w_fold : w_hh) + (size_t)(gate * kD + j * kSliceCols + c) * kD + kb * 64 + k8 * 8;
     const float4 a = *reinterpret_cast<const float4 *>(W), b = *reinterpret_cast<const float4 *>(W + 4);
     const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -161,14 +164,14 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t kIdesc96 = make_idesc(96), kIdesc64 = make_idesc(64), kIdesc32 = make_idesc(32);
+      constexpr uint32_t kIdesc96 = make_idesc(96);
       mbar_wait(w_full, 0);
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int buf = k % kAccBufs, buse = k / kAccBufs;
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [r 0-31 | z 32-63 | gin 64-95 | ghn 96-127]
+        const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [gin 0-31 | r 32-63 | z 64-95 | ghn 96-127]
         for (int ci = 0; ci < 8; ++ci, ++cc) {
           const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
@@ -182,11 +185,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t ad = make_desc(a_addr + k4 * 32);
               const bool first = (kb == 0 && v == 0 && wv == 0 && k4 == 0);
+              // p = 0: [gin | r | z] (zero-initialised by the first MMA of the tile);
+              // p = 1: [r | z | ghn] accumulates onto r, z — ghn must start from zero, so the first p = 1 MMA of a tile
+              //        is split into an accumulating N = 64 and a zero-initialising N = 32.
               if (p == 0) {
-                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc96, first ? 0u : 1u);            // r | z | gin
+                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc96, first ? 0u : 1u);
+              } else if (!first) {
+                umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), kIdesc96, 1u);
               } else {
-                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, 1u);                          // r | z
-                umma_f16(d_base + 96, ad, make_desc(w_addr + 64 * 128 + k4 * 32), kIdesc32, first ? 0u : 1u);  // ghn
+                umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), make_idesc(64), 1u);
+                umma_f16(d_base + 96, ad, make_desc(w_addr + 64 * 128 + k4 * 32), make_idesc(32), 0u);
               }
             }
           }
@@ -204,31 +212,40 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
     const int gc0 = slice * kSliceCols + csub * 16;   // first global column of this thread
     const int lc0 = csub * 16;                         // first column inside the slice
     const size_t plane = (size_t)N * kD;
+    // software prefetch, one tile ahead: the fp32 h row piece and the in-degree of this thread's node
+    float4 hn[4];
+    int32_t ip0n = 0, ip1n = 0;
+    auto prefetch = [&](int kk) {
+      const int64_t nd = (int64_t)(group + kk * num_groups) * kTileM + row;
+      if (kk < my_tiles && nd < N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hn[i] = ldg_nc_f4(h + nd * kD + gc0 + i * 4);
+        ip0n = __ldg(indptr + nd);
+        ip1n = __ldg(indptr + nd + 1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ip0n = ip1n = 0;
+      }
+    };
+    prefetch(0);
     for (int k = 0; k < my_tiles; ++k) {
       const int tile = group + k * num_groups;
       const int buf = k % kAccBufs, buse = k / kAccBufs;
       const int64_t node = (int64_t)tile * kTileM + row;
       const bool valid = node < N;
       float hv[16];
-      float deg = 0.f;
-      if (valid) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t4 = ldg_nc_f4(h + node * kD + gc0 + i * 4);
-          hv[i * 4 + 0] = t4.x; hv[i * 4 + 1] = t4.y; hv[i * 4 + 2] = t4.z; hv[i * 4 + 3] = t4.w;
-        }
-        deg = (float)(indptr[node + 1] - indptr[node]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hv[i] = 0.f;
-      }
+      for (int i = 0; i < 4; ++i) { hv[i * 4 + 0] = hn[i].x; hv[i * 4 + 1] = hn[i].y; hv[i * 4 + 2] = hn[i].z; hv[i * 4 + 3] = hn[i].w; }
+      const float deg = (float)(ip1n - ip0n);
+      prefetch(k + 1);
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + lc0);
       float ar[16], az[16], agi[16], agh[16];
-      tmem_ld16(taddr + 0, ar);
-      tmem_ld16(taddr + 32, az);
-      tmem_ld16(taddr + 64, agi);
+      tmem_ld16(taddr + 0, agi);
+      tmem_ld16(taddr + 32, ar);
+      tmem_ld16(taddr + 64, az);
       tmem_ld16(taddr + 96, agh);
       tmem_ld_wait();
       tc_fence_before();

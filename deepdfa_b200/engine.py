@@ -253,22 +253,21 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     h_cur = x
     if use_images:
         img_bytes = L.call("ddfa_act_image_bytes", N)
-        s_img = alloc.get_zeroed("s_img", (img_bytes,), torch.uint8)
         h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(2)]
         L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
     for t in range(T):
         if training:
-            s_t = alloc.get(f"s{t}", (N, D))
+            # with images, s_t is kept only as its image (same bytes as fp32); the backward GEMMs read it directly
+            s_t = alloc.get_zeroed(f"s_img{t}", (img_bytes,), torch.uint8) if use_images else alloc.get(f"s{t}", (N, D))
             h_next = alloc.get(f"h{t + 1}", (N, D))
             g_t = alloc.get(f"gates{t}", (4, N, D))
         else:
-            s_t = None if use_images else alloc.get("s", (N, D))
+            s_t = alloc.get_zeroed("s_img", (img_bytes,), torch.uint8) if use_images else alloc.get("s", (N, D))
             h_next = alloc.get(f"hpp{t % 2}", (N, D))
             g_t = None
         if use_images:
-            # round 1: the weight-gradient kernel still reads fp32 s, so training keeps the fp32 copy next to the image
-            _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_img), _p(s_t), st, tag="gather_fwd")
-            _call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_imgs[t % 2]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
+            _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), None, st, tag="gather_fwd")
+            _call("ddfa_gru_step_fwd_image", _p(s_t), _p(h_imgs[t % 2]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
                   _p(h_imgs[(t + 1) % 2]) if t + 1 < T else None, _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
         else:
             _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
@@ -337,9 +336,14 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
-        _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
-               _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
-               _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes, engine, st)
+        if engine == ENGINE_TCGEN05:     # saved.s[t] is the activation image of s_t
+            _call("ddfa_gru_step_bwd_image", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
+                  _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
+                  st, tag="ddfa_gru_step_bwd")
+        else:
+            _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
+                  _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
+                  _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes, engine, st)
         # dh_t += A^T ds   (gather over the transposed graph)
         _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st, tag="gather_bwd")
         dh, dh_alt = dh_alt, dh

@@ -149,6 +149,15 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
                             void *h_out_image, float *save_gates, const void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/* Backward of one step on images (tcgen05 engine): like ddfa_gru_step_bwd below, but s arrives as its
+ * activation image (the one ddfa_gather_sum_image wrote in the forward pass); the q matrices and h are turned
+ * into images inside the workspace.  workspace: ddfa_gru_step_bwd_workspace_bytes(N, D, TCGEN05), prepared by
+ * ddfa_gru_step_prepare_bwd. */
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates,
+                            const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
+                            float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
  * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
  * Accumulated (+=): dw_fold[3D,D], db_fold[3D], db_ih[3D], dw_hh[3D,D], db_hh[3D].
