@@ -84,23 +84,53 @@ __global__ void __launch_bounds__(kReadoutWarps * 32) readout_mlp_fwd_kernel(
 #pragma unroll
     for (int i = 0; i < CH; ++i) acc.v[p][i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int32_t n = n0 + warp; n < n1; n += kReadoutWarps) {
-    RowFrag<CH> o;
-    load_row<CH>(o, h, x, n, D, lane);
-    const float g = warp_sum(dot_row<CH>(o, wg)) + bg;
-    if (gate_logit && lane == 0) gate_logit[n] = g;
-    const float m_new = fmaxf(m, g);
-    const float scale = expf(m - m_new);  // first iteration: exp(-inf) = 0
-    const float p = expf(g - m_new);
-    l = fmaf(l, scale, p);
+  // U node rows per iteration: their loads and warp reductions are independent (memory-level parallelism; the
+  // one-row-at-a-time version was a chain of ~1 us global-load latencies), one online-softmax update for the group.
+  constexpr int U = (CH == 1) ? 4 : (CH == 2 ? 2 : 1);
+  for (int32_t nb = n0 + warp; nb < n1; nb += kReadoutWarps * U) {
+    RowFrag<CH> o[U];
+    float g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t n = nb + u * kReadoutWarps;
+      if (n < n1) load_row<CH>(o[u], h, x, n, D, lane);
+      else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int i = 0; i < CH; ++i) o[u].v[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = dot_row<CH>(o[u], wg);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) g[u] += __shfl_xor_sync(0xffffffffu, g[u], off);
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t n = nb + u * kReadoutWarps;
+      g[u] = (n < n1) ? g[u] + bg : -INFINITY;
+      if (n < n1 && gate_logit && lane == 0) gate_logit[n] = g[u];
+      m_new = fmaxf(m_new, g[u]);
+    }
+    const float scale = expf(m - m_new);  // first iteration: exp(-inf) = 0  (m_new is finite: row nb exists)
+    float p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = expf(g[u] - m_new);   // exp(-inf) = 0 for rows past the graph
+    float psum = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) psum += p[u];
+    l = fmaf(l, scale, psum);
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         float4 &a = acc.v[q][i];
-        const float4 &ov = o.v[q][i];
-        a.x = fmaf(a.x, scale, p * ov.x); a.y = fmaf(a.y, scale, p * ov.y);
-        a.z = fmaf(a.z, scale, p * ov.z); a.w = fmaf(a.w, scale, p * ov.w);
+        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+#pragma unroll
+        for (int u = 0; u < U; ++u) f4_fma(a, p[u], o[u].v[q][i]);
       }
     m = m_new;
   }

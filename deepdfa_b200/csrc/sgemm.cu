@@ -140,10 +140,70 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
   }
 }
 
+// Small problems (weight folding, MLP head backward: M, N <= a few hundred) would occupy 1-6 of the 148 SMs with the
+// 128x128 tile and run for tens of microseconds; this kernel uses 32x32 output tiles (256 threads, 2x2 per thread,
+// K staged 32 at a time through shared memory) so the same work spreads over dozens of CTAs.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_small_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
+                                                          const float *__restrict__ B, int ldb, float beta, float *__restrict__ C,
+                                                          int ldc) {
+  __shared__ float As[32][33];  // [k][m]
+  __shared__ float Bs[32][33];  // [k][n]
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;      // 1024 elements per tile
+      {  // A tile: element (m, k); the fastest-varying index follows the memory layout for coalescing
+        const int m = TA ? (e & 31) : (e >> 5), k = TA ? (e >> 5) : (e & 31);
+        const int gm = m0 + m, gk = k0 + k;
+        As[k][m] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.f;
+      }
+      {  // B tile: element (k, n)
+        const int n = TB ? (e >> 5) : (e & 31), k = TB ? (e & 31) : (e >> 5);
+        const int gn = n0 + n, gk = k0 + k;
+        Bs[k][n] = (gn < N && gk < K) ? (TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < M && n < N) {
+        float *c = C + (int64_t)m * ldc + n;
+        const float v = alpha * acc[i][j];
+        *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
+      }
+    }
+}
+
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
           float beta, float *C, int ldc, int split_k, cudaStream_t stream) {
   if (M == 0 || N == 0) return DDFA_OK;
   if (split_k < 1) split_k = 1;
+  if (split_k == 1 && (int64_t)M * N <= 512 * 512 && K <= 4096) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+#define LAUNCH_S(TA, TB) sgemm_small_kernel<TA, TB><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)
+    if (!ta && !tb) LAUNCH_S(false, false);
+    else if (!ta && tb) LAUNCH_S(false, true);
+    else if (ta && !tb) LAUNCH_S(true, false);
+    else LAUNCH_S(true, true);
+#undef LAUNCH_S
+    DDFA_CHECK_LAUNCH("sgemm_small_kernel");
+    return DDFA_OK;
+  }
   int k_tiles = (K + BK - 1) / BK;
   if (split_k > k_tiles) split_k = k_tiles > 0 ? k_tiles : 1;
   const int k_per_split = ((k_tiles + split_k - 1) / split_k) * BK;
