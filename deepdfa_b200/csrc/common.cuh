@@ -60,7 +60,8 @@ size_t gru_tc2_bwd_workspace_bytes(int32_t N);
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
                      float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
-                     size_t workspace_bytes, cudaStream_t stream);
+                     size_t workspace_bytes, int wgrad_mode, cudaStream_t stream);
+int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
   float4 v;

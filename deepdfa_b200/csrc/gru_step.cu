@@ -298,15 +298,25 @@ size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
 
 int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates, const int32_t *indptr,
                             int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
-                            float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, void *stream_) {
+                            float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode,
+                            void *stream_) {
   using namespace ddfa;
   DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_bwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  DDFA_REQUIRE(wgrad_mode >= 0 && wgrad_mode <= 2, "ddfa_gru_step_bwd_image: wgrad_mode must be 0, 1 or 2 (got %d)", wgrad_mode);
   if (N == 0) return DDFA_OK;
   DDFA_REQUIRE(dh_out && h && s_image && gates && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
                "ddfa_gru_step_bwd_image: NULL pointer");
   DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image: dh must not alias dh_out");
   return gru_tc2_step_bwd(dh_out, h, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
-                          workspace_bytes, as_stream(stream_));
+                          workspace_bytes, wgrad_mode, as_stream(stream_));
+}
+
+int ddfa_gru_step_bwd_finish(int32_t N, int32_t D, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes,
+                             void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128 && dw_fold && dw_hh, "ddfa_gru_step_bwd_finish: bad arguments (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, as_stream(stream_));
 }
 
 int ddfa_gru_step_prepare_bwd(const float *w_fold, const float *w_hh, int32_t D, int engine, void *workspace,
@@ -342,7 +352,7 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
     rc = act_to_image(s, N, s_img, stream);
     if (rc) return rc;
     return gru_tc2_step_bwd(dh_out, h, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
-                            workspace_bytes, stream);
+                            workspace_bytes, /*wgrad_mode=*/0, stream);
   }
   float *dgi = static_cast<float *>(workspace);
   float *dgh = dgi + (size_t)N * 3 * D;

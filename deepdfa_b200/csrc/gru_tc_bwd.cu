@@ -100,10 +100,11 @@ __global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__rest
 // =================================================================================================
 constexpr int kDgWImgBytes = 64 * 128;                  // [rows 0-31: W'^T slice | rows 32-63: Whh^T slice] x 64 k = 8 KB
 constexpr int kDgWSliceBytes = 12 * kDgWImgBytes;       // (gate*2 + kb)*2 + v  -> 96 KB
-constexpr int kDgAStages = 7;
+constexpr int kDgAStages = 2;                           // 2 x 64 KB whole-tile operand stages (see gru_tc_fwd.cu)
+constexpr int kDgAStageBytes = kImageTileBytes;
 constexpr int kDgAccBufs = 4;
 constexpr int kDgOffA = kDgWSliceBytes;
-constexpr int kDgOffBar = kDgOffA + kDgAStages * kChunkBytes;
+constexpr int kDgOffBar = kDgOffA + kDgAStages * kDgAStageBytes;
 constexpr int kDgNumBars = 1 + 2 * kDgAStages + 2 * kDgAccBufs;
 constexpr int kDgOffTmemPtr = kDgOffBar + kDgNumBars * 8;
 constexpr int kDgSmemAlloc = kDgOffTmemPtr + 16 + 1024;
@@ -173,13 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
-        for (int ci = 0; ci < 16; ++ci, ++cc) {       // ci = (m*2 + kb)*2 + v ; m: q_r, q_z, q_n, q_nr
-          const int m = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+        for (int m = 0; m < 4; ++m, ++cc) {           // one 64 KB bulk copy per q matrix tile (q_r, q_z, q_n, q_nr)
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
-          mbar_arrive_expect_tx(a_full(stage), kChunkBytes);
-          const uint8_t *src = q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes + (size_t)(v * 2 + kb) * kChunkBytes;
-          bulk_g2s(sbase + kDgOffA + stage * kChunkBytes, src, kChunkBytes, a_full(stage));
+          mbar_arrive_expect_tx(a_full(stage), kDgAStageBytes);
+          bulk_g2s(sbase + kDgOffA + stage * kDgAStageBytes, q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes,
+                   kDgAStageBytes, a_full(stage));
         }
       }
     }
@@ -193,13 +193,15 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * 64u;   // [ds 0-31 | dh 32-63]
-        for (int ci = 0; ci < 16; ++ci, ++cc) {
+        for (int ci = 0; ci < 16; ++ci) {             // ci = (m*2 + kb)*2 + v ; m: q_r, q_z, q_n, q_nr
           const int m = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
           const int g = m < 2 ? m : 2;
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
-          mbar_wait(a_full(stage), use & 1);
-          tc_fence_after();
-          const uint32_t a_addr = sbase + kDgOffA + stage * kChunkBytes;
+          if ((ci & 3) == 0) {
+            mbar_wait(a_full(stage), use & 1);
+            tc_fence_after();
+          }
+          const uint32_t a_addr = sbase + kDgOffA + stage * kDgAStageBytes + (uint32_t)(v * 2 + kb) * kChunkBytes;
           const int n_wv = (v == 0) ? 2 : 1;
           for (int wv = 0; wv < n_wv; ++wv) {
             const uint32_t w_addr = sbase + (uint32_t)(((g * 2 + kb) * 2 + wv) * kDgWImgBytes);
@@ -215,7 +217,10 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
                 umma_f16(d_base + 32, ad, make_desc(w_addr + 32 * 128 + k4 * 32), kIdesc32, 1u);
             }
           }
-          umma_commit(a_empty(stage));
+          if ((ci & 3) == 3) {
+            umma_commit(a_empty(stage));
+            ++cc;
+          }
         }
         umma_commit(acc_full(buf));
       }
@@ -282,19 +287,29 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
 // =================================================================================================
 // (3) wgrad
 // =================================================================================================
-constexpr int kWgTileK = 64;                              // nodes per half tile
-constexpr int kWgPiece = kWgTileK * 128;                  // 8 KB: rows 0-63 or 64-127 of one image chunk
-constexpr int kWgSlotBytes = 4 * kWgPiece;                // [hi|lo][col block] = 32 KB per operand
-constexpr int kWgSlots = 6;
+// Operands are whole 128-node image tiles (64 KB, ONE bulk copy each — see the copy-size note in gru_tc_fwd.cu),
+// three 64 KB slots.  Per tile the operand sequence is B_t, A_0, A_1, A_2 (B_t = s or h tile, A_g = q tiles);
+// B_t must stay until A_2 is consumed, so the slots rotate:  slot(B_i) = (-i) mod 3, A_0 -> slot(B)+1, A_1 ->
+// slot(B)+2, A_2 -> the slot A_0 just released.  Both operands are read MN-major (K = nodes).
+constexpr int kWgSlotBytes = kImageTileBytes;             // 64 KB
+constexpr int kWgSlots = 3;
 constexpr int kWgOffBar = kWgSlots * kWgSlotBytes;        // 192 KB
 constexpr int kWgNumBars = 2 * kWgSlots + 1;
 constexpr int kWgOffTmemPtr = kWgOffBar + kWgNumBars * 8;
 constexpr int kWgSmemAlloc = kWgOffTmemPtr + 16 + 1024;
+constexpr size_t kWgPartialFloats = (size_t)3 * kD * kD;  // one CTA's [384 x 128] partial sum
 
-// grid = (ctas, 2): blockIdx.y = role: 0: A in {q_r,q_z,q_n}, B = s image -> dW' ; 1: A in {q_r,q_z,q_nr}, B = h image -> dWhh
+__device__ __forceinline__ int wg_slot(int tile_i, int w) {   // w: 0 = B, 1..3 = A_0..A_2
+  const int sb = (3 - tile_i % 3) % 3;
+  return w == 0 ? sb : (w == 2 ? (sb + 2) % 3 : (sb + 1) % 3);
+}
+
+// grid = (ctas, 2): blockIdx.y = role: 0: A in {q_r,q_z,q_n}, B = s image -> dW' ; 1: A in {q_r,q_z,q_nr}, B = h image -> dWhh.
+// partial: [2][ctas][384*128] fp32, private per CTA: accumulate (first == 0) or overwrite (first != 0); the sum over CTAs
+// is taken once per backward pass by wgrad_reduce_kernel (no atomics on the hot path).
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
                                                             const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
-                                                            int32_t N, float *__restrict__ dw_fold, float *__restrict__ dw_hh) {
+                                                            int32_t N, float *__restrict__ partial, int first) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = blockIdx.y;
-  const int num_tiles = 2 * ((N + kTileM - 1) / kTileM);   // 64-node half tiles (images are padded to 128 rows with zeros)
+  const int num_tiles = (N + kTileM - 1) / kTileM;
   const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
@@ -324,14 +339,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // TMA producer: per half tile the operand sequence B_t, A_0, A_1, A_2 (each 4 x 8 KB pieces of an image tile)
     if (lane == 0) {
+      int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
-        const int ht = (int)blockIdx.x + i * (int)gridDim.x;
-        const size_t tile_off = (size_t)(ht >> 1) * kImageTileBytes + (size_t)(ht & 1) * kWgPiece;
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         for (int w = 0; w < 4; ++w) {
-          const int j = 4 * i + w, slot = j % kWgSlots;
-          if (j >= kWgSlots) mbar_wait(empty_bar(slot), ((j / kWgSlots) - 1) & 1);
+          const int slot = wg_slot(i, w);
+          if (uses[slot] > 0) mbar_wait(empty_bar(slot), (uses[slot] - 1) & 1);
+          ++uses[slot];
           const uint8_t *src;
           if (w == 0) src = (role == 0) ? s_img : h_img;
           else {
@@ -339,31 +354,33 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
             src = q_img + (size_t)pl * img_stride;
           }
           mbar_arrive_expect_tx(full_bar(slot), kWgSlotBytes);
-          for (int c = 0; c < 4; ++c)   // c = v*2 + kb
-            bulk_g2s(sbase + slot * kWgSlotBytes + c * kWgPiece, src + tile_off + (size_t)c * kChunkBytes, kWgPiece, full_bar(slot));
+          bulk_g2s(sbase + slot * kWgSlotBytes, src + (size_t)tile * kImageTileBytes, kWgSlotBytes, full_bar(slot));
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t kIdescMN = make_idesc(128, true, true);
+      int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
-        const int jb = 4 * i, slot_b = jb % kWgSlots;
-        mbar_wait(full_bar(slot_b), (jb / kWgSlots) & 1);
+        const int slot_b = wg_slot(i, 0);
+        mbar_wait(full_bar(slot_b), uses[slot_b] & 1);
+        ++uses[slot_b];
         for (int g = 0; g < 3; ++g) {
-          const int ja = jb + 1 + g, slot_a = ja % kWgSlots;
-          mbar_wait(full_bar(slot_a), (ja / kWgSlots) & 1);
+          const int slot_a = wg_slot(i, 1 + g);
+          mbar_wait(full_bar(slot_a), uses[slot_a] & 1);
+          ++uses[slot_a];
           tc_fence_after();
           const uint32_t a0 = sbase + slot_a * kWgSlotBytes, b0 = sbase + slot_b * kWgSlotBytes;
           const uint32_t d_addr = tmem_base + (uint32_t)g * 128u;
 #pragma unroll
-          for (int k16 = 0; k16 < kWgTileK / 16; ++k16) {
+          for (int k16 = 0; k16 < kTileM / 16; ++k16) {
             const uint32_t koff = (uint32_t)k16 * 2048u;     // 16 nodes = two 8-node groups of 1024 B
-            const uint32_t vs = 2 * kWgPiece;                // hi -> lo variant
+            const uint32_t vs = 2 * kChunkBytes;             // hi -> lo variant ([v][kb] chunks of 16 KB)
             const uint32_t acc = (i > 0 || k16 > 0) ? 1u : 0u;
-            umma_f16(d_addr, make_desc_mn(a0 + koff, kWgPiece), make_desc_mn(b0 + koff, kWgPiece), kIdescMN, acc);            // a_hi b_hi
-            umma_f16(d_addr, make_desc_mn(a0 + vs + koff, kWgPiece), make_desc_mn(b0 + koff, kWgPiece), kIdescMN, 1u);        // a_lo b_hi
-            umma_f16(d_addr, make_desc_mn(a0 + koff, kWgPiece), make_desc_mn(b0 + vs + koff, kWgPiece), kIdescMN, 1u);        // a_hi b_lo
+            umma_f16(d_addr, make_desc_mn(a0 + koff, kChunkBytes), make_desc_mn(b0 + koff, kChunkBytes), kIdescMN, acc);       // a_hi b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + vs + koff, kChunkBytes), make_desc_mn(b0 + koff, kChunkBytes), kIdescMN, 1u);   // a_lo b_hi
+            umma_f16(d_addr, make_desc_mn(a0 + koff, kChunkBytes), make_desc_mn(b0 + vs + koff, kChunkBytes), kIdescMN, 1u);   // a_hi b_lo
           }
           umma_commit(empty_bar(slot_a));
         }
@@ -371,23 +388,35 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
       }
       umma_commit(acc_bar);
     }
-  } else if (my_tiles > 0) {
+  } else {
+    // epilogue: this CTA's private partial sums (thread = one of the 128 rows of a gate block, 64 columns)
     const int lw = warp - 2, qd = warp & 3, chalf = lw >> 2;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
     const int m = qd * 32 + lane;
-    float *dW = (role == 0) ? dw_fold : dw_hh;
+    float *dst0 = partial + ((size_t)role * gridDim.x + blockIdx.x) * kWgPartialFloats;
+    if (my_tiles > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
 #pragma unroll 1
     for (int g = 0; g < 3; ++g) {
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = chalf * 64 + cc * 16;
         float a[16];
-        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + col0), a);
-        tmem_ld_wait();
-        float *dst = dW + (size_t)(g * 128 + m) * kD + col0;
+        if (my_tiles > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + col0), a);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) atomicAdd(dst + x, a[x]);
+          for (int x = 0; x < 16; ++x) a[x] = 0.f;
+        }
+        float *dst = dst0 + (size_t)(g * 128 + m) * kD + col0;
+#pragma unroll
+        for (int x4 = 0; x4 < 4; ++x4) {
+          float4 v = make_float4(a[x4 * 4], a[x4 * 4 + 1], a[x4 * 4 + 2], a[x4 * 4 + 3]);
+          if (!first) f4_add(v, *reinterpret_cast<const float4 *>(dst + x4 * 4));
+          *reinterpret_cast<float4 *>(dst + x4 * 4) = v;
+        }
       }
     }
   }
@@ -399,10 +428,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
   }
 }
 
+// dW'[384,128] += sum_cta partial[0][cta] ; dWhh += sum_cta partial[1][cta]     (once per backward pass)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int ctas, float *__restrict__ dw_fold,
+                                                           float *__restrict__ dw_hh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // float4 index inside one [384 x 128] matrix
+  const int role = blockIdx.y;
+  if (i >= (int)(kWgPartialFloats / 4)) return;
+  const float4 *src = reinterpret_cast<const float4 *>(partial + (size_t)role * ctas * kWgPartialFloats) + i;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < ctas; ++c) f4_add(s, src[(size_t)c * (kWgPartialFloats / 4)]);
+  float4 *dst = reinterpret_cast<float4 *>(role == 0 ? dw_fold : dw_hh) + i;
+  float4 d = *dst;
+  f4_add(d, s);
+  *dst = d;
+}
+
 }  // namespace tc2b
 
-// workspace = [dgrad per-slice transposed weight images (384 KB)][q images x4][h image]
-size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N); }
+// workspace = [dgrad per-slice transposed weight images (384 KB)][q images x4][h image][wgrad partial sums: 2 x 74 x 384 x 128 fp32]
+constexpr int kWgCtas = kNumSMs / 2;
+static size_t wg_partial_bytes() { return (size_t)2 * kWgCtas * tc2b::kWgPartialFloats * sizeof(float); }
+size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < tc2b::kDgPackedBytes) {
@@ -415,9 +461,24 @@ int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace,
   return DDFA_OK;
 }
 
+// dW' += sum of the per-CTA partial sums, dWhh likewise (closes a deferred weight-gradient accumulation)
+int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
+    set_error("tcgen05 engine (bwd finish): workspace too small");
+    return DDFA_ERR_WORKSPACE;
+  }
+  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N));
+  const int n4 = (int)(tc2b::kWgPartialFloats / 4);
+  tc2b::wgrad_reduce_kernel<<<dim3((n4 + 255) / 256, 2), 256, 0, stream>>>(partial, kWgCtas, dw_fold, dw_hh);
+  DDFA_CHECK_LAUNCH("tc2b::wgrad_reduce_kernel");
+  return DDFA_OK;
+}
+
+// wgrad_mode: 0 = immediate (dW += this step's contribution before returning), 1 = first step of a deferred accumulation
+// (partials overwritten), 2 = further deferred step (partials accumulated); deferred passes end with gru_tc2_bwd_finish.
 int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
                      float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
-                     size_t workspace_bytes, cudaStream_t stream) {
+                     size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
     set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N));
     return DDFA_ERR_WORKSPACE;
@@ -426,6 +487,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, con
   const size_t img = tcc::image_bytes(N);
   uint8_t *q_img = packed + tc2b::kDgPackedBytes;
   uint8_t *h_img = q_img + 4 * img;
+  float *partial = reinterpret_cast<float *>(h_img + img);
   const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
   tc2b::gate_bwd_image_kernel<<<(unsigned)((rows + tc2b::kGbRows - 1) / tc2b::kGbRows), 256, 0, stream>>>(
       dh_out, h, gates, indptr, N, q_img, img, h_img, db_fold, db_ih, db_hh);
@@ -437,11 +499,11 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, con
   if (groups > tiles) groups = tiles;
   tc2b::dgrad_kernel<<<groups * tc2b::kSlices, tc2b::kThreads, tc2b::kDgSmemAlloc, stream>>>(q_img, img, dh_out, gates, packed, N, ds, dh);
   DDFA_CHECK_LAUNCH("tc2b::dgrad_kernel");
-  int ctas = kNumSMs / 2;
-  if (ctas > 2 * tiles) ctas = 2 * tiles;
-  tc2b::wgrad_kernel<<<dim3(ctas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,
-                                                                                   dw_fold, dw_hh);
+  // every one of the 74 x 2 CTAs writes its partial slot (zeros if it owns no tile), so the reduction can sum all of them
+  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,
+                                                                                     partial, wgrad_mode == 2 ? 0 : 1);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
+  if (wgrad_mode == 0) return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, stream);
   return DDFA_OK;
 }
 

@@ -31,10 +31,14 @@ constexpr int kWRows = 3 * kSliceCols;                   // 96 weight rows per s
 constexpr int kWImgBytes = kWRows * 128;                 // 12 KB: one (matrix p, kblock, variant) image
 constexpr int kWSliceBytes = 8 * kWImgBytes;             // 96 KB per slice, index (p*2 + kb)*2 + v
 constexpr int kBiasSlice = 7 * kSliceCols;               // floats per slice
-constexpr int kAStages = 7;
+// A feed: ONE cp.async.bulk per operand tile (64 KB = [hi|lo][kb0|kb1], contiguous in the image), two stages.
+// profiles/r01g_copy_bench.log: a 1-D bulk copy costs ~0.42 us almost independently of its size and copies from one
+// SM do not overlap, so throughput = size / 0.42 us (16 KB -> 38 GB/s/SM, 32 KB -> 70 GB/s/SM): copy whole tiles.
+constexpr int kAStages = 2;
+constexpr int kAStageBytes = kImageTileBytes;            // 64 KB
 constexpr int kAccBufs = 4;
 constexpr int kOffA = kWSliceBytes;
-constexpr int kOffBias = kOffA + kAStages * kChunkBytes;
+constexpr int kOffBias = kOffA + kAStages * kAStageBytes;
 constexpr int kOffBar = kOffBias + kBiasSlice * 4;
 constexpr int kNumBars = 1 + 2 * kAStages + 2 * kAccBufs;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
@@ -151,13 +155,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
-        for (int ci = 0; ci < 8; ++ci, ++cc) {
-          const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+        for (int p = 0; p < 2; ++p, ++cc) {
           const int stage = cc % kAStages, use = cc / kAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
-          mbar_arrive_expect_tx(a_full(stage), kChunkBytes);
-          const uint8_t *src = (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)(v * 2 + kb) * kChunkBytes;
-          bulk_g2s(sbase + kOffA + stage * kChunkBytes, src, kChunkBytes, a_full(stage));
+          mbar_arrive_expect_tx(a_full(stage), kAStageBytes);
+          bulk_g2s(sbase + kOffA + stage * kAStageBytes, (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes, kAStageBytes,
+                   a_full(stage));
         }
       }
     }
@@ -172,12 +175,14 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [gin 0-31 | r 32-63 | z 64-95 | ghn 96-127]
-        for (int ci = 0; ci < 8; ++ci, ++cc) {
+        for (int ci = 0; ci < 8; ++ci) {
           const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
-          mbar_wait(a_full(stage), use & 1);
-          tc_fence_after();
-          const uint32_t a_addr = sbase + kOffA + stage * kChunkBytes;
+          if ((ci & 3) == 0) {             // first chunk of an operand: wait for its 64 KB stage
+            mbar_wait(a_full(stage), use & 1);
+            tc_fence_after();
+          }
+          const uint32_t a_addr = sbase + kOffA + stage * kAStageBytes + (uint32_t)(v * 2 + kb) * kChunkBytes;
           const int n_wv = (v == 0) ? 2 : 1;   // a_hi pairs with w_hi and w_lo; a_lo with w_hi only
           for (int wv = 0; wv < n_wv; ++wv) {
             const uint32_t w_addr = sbase + (uint32_t)(((p * 2 + kb) * 2 + wv) * kWImgBytes);
@@ -198,7 +203,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
               }
             }
           }
-          umma_commit(a_empty(stage));
+          if ((ci & 3) == 3) {             // last chunk of the operand: release its stage
+            umma_commit(a_empty(stage));
+            ++cc;
+          }
         }
         umma_commit(acc_full(buf));
       }

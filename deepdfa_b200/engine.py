@@ -339,7 +339,7 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
         if engine == ENGINE_TCGEN05:     # saved.s[t] is the activation image of s_t
             _call("ddfa_gru_step_bwd_image", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
                   _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
-                  st, tag="ddfa_gru_step_bwd")
+                  1 if t == T - 1 else 2, st, tag="ddfa_gru_step_bwd")   # deferred weight-gradient accumulation
         else:
             _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
                   _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
@@ -347,6 +347,8 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
         # dh_t += A^T ds   (gather over the transposed graph)
         _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st, tag="gather_bwd")
         dh, dh_alt = dh_alt, dh
+    if engine == ENGINE_TCGEN05 and T > 0:
+        L.call("ddfa_gru_step_bwd_finish", N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st)
     L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
            _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)
     _call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,

@@ -156,7 +156,12 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
 int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates,
                             const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
                             float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
-                            void *workspace, size_t workspace_bytes, void *stream);
+                            void *workspace, size_t workspace_bytes, int wgrad_mode, void *stream);
+/* wgrad_mode: 0 = dw_fold / dw_hh are updated before the call returns (stream order); 1 / 2 = deferred: the
+ * weight-gradient GEMM accumulates per-CTA partial sums inside the workspace over the T steps of one backward pass
+ * (1 = first step, overwrites; 2 = later steps) and ddfa_gru_step_bwd_finish adds them to dw_fold / dw_hh once. */
+int ddfa_gru_step_bwd_finish(int32_t num_nodes, int32_t dim, float *dw_fold, float *dw_hh, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
  * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
