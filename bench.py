@@ -276,31 +276,59 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = L.call("ddfa_launch_count") - l0
 
-    # ---- timed region: K resident-input train steps ------------------------------------------------
+    # ---- instrumented region (eager launches): CUDA-event pairs around every gather / GRU-step call -> roofline -----
     prof = SpanProfiler(["gather_fwd", "gather_bwd", "ddfa_gru_step_fwd", "ddfa_gru_step_bwd"])
     E.profile_hook = prof
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
     ev0.record()
     for i in range(args.steps):
         trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
     ev1.record()
     barrier()
-    t_wall1 = time.time()
     E.profile_hook = None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms = ev0.elapsed_time(ev1)                      # denominator of the kernel shares below
+    ms_eager_per_step = ms / args.steps
+
+    # ---- capture one CUDA graph per resident batch (launch-bound inner loop: ~100 kernels per step) ------------------
+    graph_note = "off (--no-graphs)"
+    if args.graphs:
+        try:
+            trainer.use_cuda_graph = True
+            for i in range(2 * NUM_BATCHES):        # first visit: capture, second visit: replay
+                trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
+            torch.cuda.synchronize()
+            graph_note = f"on ({len(trainer._graphs)} graphs, one per resident batch)"
+        except Exception as exc:                    # an execution-mode downgrade, not a compute fallback: same kernels, eager launches
+            trainer.use_cuda_graph = False
+            trainer._graphs.clear()
+            torch.cuda.synchronize()
+            graph_note = f"off (capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+
+    # ---- timed region (headline): K resident-input train steps ----------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    for i in range(max(args.warmup, min_warm)):
+        trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
+    barrier()
+    tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    tv0.record()
+    for i in range(args.steps):
+        trainer.step(dev_batches[i % NUM_BATCHES], global_batch)
+    tv1.record()
+    barrier()
+    t_wall1 = time.time()
+    t = torch.tensor([tv0.elapsed_time(tv1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     final_loss = float(trainer.loss_slot.item())
     value = global_batch * args.steps / (ms_total * 1e-3)
+    trainer.use_cuda_graph = False                  # the e2e path below builds a new graph structure every step
 
     # ---- e2e: host (pinned) buffers -> H2D -> device CSR build -> train step -> loss D2H, every step ----
     def fresh(b):  # a new graph object: no cached device CSR, so the whole input path is inside the timed region
@@ -368,6 +396,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
                 "path": "pinned host COO + node indices -> H2D -> ddfa_build_csr -> fused train step -> loss .item()"},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+        "cuda_graph": graph_note, "ms_per_step_eager_instrumented": ms_eager_per_step,
         "roofline": roofline, "roofline_gru": gru,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_done} full train steps of one {args.graphs}-graph C0 batch, oracle/ggnn_oracle.py (torch CPU)"},
@@ -386,7 +415,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--graphs", type=int, default=CFG["graphs"], help="graphs per GPU per step")
-    ap.add_argument("--engine", choices=["simt", "tcgen05"], default=os.environ.get("DDFA_B200_ENGINE", "simt"))
+    ap.add_argument("--engine", choices=["simt", "tcgen05"], default=os.environ.get("DDFA_B200_ENGINE", "tcgen05"))
+    ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="launch every kernel eagerly in the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
