@@ -100,11 +100,15 @@ __global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__rest
 // =================================================================================================
 constexpr int kDgWImgBytes = 64 * 128;                  // [rows 0-31: W'^T slice | rows 32-63: Whh^T slice] x 64 k = 8 KB
 constexpr int kDgWSliceBytes = 12 * kDgWImgBytes;       // (gate*2 + kb)*2 + v  -> 96 KB
-constexpr int kDgAStages = 2;                           // 2 x 64 KB whole-tile operand stages (see gru_tc_fwd.cu)
-constexpr int kDgAStageBytes = kImageTileBytes;
+constexpr int kDgAStages = 2;                           // 2 x 32 KB stages: one variant (hi | lo) of one q-matrix tile
+constexpr int kDgAStageBytes = 2 * kChunkBytes;
 constexpr int kDgAccBufs = 4;
 constexpr int kDgOffA = kDgWSliceBytes;
-constexpr int kDgOffBar = kDgOffA + kDgAStages * kDgAStageBytes;
+// epilogue staging (tc_common.cuh "coalesced epilogue I/O"): per warp pair 2 planes, used first for the inputs
+// (dh', z rows) and then for the outputs (ds, dh rows)
+constexpr int kDgOffStage = kDgOffA + kDgAStages * kDgAStageBytes;
+constexpr int kDgStageBytes = 4 * 2 * kStagePlaneFloats * 4;
+constexpr int kDgOffBar = kDgOffStage + kDgStageBytes;
 constexpr int kDgNumBars = 1 + 2 * kDgAStages + 2 * kDgAccBufs;
 constexpr int kDgOffTmemPtr = kDgOffBar + kDgNumBars * 8;
 constexpr int kDgSmemAlloc = kDgOffTmemPtr + 16 + 1024;
@@ -174,12 +178,14 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
-        for (int m = 0; m < 4; ++m, ++cc) {           // one 64 KB bulk copy per q matrix tile (q_r, q_z, q_n, q_nr)
+        for (int mv = 0; mv < 8; ++mv, ++cc) {        // (q matrix m: q_r, q_z, q_n, q_nr) x (variant hi, lo): 32 KB each
+          const int m = mv >> 1, v = mv & 1;
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
           mbar_arrive_expect_tx(a_full(stage), kDgAStageBytes);
-          bulk_g2s(sbase + kDgOffA + stage * kDgAStageBytes, q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes,
-                   kDgAStageBytes, a_full(stage));
+          bulk_g2s(sbase + kDgOffA + stage * kDgAStageBytes,
+                   q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes + (size_t)v * kDgAStageBytes, kDgAStageBytes,
+                   a_full(stage));
         }
       }
     }
@@ -193,66 +199,72 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * 64u;   // [ds 0-31 | dh 32-63]
-        for (int ci = 0; ci < 16; ++ci) {             // ci = (m*2 + kb)*2 + v ; m: q_r, q_z, q_n, q_nr
-          const int m = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+        for (int mv = 0; mv < 8; ++mv, ++cc) {
+          const int m = mv >> 1, v = mv & 1;
           const int g = m < 2 ? m : 2;
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
-          if ((ci & 3) == 0) {
-            mbar_wait(a_full(stage), use & 1);
-            tc_fence_after();
-          }
-          const uint32_t a_addr = sbase + kDgOffA + stage * kDgAStageBytes + (uint32_t)(v * 2 + kb) * kChunkBytes;
+          mbar_wait(a_full(stage), use & 1);
+          tc_fence_after();
           const int n_wv = (v == 0) ? 2 : 1;
-          for (int wv = 0; wv < n_wv; ++wv) {
-            const uint32_t w_addr = sbase + (uint32_t)(((g * 2 + kb) * 2 + wv) * kDgWImgBytes);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t a_addr = sbase + kDgOffA + stage * kDgAStageBytes + (uint32_t)kb * kChunkBytes;
+            for (int wv = 0; wv < n_wv; ++wv) {
+              const uint32_t w_addr = sbase + (uint32_t)(((g * 2 + kb) * 2 + wv) * kDgWImgBytes);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t ad = make_desc(a_addr + k4 * 32);
-              if (m < 2) {        // q_r, q_z feed both ds and dh: one N = 64 MMA
-                const bool first = (ci == 0 && wv == 0 && k4 == 0);
-                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, first ? 0u : 1u);
-              } else if (m == 2)  // q_n -> ds only (rows 0..31 of the image)
-                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc32, 1u);
-              else                // q_nr -> dh only (rows 32..63)
-                umma_f16(d_base + 32, ad, make_desc(w_addr + 32 * 128 + k4 * 32), kIdesc32, 1u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t ad = make_desc(a_addr + k4 * 32);
+                if (m < 2) {        // q_r, q_z feed both ds and dh: one N = 64 MMA
+                  const bool first = (mv == 0 && kb == 0 && wv == 0 && k4 == 0);
+                  umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, first ? 0u : 1u);
+                } else if (m == 2)  // q_n -> ds only (rows 0..31 of the image)
+                  umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc32, 1u);
+                else                // q_nr -> dh only (rows 32..63)
+                  umma_f16(d_base + 32, ad, make_desc(w_addr + 32 * 128 + k4 * 32), kIdesc32, 1u);
+              }
             }
           }
-          if ((ci & 3) == 3) {
-            umma_commit(a_empty(stage));
-            ++cc;
-          }
+          umma_commit(a_empty(stage));
         }
         umma_commit(acc_full(buf));
       }
     }
   } else {
+    // epilogue: ds = acc_ds ; dh = acc_dh + dh' * z — all global I/O as full 128-byte rows through the pair staging planes
     const int lw = warp - 2, q = warp & 3, csub = lw >> 2;
-    const int row = q * 32 + lane;
-    const int gc0 = slice * kSliceCols + csub * 16, lc0 = csub * 16;
+    const int bar_id = 1 + q;
+    float *P0 = reinterpret_cast<float *>(smem + kDgOffStage) + (size_t)q * 2 * kStagePlaneFloats;
+    float *P1 = P0 + kStagePlaneFloats;
+    const int lc0 = csub * 16, gcs = slice * kSliceCols;
     const size_t plane = (size_t)N * kD;
-    float4 dn[4], zn[4];
-    auto prefetch = [&](int kk) {
-      const int64_t nd = (int64_t)(group + kk * num_groups) * kTileM + row;
-      if (kk < my_tiles && nd < N) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          dn[i] = ldg_nc_f4(dh_out + nd * kD + gc0 + i * 4);
-          zn[i] = ldg_nc_f4(gates + plane + nd * kD + gc0 + i * 4);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dn[i] = zn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    auto rows_of = [&](int kk) -> int {
+      if (kk >= my_tiles) return 0;
+      const int64_t r0 = (int64_t)(group + kk * num_groups) * kTileM + q * 32;
+      const int64_t rem = (int64_t)N - r0;
+      return rem <= 0 ? 0 : (rem > 32 ? 32 : (int)rem);
     };
-    prefetch(0);
+    float4 dreg[4], zreg[4];
+    {
+      const int64_t r0 = (int64_t)group * kTileM + q * 32;
+      stage_fetch_rows(dh_out + r0 * kD + gcs, kD, lane, csub, rows_of(0), dreg);
+      stage_fetch_rows(gates + plane + r0 * kD + gcs, kD, lane, csub, rows_of(0), zreg);
+    }
     for (int k = 0; k < my_tiles; ++k) {
       const int tile = group + k * num_groups;
       const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
-      const int64_t node = (int64_t)tile * kTileM + row;
-      float4 dv[4], zv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { dv[i] = dn[i]; zv[i] = zn[i]; }
-      prefetch(k + 1);
+      const int64_t r0 = (int64_t)tile * kTileM + q * 32;
+      const int rows_valid = rows_of(k);
+      stage_put_rows(P0, lane, csub, dreg);
+      stage_put_rows(P1, lane, csub, zreg);
+      pair_sync(bar_id);
+      float dv[16], zv[16];
+      stage_read16(P0, lane, csub, dv);
+      stage_read16(P1, lane, csub, zv);
+      pair_sync(bar_id);                               // both warps have read the inputs: the planes may be overwritten
+      {
+        const int64_t rn = (int64_t)(group + (k + 1) * num_groups) * kTileM + q * 32;
+        stage_fetch_rows(dh_out + rn * kD + gcs, kD, lane, csub, rows_of(k + 1), dreg);
+        stage_fetch_rows(gates + plane + rn * kD + gcs, kD, lane, csub, rows_of(k + 1), zreg);
+      }
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + lc0);
@@ -263,17 +275,14 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
-      if (node < N) {
-        float *pds = ds + node * kD + gc0;
-        float *pdh = dh + node * kD + gc0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<float4 *>(pds + i * 4) = make_float4(a_ds[i * 4], a_ds[i * 4 + 1], a_ds[i * 4 + 2], a_ds[i * 4 + 3]);
-          *reinterpret_cast<float4 *>(pdh + i * 4) =
-              make_float4(fmaf(dv[i].x, zv[i].x, a_dh[i * 4]), fmaf(dv[i].y, zv[i].y, a_dh[i * 4 + 1]),
-                          fmaf(dv[i].z, zv[i].z, a_dh[i * 4 + 2]), fmaf(dv[i].w, zv[i].w, a_dh[i * 4 + 3]));
-        }
-      }
+      for (int i = 0; i < 16; ++i) a_dh[i] = fmaf(dv[i], zv[i], a_dh[i]);
+      stage_write16(P0, lane, csub, a_ds);
+      stage_write16(P1, lane, csub, a_dh);
+      pair_sync(bar_id);
+      stage_store_rows(P0, ds + r0 * kD + gcs, kD, lane, csub, rows_valid);
+      stage_store_rows(P1, dh + r0 * kD + gcs, kD, lane, csub, rows_valid);
+      pair_sync(bar_id);
     }
   }
   tc_fence_before();
@@ -389,35 +398,45 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
       umma_commit(acc_bar);
     }
   } else {
-    // epilogue: this CTA's private partial sums (thread = one of the 128 rows of a gate block, 64 columns)
+    // epilogue: this CTA's private partial sums.  Thread = one of the 128 rows of a gate block, this warp's 64 columns;
+    // the read-modify-write of the partial slot goes through a warp-private staging tile [32 rows][68 floats] carved out
+    // of the (now idle) operand ring, so global accesses are 256-byte row segments instead of 16-byte pieces.
     const int lw = warp - 2, qd = warp & 3, chalf = lw >> 2;
-    const int m = qd * 32 + lane;
+    constexpr int kLd = 68;
     float *dst0 = partial + ((size_t)role * gridDim.x + blockIdx.x) * kWgPartialFloats;
     if (my_tiles > 0) {
-      mbar_wait(acc_bar, 0);
+      mbar_wait(acc_bar, 0);       // every MMA (and therefore every read of the ring) has completed
       tc_fence_after();
     }
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)lw * 32 * kLd;
 #pragma unroll 1
     for (int g = 0; g < 3; ++g) {
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = chalf * 64 + cc * 16;
         float a[16];
         if (my_tiles > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + col0), a);
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * 128 + chalf * 64 + cc * 16), a);
           tmem_ld_wait();
         } else {
 #pragma unroll
           for (int x = 0; x < 16; ++x) a[x] = 0.f;
         }
-        float *dst = dst0 + (size_t)(g * 128 + m) * kD + col0;
 #pragma unroll
-        for (int x4 = 0; x4 < 4; ++x4) {
-          float4 v = make_float4(a[x4 * 4], a[x4 * 4 + 1], a[x4 * 4 + 2], a[x4 * 4 + 3]);
-          if (!first) f4_add(v, *reinterpret_cast<const float4 *>(dst + x4 * 4));
-          *reinterpret_cast<float4 *>(dst + x4 * 4) = v;
-        }
+        for (int x4 = 0; x4 < 4; ++x4)
+          *reinterpret_cast<float4 *>(stg + lane * kLd + cc * 16 + x4 * 4) = make_float4(a[x4 * 4], a[x4 * 4 + 1], a[x4 * 4 + 2], a[x4 * 4 + 3]);
       }
+      __syncwarp();
+      // rows 32*qd .. +31 of gate block g, columns 64*chalf .. +63: lane = (row parity, 16-byte piece)
+      float *gdst = dst0 + (size_t)(g * 128 + qd * 32) * kD + chalf * 64;
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const int row = 2 * j + (lane >> 4), piece = lane & 15;
+        float4 v = *reinterpret_cast<const float4 *>(stg + row * kLd + piece * 4);
+        float4 *gp = reinterpret_cast<float4 *>(gdst + (size_t)row * kD + piece * 4);
+        if (!first) f4_add(v, *gp);
+        *gp = v;
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();

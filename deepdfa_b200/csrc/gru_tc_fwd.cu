@@ -31,14 +31,18 @@ constexpr int kWRows = 3 * kSliceCols;                   // 96 weight rows per s
 constexpr int kWImgBytes = kWRows * 128;                 // 12 KB: one (matrix p, kblock, variant) image
 constexpr int kWSliceBytes = 8 * kWImgBytes;             // 96 KB per slice, index (p*2 + kb)*2 + v
 constexpr int kBiasSlice = 7 * kSliceCols;               // floats per slice
-// A feed: ONE cp.async.bulk per operand tile (64 KB = [hi|lo][kb0|kb1], contiguous in the image), two stages.
-// profiles/r01g_copy_bench.log: a 1-D bulk copy costs ~0.42 us almost independently of its size and copies from one
-// SM do not overlap, so throughput = size / 0.42 us (16 KB -> 38 GB/s/SM, 32 KB -> 70 GB/s/SM): copy whole tiles.
+// A feed: cp.async.bulk of one VARIANT (hi or lo) of an operand tile = 32 KB ([kb0 | kb1], contiguous in the image),
+// two stages.  profiles/r01g_copy_bench.log: a 1-D bulk copy costs ~0.42 us almost independently of its size and the
+// copies of one SM do not overlap, so throughput = size / 0.42 us (16 KB -> 38 GB/s/SM, 32 KB -> 70 GB/s/SM).
 constexpr int kAStages = 2;
-constexpr int kAStageBytes = kImageTileBytes;            // 64 KB
+constexpr int kAStageBytes = 2 * kChunkBytes;            // 32 KB
 constexpr int kAccBufs = 4;
 constexpr int kOffA = kWSliceBytes;
-constexpr int kOffBias = kOffA + kAStages * kAStageBytes;
+// epilogue staging (tc_common.cuh "coalesced epilogue I/O"): per warp pair 2 output planes + 1 input plane
+constexpr int kStgPlanes = 3;
+constexpr int kOffStage = kOffA + kAStages * kAStageBytes;
+constexpr int kStageBytes = 4 * kStgPlanes * kStagePlaneFloats * 4;
+constexpr int kOffBias = kOffStage + kStageBytes;
 constexpr int kOffBar = kOffBias + kBiasSlice * 4;
 constexpr int kNumBars = 1 + 2 * kAStages + 2 * kAccBufs;
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===== TMA producer: resident weights once, then the A chunks of every tile =====
+    // ===== TMA producer: resident weights once, then per tile the operand variants s_hi, s_lo, h_hi, h_lo =====
     if (lane == 0 && my_tiles > 0) {
       mbar_arrive_expect_tx(w_full, kWSliceBytes);
       for (int i = 0; i < 8; ++i)
@@ -155,12 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
-        for (int p = 0; p < 2; ++p, ++cc) {
+        for (int pv = 0; pv < 4; ++pv, ++cc) {
+          const int p = pv >> 1, v = pv & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
           mbar_arrive_expect_tx(a_full(stage), kAStageBytes);
-          bulk_g2s(sbase + kOffA + stage * kAStageBytes, (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes, kAStageBytes,
-                   a_full(stage));
+          bulk_g2s(sbase + kOffA + stage * kAStageBytes,
+                   (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)v * kAStageBytes, kAStageBytes, a_full(stage));
         }
       }
     }
@@ -175,130 +180,154 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [gin 0-31 | r 32-63 | z 64-95 | ghn 96-127]
-        for (int ci = 0; ci < 8; ++ci) {
-          const int p = ci >> 2, kb = (ci >> 1) & 1, v = ci & 1;
+        for (int pv = 0; pv < 4; ++pv, ++cc) {
+          const int p = pv >> 1, v = pv & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
-          if ((ci & 3) == 0) {             // first chunk of an operand: wait for its 64 KB stage
-            mbar_wait(a_full(stage), use & 1);
-            tc_fence_after();
-          }
-          const uint32_t a_addr = sbase + kOffA + stage * kAStageBytes + (uint32_t)(v * 2 + kb) * kChunkBytes;
+          mbar_wait(a_full(stage), use & 1);
+          tc_fence_after();
           const int n_wv = (v == 0) ? 2 : 1;   // a_hi pairs with w_hi and w_lo; a_lo with w_hi only
-          for (int wv = 0; wv < n_wv; ++wv) {
-            const uint32_t w_addr = sbase + (uint32_t)(((p * 2 + kb) * 2 + wv) * kWImgBytes);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t a_addr = sbase + kOffA + stage * kAStageBytes + (uint32_t)kb * kChunkBytes;
+            for (int wv = 0; wv < n_wv; ++wv) {
+              const uint32_t w_addr = sbase + (uint32_t)(((p * 2 + kb) * 2 + wv) * kWImgBytes);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t ad = make_desc(a_addr + k4 * 32);
-              const bool first = (kb == 0 && v == 0 && wv == 0 && k4 == 0);
-              // p = 0: [gin | r | z] (zero-initialised by the first MMA of the tile);
-              // p = 1: [r | z | ghn] accumulates onto r, z — ghn must start from zero, so the first p = 1 MMA of a tile
-              //        is split into an accumulating N = 64 and a zero-initialising N = 32.
-              if (p == 0) {
-                umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc96, first ? 0u : 1u);
-              } else if (!first) {
-                umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), kIdesc96, 1u);
-              } else {
-                umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), make_idesc(64), 1u);
-                umma_f16(d_base + 96, ad, make_desc(w_addr + 64 * 128 + k4 * 32), make_idesc(32), 0u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t ad = make_desc(a_addr + k4 * 32);
+                const bool first = (v == 0 && kb == 0 && wv == 0 && k4 == 0);
+                // p = 0: [gin | r | z] (zero-initialised by the first MMA of the tile);
+                // p = 1: [r | z | ghn] accumulates onto r, z — ghn must start from zero, so the first p = 1 MMA of a tile
+                //        is split into an accumulating N = 64 and a zero-initialising N = 32.
+                if (p == 0) {
+                  umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc96, first ? 0u : 1u);
+                } else if (!first) {
+                  umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), kIdesc96, 1u);
+                } else {
+                  umma_f16(d_base + 32, ad, make_desc(w_addr + k4 * 32), make_idesc(64), 1u);
+                  umma_f16(d_base + 96, ad, make_desc(w_addr + 64 * 128 + k4 * 32), make_idesc(32), 0u);
+                }
               }
             }
           }
-          if ((ci & 3) == 3) {             // last chunk of the operand: release its stage
-            umma_commit(a_empty(stage));
-            ++cc;
-          }
+          umma_commit(a_empty(stage));
         }
         umma_commit(acc_full(buf));
       }
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue: warps w and w+4 share a TMEM lane quarter (32 rows) and hold column halves 0 / 1 of the slice =====
     const int lw = warp - 2;
     const int q = warp & 3;          // TMEM lane quarter
     const int csub = lw >> 2;        // which 16 of the slice's 32 columns
-    const int row = q * 32 + lane;
-    const int gc0 = slice * kSliceCols + csub * 16;   // first global column of this thread
+    const int bar_id = 1 + q;        // named barrier of this warp pair
+    float *P0 = reinterpret_cast<float *>(smem + kOffStage) + (size_t)q * kStgPlanes * kStagePlaneFloats;
+    float *P1 = P0 + kStagePlaneFloats, *PI = P1 + kStagePlaneFloats;
     const int lc0 = csub * 16;                         // first column inside the slice
+    const int gcs = slice * kSliceCols;                // first global column of the slice
     const size_t plane = (size_t)N * kD;
-    // software prefetch, one tile ahead: the fp32 h row piece and the in-degree of this thread's node
-    float4 hn[4];
-    int32_t ip0n = 0, ip1n = 0;
-    auto prefetch = [&](int kk) {
-      const int64_t nd = (int64_t)(group + kk * num_groups) * kTileM + row;
-      if (kk < my_tiles && nd < N) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hn[i] = ldg_nc_f4(h + nd * kD + gc0 + i * 4);
-        ip0n = __ldg(indptr + nd);
-        ip1n = __ldg(indptr + nd + 1);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ip0n = ip1n = 0;
-      }
+    auto rows_of = [&](int kk) -> int {                // valid rows of this pair's 32-row block in tile kk
+      if (kk >= my_tiles) return 0;
+      const int64_t r0 = (int64_t)(group + kk * num_groups) * kTileM + q * 32;
+      const int64_t rem = (int64_t)N - r0;
+      return rem <= 0 ? 0 : (rem > 32 ? 32 : (int)rem);
     };
-    prefetch(0);
+    float4 hreg[4];                                    // next tile's h rows, fetched one tile ahead (coalesced)
+    {
+      const int64_t r0 = (int64_t)group * kTileM + q * 32;
+      stage_fetch_rows(h + r0 * kD + gcs, kD, lane, csub, rows_of(0), hreg);
+    }
     for (int k = 0; k < my_tiles; ++k) {
       const int tile = group + k * num_groups;
       const int buf = k % kAccBufs, buse = k / kAccBufs;
-      const int64_t node = (int64_t)tile * kTileM + row;
-      const bool valid = node < N;
+      const int64_t r0 = (int64_t)tile * kTileM + q * 32;      // first node row of this pair's block
+      const int64_t node = r0 + lane;
+      const int rows_valid = rows_of(k);
+      const bool valid = lane < rows_valid;
+      // h rows of this tile: registers -> staging -> this thread's row piece
+      stage_put_rows(PI, lane, csub, hreg);
+      pair_sync(bar_id);
       float hv[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { hv[i * 4 + 0] = hn[i].x; hv[i * 4 + 1] = hn[i].y; hv[i * 4 + 2] = hn[i].z; hv[i * 4 + 3] = hn[i].w; }
-      const float deg = (float)(ip1n - ip0n);
-      prefetch(k + 1);
+      stage_read16(PI, lane, csub, hv);
+      {
+        const int64_t rn = (int64_t)(group + (k + 1) * num_groups) * kTileM + q * 32;
+        stage_fetch_rows(h + rn * kD + gcs, kD, lane, csub, rows_of(k + 1), hreg);
+      }
+      const float deg = valid ? (float)(__ldg(indptr + node + 1) - __ldg(indptr + node)) : 0.f;
+
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + lc0);
-      float ar[16], az[16], agi[16], agh[16];
-      tmem_ld16(taddr + 0, agi);
-      tmem_ld16(taddr + 32, ar);
-      tmem_ld16(taddr + 64, az);
-      tmem_ld16(taddr + 96, agh);
+      float va[16], vb[16];
+      tmem_ld16(taddr + 32, va);   // r accumulator
+      tmem_ld16(taddr + 96, vb);   // gh_n accumulator
+      tmem_ld_wait();
+      float o_r[16], o_g[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = lc0 + i;
+        o_r[i] = fast_sigmoid(va[i] + fmaf(deg, bias_s[4 * kSliceCols + c], bias_s[0 * kSliceCols + c]));
+        o_g[i] = vb[i] + bias_s[3 * kSliceCols + c];
+      }
+      tmem_ld16(taddr + 64, va);   // z accumulator
+      tmem_ld16(taddr + 0, vb);    // gi_n accumulator
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has drained its part of the buffer
-      float o_r[16], o_z[16], o_n[16], o_g[16], o_h[16];
+      float o_z[16], o_n[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int c = lc0 + i;
-        const float r = fast_sigmoid(ar[i] + fmaf(deg, bias_s[4 * kSliceCols + c], bias_s[0 * kSliceCols + c]));
-        const float z = fast_sigmoid(az[i] + fmaf(deg, bias_s[5 * kSliceCols + c], bias_s[1 * kSliceCols + c]));
-        const float ghn = agh[i] + bias_s[3 * kSliceCols + c];
-        const float nn = fast_tanh(agi[i] + fmaf(deg, bias_s[6 * kSliceCols + c], bias_s[2 * kSliceCols + c]) + r * ghn);
-        o_r[i] = r; o_z[i] = z; o_n[i] = nn; o_g[i] = ghn;
-        o_h[i] = valid ? fmaf(z, hv[i] - nn, nn) : 0.f;
+        o_z[i] = fast_sigmoid(va[i] + fmaf(deg, bias_s[5 * kSliceCols + c], bias_s[1 * kSliceCols + c]));
+        o_n[i] = fast_tanh(vb[i] + fmaf(deg, bias_s[6 * kSliceCols + c], bias_s[2 * kSliceCols + c]) + o_r[i] * o_g[i]);
       }
-      // h' image (all 128 rows of the tile: rows past N are zero — the weight-gradient GEMM sums over nodes)
-      if (h_out_img) {
+      if (gates) {
+        float *g0 = gates + r0 * kD + gcs;
+        stage_write16(P0, lane, csub, o_r);
+        stage_write16(P1, lane, csub, o_g);
+        pair_sync(bar_id);
+        stage_store_rows(P0, g0, kD, lane, csub, rows_valid);
+        stage_store_rows(P1, g0 + 3 * plane, kD, lane, csub, rows_valid);
+        pair_sync(bar_id);
+        stage_write16(P0, lane, csub, o_z);
+        stage_write16(P1, lane, csub, o_n);
+        pair_sync(bar_id);
+        stage_store_rows(P0, g0 + plane, kD, lane, csub, rows_valid);
+        stage_store_rows(P1, g0 + 2 * plane, kD, lane, csub, rows_valid);
+        pair_sync(bar_id);
+      }
+      // h' (rows past N are zero: the image's padding rows must be zero for the weight-gradient GEMM)
+      float o_h[16];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+      for (int i = 0; i < 16; ++i) o_h[i] = valid ? fmaf(o_z[i], hv[i] - o_n[i], o_n[i]) : 0.f;
+      stage_write16(P0, lane, csub, o_h);
+      if (h_out_img) {
+        // image words of this thread's 16 columns: P1 row = [16 words hi | 16 words lo] for the slice's 32 columns
+        uint4 ph0, pl0, ph1, pl1;
+        {
           float x8[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x8[i] = o_h[u * 8 + i];
-          uint4 ph, pl;
-          split8(x8, ph, pl);
-          *reinterpret_cast<uint4 *>(h_out_img + image_offset(node, gc0 + u * 8, 0)) = ph;
-          *reinterpret_cast<uint4 *>(h_out_img + image_offset(node, gc0 + u * 8, 1)) = pl;
+          for (int i = 0; i < 8; ++i) x8[i] = o_h[i];
+          split8(x8, ph0, pl0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x8[i] = o_h[8 + i];
+          split8(x8, ph1, pl1);
+        }
+        uint4 *rowp = reinterpret_cast<uint4 *>(P1 + lane * kStageLd);
+        rowp[2 * csub] = ph0; rowp[2 * csub + 1] = ph1;
+        rowp[4 + 2 * csub] = pl0; rowp[4 + 2 * csub + 1] = pl1;
+      }
+      pair_sync(bar_id);
+      stage_store_rows(P0, h_out + r0 * kD + gcs, kD, lane, csub, rows_valid);
+      if (h_out_img) {
+        const int piece = lane & 7;              // 0-3: hi pieces (8 columns each), 4-7: lo pieces
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = csub * 16 + j * 4 + (lane >> 3);
+          const uint4 w = *reinterpret_cast<const uint4 *>(P1 + row * kStageLd + piece * 4);
+          *reinterpret_cast<uint4 *>(h_out_img + image_offset(r0 + row, gcs + 8 * (piece & 3), piece >> 2)) = w;
         }
       }
-      if (valid) {
-        float *dst = h_out + node * kD + gc0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4 *>(dst + i * 4) = make_float4(o_h[i * 4], o_h[i * 4 + 1], o_h[i * 4 + 2], o_h[i * 4 + 3]);
-        if (gates) {
-          float *gd = gates + node * kD + gc0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            *reinterpret_cast<float4 *>(gd + i * 4) = make_float4(o_r[i * 4], o_r[i * 4 + 1], o_r[i * 4 + 2], o_r[i * 4 + 3]);
-            *reinterpret_cast<float4 *>(gd + plane + i * 4) = make_float4(o_z[i * 4], o_z[i * 4 + 1], o_z[i * 4 + 2], o_z[i * 4 + 3]);
-            *reinterpret_cast<float4 *>(gd + 2 * plane + i * 4) = make_float4(o_n[i * 4], o_n[i * 4 + 1], o_n[i * 4 + 2], o_n[i * 4 + 3]);
-            *reinterpret_cast<float4 *>(gd + 3 * plane + i * 4) = make_float4(o_g[i * 4], o_g[i * 4 + 1], o_g[i * 4 + 2], o_g[i * 4 + 3]);
-          }
-        }
-      }
+      pair_sync(bar_id);
     }
   }
   tc_fence_before();
