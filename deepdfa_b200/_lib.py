@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ddfa_device_supported": (_int, []),
     "ddfa_launch_count": (C.c_longlong, []),
     "ddfa_engine_available": (_int, [_int]),
+    "ddfa_debug_set": (_int, [_int, _int]),
     "ddfa_build_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "ddfa_build_csr": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_graph_ptr": (_int, [_vp, _i32, _vp, _vp]),
@@ -55,7 +56,7 @@ _SIGNATURES = {
     "ddfa_act_to_image": (_int, [_vp, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum_image": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ddfa_gru_step_fwd_image": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "ddfa_gru_step_bwd_image": (_int, [_vp] * 5 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
+    "ddfa_gru_step_bwd_image": (_int, [_vp] * 6 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd_finish": (_int, [_i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "ddfa_gru_step_prepare_bwd": (_int, [_vp, _vp, _i32, _int, _vp, _sz, _vp]),

@@ -32,6 +32,13 @@ int ddfa_engine_available(int engine) {
   return 0;
 }
 
+int ddfa_debug_set(int key, int value) {
+  switch (key) {
+    case 1: ddfa::gru_tc2_set_cluster(value); return DDFA_OK;   // forward GRU kernel: cluster-multicast operand feed on/off
+    default: ddfa::set_error("ddfa_debug_set: unknown key %d", key); return DDFA_ERR_INVALID_ARG;
+  }
+}
+
 long long ddfa_launch_count(void) { return ddfa::g_launches.load(std::memory_order_relaxed); }
 
 int ddfa_device_supported(void) {

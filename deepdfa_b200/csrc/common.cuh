@@ -50,6 +50,7 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
 // gru_tc_fwd.cu — tcgen05 engine, forward (D == 128; weight-stationary, activation images)
 size_t act_image_bytes(int64_t n);
 int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
+void gru_tc2_set_cluster(int on);
 size_t gru_tc2_workspace_bytes();
 int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -58,9 +59,9 @@ int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const
 // gru_tc_bwd.cu — tcgen05 engine, backward (gate backward -> q images, dgrad, wgrad)
 size_t gru_tc2_bwd_workspace_bytes(int32_t N);
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
-int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
-                     float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
-                     size_t workspace_bytes, int wgrad_mode, cudaStream_t stream);
+int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, const void *s_img, const float *gates,
+                     const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+                     float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream);
 int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {

@@ -296,9 +296,9 @@ size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
   return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // dgi | dgh
 }
 
-int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates, const int32_t *indptr,
-                            int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
-                            float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode,
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *h_image, const void *s_image, const float *gates,
+                            const int32_t *indptr, int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold,
+                            float *db_ih, float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode,
                             void *stream_) {
   using namespace ddfa;
   DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_bwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
@@ -307,7 +307,7 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_i
   DDFA_REQUIRE(dh_out && h && s_image && gates && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
                "ddfa_gru_step_bwd_image: NULL pointer");
   DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image: dh must not alias dh_out");
-  return gru_tc2_step_bwd(dh_out, h, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+  return gru_tc2_step_bwd(dh_out, h, h_image, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
                           workspace_bytes, wgrad_mode, as_stream(stream_));
 }
 
@@ -351,8 +351,8 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
     void *s_img = static_cast<uint8_t *>(workspace) + gru_tc2_bwd_workspace_bytes(N);
     rc = act_to_image(s, N, s_img, stream);
     if (rc) return rc;
-    return gru_tc2_step_bwd(dh_out, h, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
-                            workspace_bytes, /*wgrad_mode=*/0, stream);
+    return gru_tc2_step_bwd(dh_out, h, /*h_img_in=*/nullptr, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,
+                            workspace, workspace_bytes, /*wgrad_mode=*/0, stream);
   }
   float *dgi = static_cast<float *>(workspace);
   float *dgh = dgi + (size_t)N * 3 * D;

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__rest
     split4(qz, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_lo) = pl;
     split4(qn, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_lo) = pl;
     split4(qnr, ph, pl); *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_lo) = pl;
-    split4(hv, ph, pl);  *reinterpret_cast<uint2 *>(h_img + o_hi) = ph;                  *reinterpret_cast<uint2 *>(h_img + o_lo) = pl;
+    if (h_img) {   // only when the caller did not keep the forward pass's image of h_t
+      split4(hv, ph, pl); *reinterpret_cast<uint2 *>(h_img + o_hi) = ph; *reinterpret_cast<uint2 *>(h_img + o_lo) = pl;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
@@ -173,8 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
   if (warp == 0) {
     if (lane == 0 && my_tiles > 0) {
       mbar_arrive_expect_tx(w_full, kDgWSliceBytes);
-      for (int i = 0; i < 12; ++i)
-        bulk_g2s(sbase + i * kDgWImgBytes, packed + (size_t)slice * kDgWSliceBytes + (size_t)i * kDgWImgBytes, kDgWImgBytes, w_full);
+      bulk_g2s(sbase, packed + (size_t)slice * kDgWSliceBytes, kDgWSliceBytes, w_full);   // one 96 KB copy
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
@@ -495,9 +496,10 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
 
 // wgrad_mode: 0 = immediate (dW += this step's contribution before returning), 1 = first step of a deferred accumulation
 // (partials overwritten), 2 = further deferred step (partials accumulated); deferred passes end with gru_tc2_bwd_finish.
-int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, const float *gates, const int32_t *indptr, int32_t N,
-                     float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh, void *workspace,
-                     size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
+// h_img_in: the activation image of h (kept from the forward pass) or NULL (then it is rebuilt inside the workspace).
+int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, const void *s_img, const float *gates,
+                     const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+                     float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
     set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N));
     return DDFA_ERR_WORKSPACE;
@@ -505,11 +507,12 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *s_img, con
   uint8_t *packed = static_cast<uint8_t *>(workspace);
   const size_t img = tcc::image_bytes(N);
   uint8_t *q_img = packed + tc2b::kDgPackedBytes;
-  uint8_t *h_img = q_img + 4 * img;
-  float *partial = reinterpret_cast<float *>(h_img + img);
+  uint8_t *h_img_ws = q_img + 4 * img;
+  float *partial = reinterpret_cast<float *>(h_img_ws + img);
+  const uint8_t *h_img = h_img_in ? static_cast<const uint8_t *>(h_img_in) : h_img_ws;
   const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
   tc2b::gate_bwd_image_kernel<<<(unsigned)((rows + tc2b::kGbRows - 1) / tc2b::kGbRows), 256, 0, stream>>>(
-      dh_out, h, gates, indptr, N, q_img, img, h_img, db_fold, db_ih, db_hh);
+      dh_out, h, gates, indptr, N, q_img, img, h_img_in ? nullptr : h_img_ws, db_fold, db_ih, db_hh);
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kDgSmemAlloc));
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));

@@ -44,7 +44,7 @@ constexpr int kOffStage = kOffA + kAStages * kAStageBytes;
 constexpr int kStageBytes = 4 * kStgPlanes * kStagePlaneFloats * 4;
 constexpr int kOffBias = kOffStage + kStageBytes;
 constexpr int kOffBar = kOffBias + kBiasSlice * 4;
-constexpr int kNumBars = 1 + 2 * kAStages + 2 * kAccBufs;
+constexpr int kNumBars = 1 + 3 * kAStages + 2 * kAccBufs;   // w_full, a_full/a_empty/a_ready[stages], acc_full/acc_empty[bufs]
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemAlloc = kOffTmemPtr + 16 + 1024;
 constexpr int kThreads = 320;
@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const float *__restrict__ w_f
   }
 }
 
+// CLUSTER: the 4 slice-CTAs of a tile group form a thread-block cluster and each operand variant of a tile (32 KB) is
+// fetched from L2 ONCE — CTA pv issues variant pv (s_hi, s_lo, h_hi, h_lo) as a multicast bulk copy into the same stage of
+// all four CTAs, after every CTA has armed its full barrier for that stage use and signalled it on the issuer's a_ready
+// barrier.  Per-SM copy-engine work drops from 4 copies per tile to 1 (the engine serialises copies at ~0.45 us each).
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
                                                               const float *__restrict__ h, const int32_t *__restrict__ indptr,
                                                               const uint8_t *__restrict__ packed, int32_t N,
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   auto a_empty = [&](int i) { return bar0 + 8u * (1 + kAStages + i); };
   auto acc_full = [&](int i) { return bar0 + 8u * (1 + 2 * kAStages + i); };
   auto acc_empty = [&](int i) { return bar0 + 8u * (1 + 2 * kAStages + kAccBufs + i); };
+  auto a_ready = [&](int i) { return bar0 + 8u * (1 + 2 * kAStages + 2 * kAccBufs + i); };   // CLUSTER only
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemPtr);
   float *bias_s = reinterpret_cast<float *>(smem + kOffBias);
 
@@ -135,6 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
     mbar_init(w_full, 1);
     for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < kAccBufs; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
+    for (int i = 0; i < kAStages; ++i) mbar_init(a_ready(i), kSlices);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -147,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -154,8 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
     // ===== TMA producer: resident weights once, then per tile the operand variants s_hi, s_lo, h_hi, h_lo =====
     if (lane == 0 && my_tiles > 0) {
       mbar_arrive_expect_tx(w_full, kWSliceBytes);
-      for (int i = 0; i < 8; ++i)
-        bulk_g2s(sbase + i * kWImgBytes, packed + (size_t)slice * kWSliceBytes + (size_t)i * kWImgBytes, kWImgBytes, w_full);
+      bulk_g2s(sbase, packed + (size_t)slice * kWSliceBytes, kWSliceBytes, w_full);   // one 96 KB copy (copy cost ~ size-independent)
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
@@ -164,8 +171,17 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
           const int stage = cc % kAStages, use = cc / kAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
           mbar_arrive_expect_tx(a_full(stage), kAStageBytes);
-          bulk_g2s(sbase + kOffA + stage * kAStageBytes,
-                   (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)v * kAStageBytes, kAStageBytes, a_full(stage));
+          const uint8_t *src = (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)v * kAStageBytes;
+          if (!CLUSTER) {
+            bulk_g2s(sbase + kOffA + stage * kAStageBytes, src, kAStageBytes, a_full(stage));
+          } else {
+            // tell the issuer of this variant (CTA rank pv) that my stage is free and armed; the issuer waits for all 4
+            mbar_arrive_remote(a_ready(stage), (uint32_t)pv);
+            if (slice == pv) {
+              mbar_wait_cluster(a_ready(stage), k & 1);     // this CTA issues once per tile on stage pv % 2
+              bulk_g2s_mcast(sbase + kOffA + stage * kAStageBytes, src, kAStageBytes, a_full(stage), (uint16_t)0xF);
+            }
+          }
         }
       }
     }
@@ -332,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();   // no CTA may exit while peers can still multicast into it / arrive on its barriers
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -365,20 +382,51 @@ int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
   return DDFA_OK;
 }
 
+static int g_fwd_cluster = 1;           // tuning knob (ddfa_debug_set key 1): 1 = cluster multicast feed, 0 = every CTA copies for itself
+void gru_tc2_set_cluster(int on) { g_fwd_cluster = on; }
+
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
                      void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < tc2::kPackedBytes) {
     set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, tc2::kPackedBytes);
     return DDFA_ERR_WORKSPACE;
   }
-  DDFA_CUDA(cudaFuncSetAttribute(tc2::gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
-  int groups = kNumSMs / tc2::kSlices;
+  const uint8_t *s8 = static_cast<const uint8_t *>(s_img), *h8 = static_cast<const uint8_t *>(h_img), *w8 = static_cast<const uint8_t *>(workspace);
+  uint8_t *o8 = static_cast<uint8_t *>(h_out_img);
+  if (!g_fwd_cluster) {
+    DDFA_CUDA(cudaFuncSetAttribute(tc2::gru_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemAlloc));
+    int groups = kNumSMs / tc2::kSlices;
+    if (groups > tiles) groups = tiles;
+    tc2::gru_fwd_kernel<false><<<groups * tc2::kSlices, tc2::kThreads, tc2::kSmemAlloc, stream>>>(s8, h8, h, indptr, w8, N, h_out, o8, save_gates);
+    DDFA_CHECK_LAUNCH("tc2::gru_fwd_kernel");
+    return DDFA_OK;
+  }
+  DDFA_CUDA(cudaFuncSetAttribute(tc2::gru_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemAlloc));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = tc2::kSlices;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(tc2::kThreads);
+  cfg.dynamicSmemBytes = tc2::kSmemAlloc;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // the tile schedule assumes every cluster is resident: ask how many 4-CTA clusters fit (GPC granularity: < 148 / 4)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(kNumSMs / tc2::kSlices * tc2::kSlices);
+    int n = 0;
+    DDFA_CUDA(cudaOccupancyMaxActiveClusters(&n, tc2::gru_fwd_kernel<true>, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  int groups = max_clusters;
   if (groups > tiles) groups = tiles;
-  tc2::gru_fwd_kernel<<<groups * tc2::kSlices, tc2::kThreads, tc2::kSmemAlloc, stream>>>(
-      static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr, static_cast<const uint8_t *>(workspace), N,
-      h_out, static_cast<uint8_t *>(h_out_img), save_gates);
-  DDFA_CHECK_LAUNCH("tc2::gru_fwd_kernel");
+  cfg.gridDim = dim3(groups * tc2::kSlices);
+  DDFA_CUDA(cudaLaunchKernelEx(&cfg, tc2::gru_fwd_kernel<true>, s8, h8, h, indptr, w8, (int32_t)N, h_out, o8, save_gates));
+  count_launch();
   return DDFA_OK;
 }
 

@@ -160,6 +160,7 @@ class Saved:
     seg_sum: torch.Tensor
     mlp_act: Optional[torch.Tensor]
     idx: List[torch.Tensor]
+    h_img: Optional[List[torch.Tensor]] = None   # tcgen05 engine: activation images of h[0..T-1]
 
 
 class Workspace:
@@ -253,7 +254,9 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     h_cur = x
     if use_images:
         img_bytes = L.call("ddfa_act_image_bytes", N)
-        h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(2)]
+        # training keeps the image of every h_t (the weight-gradient GEMM reads it); inference ping-pongs two
+        n_img = T if training else 2
+        h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(max(n_img, 1))]
         L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
     for t in range(T):
         if training:
@@ -267,8 +270,8 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
             g_t = None
         if use_images:
             _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), None, st, tag="gather_fwd")
-            _call("ddfa_gru_step_fwd_image", _p(s_t), _p(h_imgs[t % 2]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
-                  _p(h_imgs[(t + 1) % 2]) if t + 1 < T else None, _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
+            _call("ddfa_gru_step_fwd_image", _p(s_t), _p(h_imgs[t % n_img]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
+                  _p(h_imgs[(t + 1) % n_img]) if t + 1 < T else None, _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
         else:
             _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
             _call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
@@ -289,7 +292,8 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
            nl, _p(pooled), _p(logits), _p(gate_logit), _p(seg_max), _p(seg_sum), _p(mlp_act), st)
     saved = None
     if training:
-        saved = Saved(T, D, x, hs, ss, gs, w_fold, b_fold, pooled, gate_logit, seg_max, seg_sum, mlp_act, idx)
+        saved = Saved(T, D, x, hs, ss, gs, w_fold, b_fold, pooled, gate_logit, seg_max, seg_sum, mlp_act, idx,
+                      h_img=h_imgs if use_images else None)
     return pooled, logits, saved
 
 
@@ -337,7 +341,8 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
         if engine == ENGINE_TCGEN05:     # saved.s[t] is the activation image of s_t
-            _call("ddfa_gru_step_bwd_image", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
+            _call("ddfa_gru_step_bwd_image", _p(dh), _p(saved.h[t]), _p(saved.h_img[t]) if saved.h_img else None, _p(saved.s[t]),
+                  _p(saved.gates[t]), _p(dg.indptr), N, D,
                   _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
                   1 if t == T - 1 else 2, st, tag="ddfa_gru_step_bwd")   # deferred weight-gradient accumulation
         else:

@@ -48,6 +48,8 @@ const char *ddfa_last_error(void);
 int ddfa_device_supported(void);
 /* 1 if the given DDFA_ENGINE_* is compiled into this library, else 0 */
 int ddfa_engine_available(int engine);
+/* tuning / A-B knobs for the benchmark scripts (key 1: tcgen05 forward kernel, cluster-multicast feed 1/0) */
+int ddfa_debug_set(int key, int value);
 /* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
 long long ddfa_launch_count(void);
 
@@ -153,8 +155,9 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
  * activation image (the one ddfa_gather_sum_image wrote in the forward pass); the q matrices and h are turned
  * into images inside the workspace.  workspace: ddfa_gru_step_bwd_workspace_bytes(N, D, TCGEN05), prepared by
  * ddfa_gru_step_prepare_bwd. */
-int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *s_image, const float *gates,
-                            const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
+/* h_image: the image of h (step input) kept from the forward pass, or NULL (it is then rebuilt in the workspace). */
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *h_image, const void *s_image,
+                            const float *gates, const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
                             float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
                             void *workspace, size_t workspace_bytes, int wgrad_mode, void *stream);
 /* wgrad_mode: 0 = dw_fold / dw_hh are updated before the call returns (stream order); 1 / 2 = deferred: the

@@ -46,7 +46,7 @@ else:
     acc = [torch.zeros(3 * D, D, device=DEV), torch.zeros(3 * D, device=DEV), torch.zeros(3 * D, device=DEV),
            torch.zeros(3 * D, D, device=DEV), torch.zeros(3 * D, device=DEV)]
     for i in range(4):
-        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
+        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
                _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 1 if i == 0 else 2, st)
 torch.cuda.synchronize()
 print("done", which, N)
