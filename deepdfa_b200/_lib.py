@@ -40,6 +40,7 @@ _SIGNATURES = {
     "ddfa_launch_count": (C.c_longlong, []),
     "ddfa_engine_available": (_int, [_int]),
     "ddfa_debug_set": (_int, [_int, _int]),
+    "ddfa_debug_read": (_int, [_int, _vp, _sz]),
     "ddfa_build_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "ddfa_build_csr": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_graph_ptr": (_int, [_vp, _i32, _vp, _vp]),

@@ -51,6 +51,10 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
 size_t act_image_bytes(int64_t n);
 int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
 void gru_tc2_set_cluster(int on);
+int gru_tc2_trace_enable(int on);   // pipeline timeline of gru_fwd_kernel (development aid)
+int gru_tc2_trace_read(void *host, size_t bytes);
+int gru_tc2b_trace_enable(int on);  // same for dgrad_kernel
+int gru_tc2b_trace_read(void *host, size_t bytes);
 size_t gru_tc2_workspace_bytes();
 int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tron = (g_trace_on == 1);
+  if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
 
   if (warp == 0) {
     if (lane == 0 && my_tiles > 0) {
@@ -183,10 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
           const int m = mv >> 1, v = mv & 1;
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          if (mv == 0) trace_stamp(tron, k, 1);
           mbar_arrive_expect_tx(a_full(stage), kDgAStageBytes);
           bulk_g2s(sbase + kDgOffA + stage * kDgAStageBytes,
                    q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes + (size_t)v * kDgAStageBytes, kDgAStageBytes,
                    a_full(stage));
+          if (mv == 7) trace_stamp(tron, k, 2);
         }
       }
     }
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
         const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
+        trace_stamp(tron, k, 3);
         const uint32_t d_base = tmem_base + (uint32_t)buf * 64u;   // [ds 0-31 | dh 32-63]
         for (int mv = 0; mv < 8; ++mv, ++cc) {
           const int m = mv >> 1, v = mv & 1;
@@ -206,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
           const int stage = cc % kDgAStages, use = cc / kDgAStages;
           mbar_wait(a_full(stage), use & 1);
           tc_fence_after();
+          if (mv == 0) trace_stamp(tron, k, 4);
+          if (mv == 7) trace_stamp(tron, k, 5);
           const int n_wv = (v == 0) ? 2 : 1;
           for (int kb = 0; kb < 2; ++kb) {
             const uint32_t a_addr = sbase + kDgOffA + stage * kDgAStageBytes + (uint32_t)kb * kChunkBytes;
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
           umma_commit(a_empty(stage));
         }
         umma_commit(acc_full(buf));
+        trace_stamp(tron, k, 6);
       }
     }
   } else {
@@ -254,6 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
       const int64_t r0 = (int64_t)tile * kTileM + q * 32;
       const int rows_valid = rows_of(k);
+      const bool tr = (warp == 2 && lane == 0);
+      if (tr) trace_stamp(tron, k, 7);
       stage_put_rows(P0, lane, csub, dreg);
       stage_put_rows(P1, lane, csub, zreg);
       pair_sync(bar_id);
@@ -268,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       }
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
+      if (tr) trace_stamp(tron, k, 8);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + lc0);
       float a_ds[16], a_dh[16];
       tmem_ld16(taddr + 0, a_ds);
@@ -276,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (tr) trace_stamp(tron, k, 9);
 #pragma unroll
       for (int i = 0; i < 16; ++i) a_dh[i] = fmaf(dv[i], zv[i], a_dh[i]);
       stage_write16(P0, lane, csub, a_ds);
@@ -284,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       stage_store_rows(P0, ds + r0 * kD + gcs, kD, lane, csub, rows_valid);
       stage_store_rows(P1, dh + r0 * kD + gcs, kD, lane, csub, rows_valid);
       pair_sync(bar_id);
+      if (tr) trace_stamp(tron, k, 10);
     }
   }
   tc_fence_before();
@@ -347,6 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tron = (g_trace_on == 2) && blockIdx.y == 0;   // timeline of the role-0 CTAs (ddfa_debug_set key 2, value 2)
+  if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -357,6 +372,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
           const int slot = wg_slot(i, w);
           if (uses[slot] > 0) mbar_wait(empty_bar(slot), (uses[slot] - 1) & 1);
           ++uses[slot];
+          if (w == 0) trace_stamp(tron, i, 1);
+          if (w == 3) trace_stamp(tron, i, 2);
           const uint8_t *src;
           if (w == 0) src = (role == 0) ? s_img : h_img;
           else {
@@ -376,11 +393,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
         const int slot_b = wg_slot(i, 0);
         mbar_wait(full_bar(slot_b), uses[slot_b] & 1);
         ++uses[slot_b];
+        trace_stamp(tron, i, 3);
         for (int g = 0; g < 3; ++g) {
           const int slot_a = wg_slot(i, 1 + g);
           mbar_wait(full_bar(slot_a), uses[slot_a] & 1);
           ++uses[slot_a];
           tc_fence_after();
+          if (g == 0) trace_stamp(tron, i, 4);
+          if (g == 2) trace_stamp(tron, i, 5);
           const uint32_t a0 = sbase + slot_a * kWgSlotBytes, b0 = sbase + slot_b * kWgSlotBytes;
           const uint32_t d_addr = tmem_base + (uint32_t)g * 128u;
 #pragma unroll
@@ -395,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
           umma_commit(empty_bar(slot_a));
         }
         umma_commit(empty_bar(slot_b));
+        trace_stamp(tron, i, 6);
       }
       umma_commit(acc_bar);
     }
@@ -409,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
       mbar_wait(acc_bar, 0);       // every MMA (and therefore every read of the ring) has completed
       tc_fence_after();
     }
+    if (warp == 2 && lane == 0) trace_stamp(tron, 0, 8);
     float *stg = reinterpret_cast<float *>(smem) + (size_t)lw * 32 * kLd;
 #pragma unroll 1
     for (int g = 0; g < 3; ++g) {
@@ -439,6 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
       }
       __syncwarp();
     }
+    if (warp == 2 && lane == 0) trace_stamp(tron, 0, 10);
   }
   tc_fence_before();
   __syncthreads();
@@ -468,6 +491,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 // workspace = [dgrad per-slice transposed weight images (384 KB)][q images x4][h image][wgrad partial sums: 2 x 74 x 384 x 128 fp32]
 constexpr int kWgCtas = kNumSMs / 2;
 static size_t wg_partial_bytes() { return (size_t)2 * kWgCtas * tc2b::kWgPartialFloats * sizeof(float); }
+int gru_tc2b_trace_enable(int on) {
+  DDFA_CUDA(cudaMemcpyToSymbol(tcc::g_trace_on, &on, sizeof(int)));
+  return DDFA_OK;
+}
+int gru_tc2b_trace_read(void *host, size_t bytes) {
+  if (bytes > tcc::kTraceWords * sizeof(long long)) bytes = tcc::kTraceWords * sizeof(long long);
+  DDFA_CUDA(cudaMemcpyFromSymbol(host, tcc::g_trace, bytes));
+  return DDFA_OK;
+}
+
 size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {

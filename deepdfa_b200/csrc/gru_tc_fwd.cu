@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
   if (CLUSTER) cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tron = g_trace_on;
+  if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
 
   if (warp == 0) {
     // ===== TMA producer: resident weights once, then per tile the operand variants s_hi, s_lo, h_hi, h_lo =====
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
           const int p = pv >> 1, v = pv & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          if (pv == 0) trace_stamp(tron, k, 1);
           mbar_arrive_expect_tx(a_full(stage), kAStageBytes);
           const uint8_t *src = (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes + (size_t)v * kAStageBytes;
           if (!CLUSTER) {
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
               bulk_g2s_mcast(sbase + kOffA + stage * kAStageBytes, src, kAStageBytes, a_full(stage), (uint16_t)0xF);
             }
           }
+          if (pv == 3) trace_stamp(tron, k, 2);
         }
       }
     }
@@ -195,12 +199,15 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
         const int buf = k % kAccBufs, buse = k / kAccBufs;
         if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
         tc_fence_after();
+        trace_stamp(tron, k, 3);
         const uint32_t d_base = tmem_base + (uint32_t)buf * 128u;   // [gin 0-31 | r 32-63 | z 64-95 | ghn 96-127]
         for (int pv = 0; pv < 4; ++pv, ++cc) {
           const int p = pv >> 1, v = pv & 1;
           const int stage = cc % kAStages, use = cc / kAStages;
           mbar_wait(a_full(stage), use & 1);
           tc_fence_after();
+          if (pv == 0) trace_stamp(tron, k, 4);
+          if (pv == 3) trace_stamp(tron, k, 5);
           const int n_wv = (v == 0) ? 2 : 1;   // a_hi pairs with w_hi and w_lo; a_lo with w_hi only
           for (int kb = 0; kb < 2; ++kb) {
             const uint32_t a_addr = sbase + kOffA + stage * kAStageBytes + (uint32_t)kb * kChunkBytes;
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
           umma_commit(a_empty(stage));
         }
         umma_commit(acc_full(buf));
+        trace_stamp(tron, k, 6);
       }
     }
   } else {
@@ -258,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
       const int64_t node = r0 + lane;
       const int rows_valid = rows_of(k);
       const bool valid = lane < rows_valid;
+      const bool tr = (warp == 2 && lane == 0);
+      if (tr) trace_stamp(tron, k, 7);
       // h rows of this tile: registers -> staging -> this thread's row piece
       stage_put_rows(PI, lane, csub, hreg);
       pair_sync(bar_id);
@@ -271,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
 
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
+      if (tr) trace_stamp(tron, k, 8);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + lc0);
       float va[16], vb[16];
       tmem_ld16(taddr + 32, va);   // r accumulator
@@ -289,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has drained its part of the buffer
+      if (tr) trace_stamp(tron, k, 9);
       float o_z[16], o_n[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -344,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
         }
       }
       pair_sync(bar_id);
+      if (tr) trace_stamp(tron, k, 10);
     }
   }
   tc_fence_before();
@@ -382,8 +395,21 @@ int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
   return DDFA_OK;
 }
 
-static int g_fwd_cluster = 1;           // tuning knob (ddfa_debug_set key 1): 1 = cluster multicast feed, 0 = every CTA copies for itself
+// tuning knob (ddfa_debug_set key 1): 1 = cluster multicast feed, 0 = every CTA copies for itself.  Measured on B200 at
+// C0 (profiles/r01k_tcdebug.log): multicast 56.8 us vs unicast 43.3 us per launch, bit-identical results — at cluster
+// size 4 the L2 already de-duplicates the four unicast reads, and the cluster handshake only adds lock-step latency.
+static int g_fwd_cluster = 0;
 void gru_tc2_set_cluster(int on) { g_fwd_cluster = on; }
+
+int gru_tc2_trace_enable(int on) {
+  DDFA_CUDA(cudaMemcpyToSymbol(tcc::g_trace_on, &on, sizeof(int)));
+  return DDFA_OK;
+}
+int gru_tc2_trace_read(void *host, size_t bytes) {
+  if (bytes > tcc::kTraceWords * sizeof(long long)) bytes = tcc::kTraceWords * sizeof(long long);
+  DDFA_CUDA(cudaMemcpyFromSymbol(host, tcc::g_trace, bytes));
+  return DDFA_OK;
+}
 
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
                      void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {

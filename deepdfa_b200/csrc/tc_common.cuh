@@ -242,5 +242,16 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.f - __fdividef(2.f, e + 1.f);
 }
 
+// ---- pipeline timeline (development aid; ddfa_debug_set key 2 switches it on, ddfa_debug_read fetches it) -----------
+// Each translation unit that includes this header gets its own buffer: [CTA][tile][event] SM-clock stamps.
+constexpr int kTraceCtas = 148, kTraceTiles = 12, kTraceEvents = 12;
+constexpr size_t kTraceWords = (size_t)kTraceCtas * kTraceTiles * kTraceEvents;
+static __device__ long long g_trace[kTraceWords];
+static __device__ int g_trace_on = 0;
+__device__ __forceinline__ void trace_stamp(int on, int tile_i, int ev) {
+  if (on && blockIdx.x < kTraceCtas && tile_i < kTraceTiles)
+    g_trace[((size_t)blockIdx.x * kTraceTiles + tile_i) * kTraceEvents + ev] = clock64();
+}
+
 }  // namespace tcc
 }  // namespace ddfa

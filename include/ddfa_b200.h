@@ -50,6 +50,8 @@ int ddfa_device_supported(void);
 int ddfa_engine_available(int engine);
 /* tuning / A-B knobs for the benchmark scripts (key 1: tcgen05 forward kernel, cluster-multicast feed 1/0) */
 int ddfa_debug_set(int key, int value);
+/* development aid: key 1 / 2 = pipeline timeline of the tcgen05 forward / dgrad kernel (after ddfa_debug_set(2, 1)) */
+int ddfa_debug_read(int key, void *host_out, size_t bytes);
 /* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
 long long ddfa_launch_count(void);
 
