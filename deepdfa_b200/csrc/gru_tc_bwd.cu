@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
   if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
 
   if (warp == 0) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(w_full, kDgWSliceBytes);
       bulk_g2s(sbase, packed + (size_t)slice * kDgWSliceBytes, kDgWSliceBytes, w_full);   // one 96 KB copy
       int cc = 0;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && elect_one()) {
       constexpr uint32_t kIdesc64 = make_idesc(64), kIdesc32 = make_idesc(32);
       mbar_wait(w_full, 0);
       int cc = 0;
@@ -308,6 +308,236 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__res
 }
 
 // =================================================================================================
+// (2b) dgrad, weight-in-TMEM orientation ("dgrad3")
+// =================================================================================================
+// The in-kernel timeline of dgrad_kernel (profiles/r01l_trace_dgrad.log) shows it is bound by the operand feed: 96 KB of
+// shared memory hold the weight slice, only 2 x 32 KB are left for activations, and with ~1 us per copy in flight that
+// is ~35 GB/s per SM while every CTA has to pull 256 KB per tile (each q tile is read by four slice CTAs).
+// Here the GEMM is transposed:  D^T[col, node] = W^T[col, K] * Q[node, K]^T
+//   * A = the weights, held in TENSOR MEMORY for the life of the CTA (lane = output column, two bf16 per 32-bit column:
+//     K = 3 x 128 -> 192 columns hi + 192 columns lo), loaded once with tcgen05.st from a packed global array;
+//   * B = the q images (K-major SWIZZLE_128B, N = nodes), streamed through THREE 64 KB stages — all of shared memory
+//     is pipeline now (copy_bench2: 64 KB x 3 stages feeds ~130 GB/s per SM);
+//   * a CTA owns all 128 columns of one output (role 0: ds = [q_r q_z q_n] W', role 1: dh = [q_r q_z q_nr] Whh), so a q
+//     tile is read by 2 CTAs instead of 4 and 192 KB are pulled per 128 x 128 outputs (was 256 KB per 128 x 64);
+//   * D = two 64-node accumulator halves (64 TMEM columns each) so the epilogue of one half overlaps the MMAs of the other;
+//   * the epilogue thread holds one output column for 16 nodes per tcgen05.ld: a warp-wide store covers 32 consecutive
+//     columns of one node = one full 128-byte line, no shared-memory staging.
+constexpr int kD3Stages = 3;
+constexpr int kD3StageBytes = kImageTileBytes;               // one q-matrix tile: [hi|lo][kb0|kb1], 64 KB
+constexpr int kD3WColsHalf = 192;                            // K = 384 bf16 -> 192 packed columns per variant
+constexpr int kD3AccCol = 2 * kD3WColsHalf;                  // accumulators start at TMEM column 384
+constexpr int kD3OffBar = kD3Stages * kD3StageBytes;         // 192 KB
+constexpr int kD3NumBars = 2 * kD3Stages + 4 + 1;            // a_full, a_empty, acc_full[2], acc_empty[2], w_ready
+constexpr int kD3OffTmemPtr = kD3OffBar + kD3NumBars * 8;
+constexpr int kD3SmemAlloc = kD3OffTmemPtr + 16 + 1024;
+constexpr int kD3Chunks = 2 * kD3WColsHalf / 16;             // 24 chunks of 16 TMEM columns
+constexpr size_t kD3PackedBytes = (size_t)2 * kD3Chunks * 128 * 64;   // [role][chunk][lane][16 words] = 384 KB
+
+// packed[role][chunk][lane j][i]: TMEM column chunk*16+i of lane j = bf16 pair (W[kk][j], W[kk+1][j]), hi for columns
+// 0..191, lo for 192..383, kk = 2 * (column mod 192); W = W' (role 0) or Whh (role 1), both [3D x D] row-major.
+__global__ void dgrad3_pack_kernel(const float *__restrict__ w_fold, const float *__restrict__ w_hh, uint32_t *__restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * kD3Chunks * 128) return;
+  const int lane = idx % 128, chunk = (idx / 128) % kD3Chunks, role = idx / (128 * kD3Chunks);
+  const float *W = role == 0 ? w_fold : w_hh;
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int col = chunk * 16 + i;
+    const int v = col >= kD3WColsHalf ? 1 : 0;
+    const int kk = (col - v * kD3WColsHalf) * 2;
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(W[(size_t)kk * kD + lane], h0, l0);
+    split_bf16(W[(size_t)(kk + 1) * kD + lane], h1, l1);
+    w[i] = v ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
+             : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(packed + (size_t)idx * 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
+                                                             const float *__restrict__ dh_out, const float *__restrict__ gates,
+                                                             const uint32_t *__restrict__ packed3, int32_t N,
+                                                             float *__restrict__ ds, float *__restrict__ dh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kD3OffBar;
+  auto a_full = [&](int i) { return bar0 + 8u * i; };
+  auto a_empty = [&](int i) { return bar0 + 8u * (kD3Stages + i); };
+  auto acc_full = [&](int i) { return bar0 + 8u * (2 * kD3Stages + i); };
+  auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kD3Stages + 2 + i); };
+  const uint32_t w_ready = bar0 + 8u * (2 * kD3Stages + 4);
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kD3OffTmemPtr);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = blockIdx.x & 1;
+  const int group = blockIdx.x >> 1, num_groups = gridDim.x >> 1;
+  const int num_tiles = (N + kTileM - 1) / kTileM;
+  const int my_tiles = (num_tiles > group) ? (num_tiles - 1 - group) / num_groups + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kD3Stages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
+    mbar_init(w_ready, kEpiWarps);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tron = (g_trace_on == 1);
+  if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
+
+  if (warp == 0) {
+    // ===== producer: per tile the three q matrices of this role, one 64 KB copy each =====
+    if (elect_one()) {
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int tile = group + k * num_groups;
+        for (int g = 0; g < 3; ++g, ++cc) {
+          const int m = g < 2 ? g : (role == 0 ? 2 : 3);      // q_r, q_z, then q_n (ds) or q_nr (dh)
+          const int stage = cc % kD3Stages, use = cc / kD3Stages;
+          if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          if (g == 0) trace_stamp(tron, k, 1);
+          mbar_arrive_expect_tx(a_full(stage), kD3StageBytes);
+          bulk_g2s(sbase + stage * kD3StageBytes, q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes, kD3StageBytes,
+                   a_full(stage));
+          if (g == 2) trace_stamp(tron, k, 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (my_tiles > 0 && elect_one()) {
+      constexpr uint32_t kIdesc64 = make_idesc(64);
+      mbar_wait(w_ready, 0);
+      tc_fence_after();
+      int cc = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        for (int g = 0; g < 3; ++g, ++cc) {
+          const int stage = cc % kD3Stages, use = cc / kD3Stages;
+          mbar_wait(a_full(stage), use & 1);
+          tc_fence_after();
+          if (g == 0) trace_stamp(tron, k, 4);
+          if (g == 2) trace_stamp(tron, k, 5);
+          for (int half = 0; half < 2; ++half) {
+            if (g == 0 && k > 0) {
+              mbar_wait(acc_empty(half), (k - 1) & 1);
+              tc_fence_after();
+              if (half == 0) trace_stamp(tron, k, 3);
+            }
+            const uint32_t d_addr = tmem_base + (uint32_t)(kD3AccCol + half * 64);
+            // nodes 64*half.. of each 16 KB chunk: [hi kb0 | hi kb1 | lo kb0 | lo kb1]
+            const uint64_t b_base = make_desc(sbase + stage * kD3StageBytes + (uint32_t)half * 8192u);
+            const uint32_t a_base = tmem_base + (uint32_t)(g * 64);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint32_t kk2 = (uint32_t)(kb * 32 + k4 * 8);                           // packed weight column of this K step
+                const uint64_t b_hi = desc_advance(b_base, (uint32_t)kb * kChunkBytes + k4 * 32);
+                const uint64_t b_lo = desc_advance(b_base, (uint32_t)(2 + kb) * kChunkBytes + k4 * 32);
+                const uint32_t first = (g == 0 && kb == 0 && k4 == 0) ? 0u : 1u;
+                umma_f16_ts(d_addr, a_base + kk2, b_hi, kIdesc64, first);                       // w_hi q_hi
+                umma_f16_ts(d_addr, a_base + kD3WColsHalf + kk2, b_hi, kIdesc64, 1u);           // w_lo q_hi
+                umma_f16_ts(d_addr, a_base + kk2, b_lo, kIdesc64, 1u);                          // w_hi q_lo
+              }
+            }
+            if (g == 2) umma_commit(acc_full(half));
+          }
+          umma_commit(a_empty(stage));
+        }
+        trace_stamp(tron, k, 6);
+      }
+    }
+  } else {
+    // ===== weights -> tensor memory, then the epilogue =====
+    const int q = warp & 3;                  // TMEM lane quarter: output columns 32q .. 32q+31
+    const int e = (warp - 2) >> 2;           // which 32 nodes of a 64-node half (and which 12 weight chunks)
+    const int col = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (my_tiles > 0) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(packed3) + ((size_t)role * kD3Chunks * 128 + (size_t)col) * 4;
+#pragma unroll 4
+      for (int c = 0; c < kD3Chunks / 2; ++c) {
+        const int chunk = e * (kD3Chunks / 2) + c;
+        const uint4 *p = src + (size_t)chunk * 128 * 4;
+        const uint4 x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3);
+        const uint32_t w[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+        tmem_st16(lane_addr + (uint32_t)(chunk * 16), w);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_ready);
+
+    const size_t plane = (size_t)N * kD;
+    float *out = role == 0 ? ds : dh;
+    const bool tr = (warp == 2 && lane == 0);
+    for (int k = 0; k < my_tiles; ++k) {
+      const int tile = group + k * num_groups;
+      if (tr) trace_stamp(tron, k, 7);
+      for (int half = 0; half < 2; ++half) {
+        const int64_t node0 = (int64_t)tile * kTileM + half * 64 + e * 32;
+        int rows_valid = (int)((int64_t)N - node0);
+        rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
+        float dv[32], zv[32];
+        if (role == 1) {       // dh = acc + dh' * z : fetch the elementwise operands while the MMAs run
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = i < rows_valid;
+            dv[i] = ok ? __ldg(dh_out + (node0 + i) * kD + col) : 0.f;
+            zv[i] = ok ? __ldg(gates + plane + (node0 + i) * kD + col) : 0.f;
+          }
+        }
+        mbar_wait(acc_full(half), k & 1);
+        tc_fence_after();
+        if (tr && half == 0) trace_stamp(tron, k, 8);
+        const uint32_t taddr = lane_addr + (uint32_t)(kD3AccCol + half * 64 + e * 32);
+        float v0[16], v1[16];
+        tmem_ld16(taddr, v0);
+        tmem_ld16(taddr + 16, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(half));
+        if (tr && half == 0) trace_stamp(tron, k, 9);
+        float *o = out + node0 * kD + col;
+        if (role == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v0[i] = fmaf(dv[i], zv[i], v0[i]);
+            v1[i] = fmaf(dv[16 + i], zv[16 + i], v1[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < rows_valid) o[(size_t)i * kD] = v0[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (16 + i < rows_valid) o[(size_t)(16 + i) * kD] = v1[i];
+      }
+      if (tr) trace_stamp(tron, k, 10);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================
 // (3) wgrad
 // =================================================================================================
 // Operands are whole 128-node image tiles (64 KB, ONE bulk copy each — see the copy-size note in gru_tc_fwd.cu),
@@ -364,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
   if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -386,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && elect_one()) {
       constexpr uint32_t kIdescMN = make_idesc(128, true, true);
       int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
@@ -501,16 +731,28 @@ int gru_tc2b_trace_read(void *host, size_t bytes) {
   return DDFA_OK;
 }
 
-size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
+// workspace: [dgrad_kernel weight slices 384 KB][dgrad3 packed weights 384 KB][q images x 4][h image][wgrad partial sums]
+static constexpr size_t kPackedTotal = tc2b::kDgPackedBytes + tc2b::kD3PackedBytes;
+size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return kPackedTotal + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
+
+static int g_dgrad_v3 = 1;   // ddfa_debug_set key 3: 1 = weights-in-TMEM dgrad3_kernel, 0 = weight-slices-in-smem dgrad_kernel
+void gru_tc2_set_dgrad3(int on) { g_dgrad_v3 = on; }
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (workspace == nullptr || workspace_bytes < tc2b::kDgPackedBytes) {
+  if (workspace == nullptr || workspace_bytes < kPackedTotal) {
     set_error("tcgen05 engine (bwd): workspace too small");
     return DDFA_ERR_WORKSPACE;
   }
-  const int total = tc2b::kSlices * 3 * 2 * 8 * 64;
-  tc2b::dgrad_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, static_cast<uint8_t *>(workspace));
-  DDFA_CHECK_LAUNCH("tc2b::dgrad_pack_kernel");
+  if (g_dgrad_v3) {
+    const int total = 2 * tc2b::kD3Chunks * 128;
+    tc2b::dgrad3_pack_kernel<<<(total + 127) / 128, 128, 0, stream>>>(
+        w_fold, w_hh, reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace) + tc2b::kDgPackedBytes));
+    DDFA_CHECK_LAUNCH("tc2b::dgrad3_pack_kernel");
+  } else {
+    const int total = tc2b::kSlices * 3 * 2 * 8 * 64;
+    tc2b::dgrad_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, static_cast<uint8_t *>(workspace));
+    DDFA_CHECK_LAUNCH("tc2b::dgrad_pack_kernel");
+  }
   return DDFA_OK;
 }
 
@@ -520,7 +762,7 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
     set_error("tcgen05 engine (bwd finish): workspace too small");
     return DDFA_ERR_WORKSPACE;
   }
-  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + tc2b::kDgPackedBytes + 5 * tcc::image_bytes(N));
+  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + kPackedTotal + 5 * tcc::image_bytes(N));
   const int n4 = (int)(tc2b::kWgPartialFloats / 4);
   tc2b::wgrad_reduce_kernel<<<dim3((n4 + 255) / 256, 2), 256, 0, stream>>>(partial, kWgCtas, dw_fold, dw_hh);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_reduce_kernel");
@@ -539,7 +781,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
   }
   uint8_t *packed = static_cast<uint8_t *>(workspace);
   const size_t img = tcc::image_bytes(N);
-  uint8_t *q_img = packed + tc2b::kDgPackedBytes;
+  uint8_t *q_img = packed + kPackedTotal;
   uint8_t *h_img_ws = q_img + 4 * img;
   float *partial = reinterpret_cast<float *>(h_img_ws + img);
   const uint8_t *h_img = h_img_in ? static_cast<const uint8_t *>(h_img_in) : h_img_ws;
@@ -547,13 +789,22 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
   tc2b::gate_bwd_image_kernel<<<(unsigned)((rows + tc2b::kGbRows - 1) / tc2b::kGbRows), 256, 0, stream>>>(
       dh_out, h, gates, indptr, N, q_img, img, h_img_in ? nullptr : h_img_ws, db_fold, db_ih, db_hh);
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
-  DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kDgSmemAlloc));
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
-  int groups = kNumSMs / tc2b::kSlices;
-  if (groups > tiles) groups = tiles;
-  tc2b::dgrad_kernel<<<groups * tc2b::kSlices, tc2b::kThreads, tc2b::kDgSmemAlloc, stream>>>(q_img, img, dh_out, gates, packed, N, ds, dh);
-  DDFA_CHECK_LAUNCH("tc2b::dgrad_kernel");
+  if (g_dgrad_v3) {
+    DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kD3SmemAlloc));
+    int groups = kNumSMs / 2;
+    if (groups > tiles) groups = tiles;
+    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(
+        q_img, img, dh_out, gates, reinterpret_cast<const uint32_t *>(packed + tc2b::kDgPackedBytes), N, ds, dh);
+    DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
+  } else {
+    DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kDgSmemAlloc));
+    int groups = kNumSMs / tc2b::kSlices;
+    if (groups > tiles) groups = tiles;
+    tc2b::dgrad_kernel<<<groups * tc2b::kSlices, tc2b::kThreads, tc2b::kDgSmemAlloc, stream>>>(q_img, img, dh_out, gates, packed, N, ds, dh);
+    DDFA_CHECK_LAUNCH("tc2b::dgrad_kernel");
+  }
   // every one of the 74 x 2 CTAs writes its partial slot (zeros if it owns no tile), so the reduction can sum all of them
   tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,
                                                                                      partial, wgrad_mode == 2 ? 0 : 1);

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
 
   if (warp == 0) {
     // ===== TMA producer: resident weights once, then per tile the operand variants s_hi, s_lo, h_hi, h_lo =====
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(w_full, kWSliceBytes);
       bulk_g2s(sbase, packed + (size_t)slice * kWSliceBytes, kWSliceBytes, w_full);   // one 96 KB copy (copy cost ~ size-independent)
       int cc = 0;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const uint8_t *__r
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && elect_one()) {
       constexpr uint32_t kIdesc96 = make_idesc(96);
       mbar_wait(w_full, 0);
       int cc = 0;
@@ -381,14 +381,18 @@ int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream) {
   return DDFA_OK;
 }
 
-size_t gru_tc2_workspace_bytes() { return tc2::kPackedBytes; }
+// workspace = [v2 weight slices + biases][v3 packed weights + biases (gru_tc_fwd3.cu)]
+static int g_fwd_v3 = 1;   // ddfa_debug_set key 4: 1 = weights-in-TMEM gru_fwd3_kernel, 0 = weight-slices-in-smem gru_fwd_kernel
+void gru_tc2_set_fwd3(int on) { g_fwd_v3 = on; }
+size_t gru_tc2_workspace_bytes() { return tc2::kPackedBytes + gru_tc3_packed_bytes(); }
 
 int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (workspace == nullptr || workspace_bytes < tc2::kPackedBytes) {
-    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, tc2::kPackedBytes);
+  if (workspace == nullptr || workspace_bytes < gru_tc2_workspace_bytes()) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_workspace_bytes());
     return DDFA_ERR_WORKSPACE;
   }
+  if (g_fwd_v3) return gru_tc3_prepare(w_fold, b_fold, b_ih, w_hh, b_hh, static_cast<uint8_t *>(workspace) + tc2::kPackedBytes, stream);
   const int total = tc2::kSlices * 2 * 2 * tc2::kWRows * 8;
   tc2::pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, b_fold, b_ih, b_hh, static_cast<uint8_t *>(workspace));
   DDFA_CHECK_LAUNCH("tc2::pack_kernel");
@@ -413,10 +417,13 @@ int gru_tc2_trace_read(void *host, size_t bytes) {
 
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
                      void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (workspace == nullptr || workspace_bytes < tc2::kPackedBytes) {
-    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, tc2::kPackedBytes);
+  if (workspace == nullptr || workspace_bytes < gru_tc2_workspace_bytes()) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_workspace_bytes());
     return DDFA_ERR_WORKSPACE;
   }
+  if (g_fwd_v3)
+    return gru_tc3_step_fwd(s_img, h_img, h, indptr, N, h_out, h_out_img, save_gates,
+                            static_cast<const uint8_t *>(workspace) + tc2::kPackedBytes, stream);
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
   const uint8_t *s8 = static_cast<const uint8_t *>(s_img), *h8 = static_cast<const uint8_t *>(h_img), *w8 = static_cast<const uint8_t *>(workspace);
   uint8_t *o8 = static_cast<uint8_t *>(h_out_img);

@@ -95,7 +95,7 @@ if os.environ.get("DDFA_TRACE"):
             L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(h), _p(dg.indptr), N, D, _p(out), _p(o_img) if train else None,
                    _p(gates) if train else None, _p(ws), wsb, st)
             torch.cuda.synchronize()
-            dump_trace(1, "gru_fwd_kernel " + ("train" if train else "infer"))
+            dump_trace(3, "gru_fwd3_kernel " + ("train" if train else "infer"))
     else:
         L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
                _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 2, st)
