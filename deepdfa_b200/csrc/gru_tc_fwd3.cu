@@ -16,9 +16,11 @@
 //   * B = the s and h image tiles (K-major SWIZZLE_128B, N = 128 nodes), THREE 64 KB stages, one bulk copy per tile;
 //   * D = two 128-node accumulator buffers (TMEM columns 256..511): 48 MMAs (M = 128, N = 128, K = 16) per tile,
 //     bf16x3: w_hi x_hi + w_lo x_hi + w_hi x_lo;
-//   * epilogue: the four pre-activations of an output element sit in four TMEM lane quarters, i.e. four warps; they are
-//     exchanged through a 16-node shared-memory tile, then a warp owns whole nodes: every global access is one full
-//     128-byte line (32 consecutive columns of a node).
+//   * lane order inside a TMEM lane quarter q: lane = 8 * gate + c  (gate: 0 gi_n, 1 r, 2 z, 3 gh_n; c: column 8 q + c of
+//     the slice), so the four pre-activations of an output element are in ONE warp.  Sixteen epilogue warps (lane quarter x
+//     32-node quarter of the tile) each read 16 nodes per tcgen05.ld, swap them through a warp-private, conflict-free
+//     shared-memory tile (thread (gate, c) -> thread (node mod 4, c)), and finish nodes {g, g+4, g+8, g+12} x column c:
+//     no cross-warp barrier anywhere in the epilogue; global accesses are 32-byte row segments (full sectors).
 #include "tc_common.cuh"
 
 namespace ddfa {
@@ -32,21 +34,23 @@ constexpr int kStageBytes = kImageTileBytes;              // 64 KB: one operand 
 constexpr int kWColsHalf = 128;                           // K = 256 bf16 -> 128 packed columns per variant
 constexpr int kAccCol = 2 * kWColsHalf;                   // accumulators: TMEM columns 256 .. 511
 constexpr int kChunks = 2 * kWColsHalf / 16;              // 16 chunks of 16 TMEM columns
-constexpr int kXFloats = 4 * 16 * 32;                     // exchange tile: [pre-activation][16 nodes][32 columns]
+constexpr int kEpiWarps = 16;
+constexpr int kXGateLd = 16 * 8 + 8;                      // floats between gates in a warp's exchange tile [gate][16 nodes][8 cols] (+8: bank skew)
+constexpr int kXFloats = 4 * kXGateLd;                    // 544 floats = 2176 B per warp
 constexpr int kOffX = kStages * kStageBytes;              // 192 KB
-constexpr int kXBytes = 2 * 2 * kXFloats * 4;             // [node half][chunk parity] = 32 KB
+constexpr int kXBytes = kEpiWarps * kXFloats * 4;         // 34 KB
 constexpr int kOffBar = kOffX + kXBytes;
 constexpr int kNumBars = 2 * kStages + 4 + 1;             // a_full, a_empty, acc_full[2], acc_empty[2], w_ready
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr int kSmemAlloc = kOffTmemPtr + 16 + 1024;
-constexpr int kThreads = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kSmemAlloc = kOffTmemPtr + 16;              // the dynamic shared window itself is 1024-byte aligned (checked)
+constexpr int kThreads = 64 + 32 * kEpiWarps;             // 576
+constexpr int kBiasSlice = 7 * kSliceCols;                // per slice: const {gi_n, r, z, gh_n} then degree {gi_n, r, z}, 32 columns each
 constexpr size_t kPackedWBytes = (size_t)kSlices * kChunks * 128 * 64;     // [slice][chunk][lane][16 words] = 512 KB
-constexpr size_t kPackedBytes = kPackedWBytes + (size_t)kSlices * 128 * 8;  // + [slice][lane] {bias, degree bias}
+constexpr size_t kPackedBytes = kPackedWBytes + (size_t)kSlices * kBiasSlice * 4;
 static_assert(kSmemAlloc <= 232448, "shared memory budget");
 
-// lane L of slice j: block = L / 32 (0 gi_n, 1 r, 2 z, 3 gh_n), output column oc = 32 j + L % 32.
-// K index kk: part p = kk / 128 (0: s -> W', 1: h -> Whh), c = kk % 128.
+// lane L of slice j: quarter q = L / 32, pre-activation blk = (L / 8) % 4 (0 gi_n, 1 r, 2 z, 3 gh_n), output column
+// oc = 32 j + 8 q + L % 8.  K index kk: part p = kk / 128 (0: s -> W', 1: h -> Whh), c = kk % 128.
 __device__ __forceinline__ float weight_of(const float *__restrict__ w_fold, const float *__restrict__ w_hh, int blk, int oc, int kk) {
   const int p = kk >> 7, c = kk & 127;
   if (blk == 0) return p == 0 ? w_fold[(size_t)(2 * kD + oc) * kD + c] : 0.f;
@@ -60,7 +64,7 @@ __global__ void pack_kernel(const float *__restrict__ w_fold, const float *__res
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= kSlices * kChunks * 128) return;
   const int lane = idx % 128, chunk = (idx / 128) % kChunks, slice = idx / (128 * kChunks);
-  const int blk = lane >> 5, oc = slice * kSliceCols + (lane & 31);
+  const int blk = (lane >> 3) & 3, oc = slice * kSliceCols + (lane >> 5) * 8 + (lane & 7);
   uint32_t w[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -76,12 +80,16 @@ __global__ void pack_kernel(const float *__restrict__ w_fold, const float *__res
   uint4 *dst = reinterpret_cast<uint4 *>(packed) + (size_t)idx * 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-  if (chunk == 0) {
-    float2 b;
-    if (blk == 0) b = make_float2(b_ih[2 * kD + oc], b_fold[2 * kD + oc]);
-    else if (blk == 3) b = make_float2(b_hh[2 * kD + oc], 0.f);
-    else b = make_float2(b_ih[(blk - 1) * kD + oc] + b_hh[(blk - 1) * kD + oc], b_fold[(blk - 1) * kD + oc]);
-    reinterpret_cast<float2 *>(packed + kPackedWBytes)[slice * 128 + lane] = b;
+  if (chunk == 0 && lane < kSliceCols) {
+    const int t = slice * kSliceCols + lane;       // output column
+    float *bias = reinterpret_cast<float *>(packed + kPackedWBytes) + slice * kBiasSlice;
+    bias[0 * kSliceCols + lane] = b_ih[2 * kD + t];
+    bias[1 * kSliceCols + lane] = b_ih[t] + b_hh[t];
+    bias[2 * kSliceCols + lane] = b_ih[kD + t] + b_hh[kD + t];
+    bias[3 * kSliceCols + lane] = b_hh[2 * kD + t];
+    bias[4 * kSliceCols + lane] = b_fold[2 * kD + t];
+    bias[5 * kSliceCols + lane] = b_fold[t];
+    bias[6 * kSliceCols + lane] = b_fold[kD + t];
   }
 }
 
@@ -90,9 +98,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
                                                                const uint8_t *__restrict__ packed, int32_t N,
                                                                float *__restrict__ h_out, uint8_t *__restrict__ h_out_img,
                                                                float *__restrict__ gates) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();        // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t bar0 = sbase + kOffBar;
   auto a_full = [&](int i) { return bar0 + 8u * i; };
   auto a_empty = [&](int i) { return bar0 + 8u * (kStages + i); };
@@ -182,90 +190,89 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     }
   } else {
     // ===== weights -> tensor memory, then the epilogue =====
-    const int q = warp & 3;                  // TMEM lane quarter = pre-activation: 0 gi_n, 1 r, 2 z, 3 gh_n
-    const int hh = (warp - 2) >> 2;          // node half of the tile: nodes 64 hh .. 64 hh + 63
+    const int q = warp & 3;                  // TMEM lane quarter: columns 8q .. 8q+7 of the slice, all four pre-activations
+    const int e = (warp - 2) >> 2;           // nodes 32 e .. 32 e + 31 of the tile
+    const int g = lane >> 3, c = lane & 7;   // this lane's TMEM row = pre-activation g of column c; it finishes nodes = g (mod 4)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int gcol = slice * kSliceCols + lane;       // this lane's output column of h
-    float2 bias = make_float2(0.f, 0.f);
+    const int scol = q * 8 + c;                       // column inside the slice
+    const int gcol = slice * kSliceCols + scol;       // column of h
+    float b_gin = 0.f, b_r = 0.f, b_z = 0.f, b_ghn = 0.f, d_gin = 0.f, d_r = 0.f, d_z = 0.f;
     if (my_tiles > 0) {
       const uint4 *src = reinterpret_cast<const uint4 *>(packed) + ((size_t)slice * kChunks * 128 + (size_t)(q * 32 + lane)) * 4;
-#pragma unroll 4
-      for (int c = 0; c < kChunks / 2; ++c) {
-        const int chunk = hh * (kChunks / 2) + c;
+#pragma unroll
+      for (int cc = 0; cc < kChunks / 4; ++cc) {
+        const int chunk = e * (kChunks / 4) + cc;
         const uint4 *p = src + (size_t)chunk * 128 * 4;
         const uint4 x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3);
         const uint32_t w[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
         tmem_st16(lane_addr + (uint32_t)(chunk * 16), w);
       }
       tmem_st_wait();
-      bias = __ldg(reinterpret_cast<const float2 *>(packed + kPackedWBytes) + slice * 128 + q * 32 + lane);
+      const float *bias = reinterpret_cast<const float *>(packed + kPackedWBytes) + slice * kBiasSlice + scol;
+      b_gin = __ldg(bias); b_r = __ldg(bias + kSliceCols); b_z = __ldg(bias + 2 * kSliceCols); b_ghn = __ldg(bias + 3 * kSliceCols);
+      d_gin = __ldg(bias + 4 * kSliceCols); d_r = __ldg(bias + 5 * kSliceCols); d_z = __ldg(bias + 6 * kSliceCols);
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
 
     const size_t plane = (size_t)N * kD;
-    float *X = reinterpret_cast<float *>(smem + kOffX) + (size_t)hh * 2 * kXFloats;
-    const int bar_id = 1 + hh;
+    float *X = reinterpret_cast<float *>(smem + kOffX) + (size_t)(warp - 2) * kXFloats;   // warp-private exchange tile
     const bool tr = (warp == 2 && lane == 0);
-    const bool is_sigmoid = (q == 1 || q == 2);
+    // h and the in-degree of the 8 nodes this thread finishes per tile (two 16-node chunks x nodes g, g+4, g+8, g+12) are
+    // fetched one tile ahead, so their latency hides behind the current tile's work
+    float hp_n[8];
+    int dg_n[8];
+    auto prefetch = [&](int kk) {
+      const int64_t nw = (int64_t)(group + kk * num_groups) * kTileM + e * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t node = nw + (i >> 2) * 16 + g + 4 * (i & 3);
+        const bool ok = kk < my_tiles && node < N;
+        hp_n[i] = ok ? __ldg(h + node * kD + gcol) : 0.f;
+        dg_n[i] = ok ? (__ldg(indptr + node + 1) - __ldg(indptr + node)) : 0;
+      }
+    };
+    prefetch(0);
     for (int k = 0; k < my_tiles; ++k) {
       const int tile = group + k * num_groups;
       const int buf = k & 1, buse = k >> 1;
-      const int64_t node_h = (int64_t)tile * kTileM + hh * 64;          // first node of this warp's half
+      const int64_t node_w = (int64_t)tile * kTileM + e * 32;          // first of this warp's 32 nodes
       if (tr) trace_stamp(tron, k, 7);
-      // h of the 16 nodes this warp finishes (4 per 16-node chunk), fetched while the MMAs of the tile run
-      float hp[16];
+      float hp[8], deg[8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t node = node_h + c * 16 + q * 4 + j;
-          hp[c * 4 + j] = node < N ? __ldg(h + node * kD + gcol) : 0.f;
-        }
-      // in-degrees of the half's 64 nodes: lane l holds deg(node_h + l) and deg(node_h + 32 + l)
-      float dlo, dhi;
-      {
-        auto ip = [&](int64_t i) { return __ldg(indptr + (i < N ? i : (int64_t)N)); };
-        const int a0 = ip(node_h + lane), a1 = ip(node_h + 32 + lane), a2 = ip(node_h + 64);
-        const int n0 = __shfl_down_sync(0xffffffffu, a0, 1), n1 = __shfl_down_sync(0xffffffffu, a1, 1);
-        const int a1_0 = __shfl_sync(0xffffffffu, a1, 0);
-        dlo = (float)((lane < 31 ? n0 : a1_0) - a0);
-        dhi = (float)((lane < 31 ? n1 : a2) - a1);
-      }
+      for (int i = 0; i < 8; ++i) { hp[i] = hp_n[i]; deg[i] = (float)dg_n[i]; }
+      prefetch(k + 1);
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
       if (tr) trace_stamp(tron, k, 8);
+      float v0[16], v1[16];
+      const uint32_t taddr = lane_addr + (uint32_t)(kAccCol + buf * 128 + e * 32);
+      tmem_ld16(taddr, v0);
+      tmem_ld16(taddr + 16, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has read its part of the accumulator buffer
+      if (tr) trace_stamp(tron, k, 9);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v[16];
-        tmem_ld16(lane_addr + (uint32_t)(kAccCol + buf * 128 + hh * 64 + c * 16), v);
-        tmem_ld_wait();
-        if (c == 3) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has read its part of the accumulator buffer
-          if (tr) trace_stamp(tron, k, 9);
-        }
-        float *Xc = X + (c & 1) * kXFloats;
-        const float dsel = (c < 2) ? dlo : dhi;
+      for (int ch = 0; ch < 2; ++ch) {
+        // thread (g, c) holds pre-activation g of column c for nodes 0..15 of the chunk -> X[g][node][c]
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float deg = __shfl_sync(0xffffffffu, dsel, (c & 1) * 16 + i);
-          const float pre = v[i] + fmaf(deg, bias.y, bias.x);
-          Xc[(q * 16 + i) * 32 + lane] = is_sigmoid ? fast_sigmoid(pre) : pre;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        // this warp now owns nodes 4q .. 4q+3 of the chunk, lane = column
+        for (int i = 0; i < 16; ++i) X[g * kXGateLd + i * 8 + c] = ch == 0 ? v0[i] : v1[i];
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int i = q * 4 + j;
-          const int64_t node = node_h + c * 16 + i;
+          const int i = g + 4 * j;                                     // node of the chunk finished by this thread
+          const int64_t node = node_w + ch * 16 + i;
           const bool valid = node < N;
-          const float gin = Xc[(0 * 16 + i) * 32 + lane], r = Xc[(1 * 16 + i) * 32 + lane];
-          const float z = Xc[(2 * 16 + i) * 32 + lane], ghn = Xc[(3 * 16 + i) * 32 + lane];
+          const float dg = deg[ch * 4 + j];
+          const float gin = X[0 * kXGateLd + i * 8 + c] + fmaf(dg, d_gin, b_gin);
+          const float r = fast_sigmoid(X[1 * kXGateLd + i * 8 + c] + fmaf(dg, d_r, b_r));
+          const float z = fast_sigmoid(X[2 * kXGateLd + i * 8 + c] + fmaf(dg, d_z, b_z));
+          const float ghn = X[3 * kXGateLd + i * 8 + c] + b_ghn;
           const float n = fast_tanh(fmaf(r, ghn, gin));
-          const float hnew = valid ? fmaf(z, hp[c * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
+          const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
           if (valid) {
             h_out[node * kD + gcol] = hnew;
             if (gates) {
@@ -277,17 +284,18 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             }
           }
           if (h_out_img) {
-            // lanes 0-15 write the hi words, 16-31 the lo words of column pairs (2 pi, 2 pi + 1)
-            const int pi = lane & 15;
-            const float x0 = __shfl_sync(0xffffffffu, hnew, 2 * pi), x1 = __shfl_sync(0xffffffffu, hnew, 2 * pi + 1);
+            // columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
+            const float other = __shfl_xor_sync(0xffffffffu, hnew, 1);
+            const float x0 = (c & 1) ? other : hnew, x1 = (c & 1) ? hnew : other;
             __nv_bfloat16 h0, l0, h1, l1;
             split_bf16(x0, h0, l0);
             split_bf16(x1, h1, l1);
-            const uint32_t word = (lane < 16) ? ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16))
-                                              : ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16));
-            *reinterpret_cast<uint32_t *>(h_out_img + image_offset(node, slice * kSliceCols + 2 * pi, lane >> 4)) = word;
+            const uint32_t word = (c & 1) ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
+                                          : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
+            *reinterpret_cast<uint32_t *>(h_out_img + image_offset(node, gcol & ~1, c & 1)) = word;
           }
         }
+        __syncwarp();
       }
       if (tr) trace_stamp(tron, k, 10);
     }
