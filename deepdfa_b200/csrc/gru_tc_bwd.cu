@@ -23,50 +23,62 @@ constexpr int kThreads = 320, kEpiWarps = 8;
 // =================================================================================================
 // (1) gate backward -> q images, h image, bias gradients
 // =================================================================================================
-constexpr int kGbRows = 64;  // node rows per CTA (8 warps x 8 rows)
-__global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
-                                                             const float *__restrict__ gates, const int32_t *__restrict__ indptr,
-                                                             int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
-                                                             uint8_t *__restrict__ h_img, float *__restrict__ db_fold,
-                                                             float *__restrict__ db_ih, float *__restrict__ db_hh) {
-  __shared__ float red[7 * kD];
+// Persistent: 2 CTAs per SM, every warp strides over node rows (lane = 4 columns), two rows in flight per warp (12 x 16-byte
+// loads outstanding per lane); the seven column sums (bias gradients) stay in registers for the whole kernel and are
+// combined once per CTA (r01s ncu: with one CTA per 64 rows the shared/global atomics of that reduction were 22% of the
+// kernel and the row loop was load-latency-bound).
+constexpr int kGbWarps = 8;
+struct GbRow {
+  float4 d, hv, rr, zz, nn, gh;
+  float deg;
+};
+__device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_out, const float *__restrict__ h,
+                                        const float *__restrict__ gates, const int32_t *__restrict__ indptr, size_t plane, int64_t node,
+                                        int col, bool ok) {
+  if (ok) {
+    const size_t off = (size_t)node * kD + col;
+    x.d = ldg_nc_f4(dh_out + off);
+    x.hv = ldg_nc_f4(h + off);
+    x.rr = ldg_nc_f4(gates + off);
+    x.zz = ldg_nc_f4(gates + plane + off);
+    x.nn = ldg_nc_f4(gates + 2 * plane + off);
+    x.gh = ldg_nc_f4(gates + 3 * plane + off);
+    x.deg = (float)(__ldg(indptr + node + 1) - __ldg(indptr + node));
+  }
+}
+
+__global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
+                                                                          const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                                                          int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
+                                                                          uint8_t *__restrict__ h_img, float *__restrict__ db_fold,
+                                                                          float *__restrict__ db_ih, float *__restrict__ db_hh) {
+  __shared__ float red[kGbWarps][7 * kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = lane * 4;
   const size_t plane = (size_t)N * kD;
-  for (int i = threadIdx.x; i < 7 * kD; i += 256) red[i] = 0.f;
-  __syncthreads();
   float4 sum[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t row0 = (int64_t)blockIdx.x * kGbRows + warp * 8;
   const int64_t Npad = ((int64_t)N + kTileM - 1) / kTileM * kTileM;
-#pragma unroll 2
-  for (int r = 0; r < 8; ++r) {
-    const int64_t node = row0 + r;
-    if (node >= Npad) break;
+  const int64_t stride = (int64_t)gridDim.x * kGbWarps;
+
+  auto finish = [&](const GbRow &x, int64_t node, bool ok) {
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr, hv = qr;
-    if (node < N) {
-      const size_t off = (size_t)node * kD + col;
-      const float4 d = ldg_nc_f4(dh_out + off);
-      hv = ldg_nc_f4(h + off);
-      const float4 rr = ldg_nc_f4(gates + off);
-      const float4 zz = ldg_nc_f4(gates + plane + off);
-      const float4 nn = ldg_nc_f4(gates + 2 * plane + off);
-      const float4 gh = ldg_nc_f4(gates + 3 * plane + off);
-      const float deg = (float)(indptr[node + 1] - indptr[node]);
-#define BWDQ(f)                                                  \
-  {                                                              \
-    const float dz_ = d.f * (hv.f - nn.f);                       \
-    const float dn_ = d.f * (1.f - zz.f);                        \
-    qn.f = dn_ * (1.f - nn.f * nn.f);                            \
-    qz.f = dz_ * zz.f * (1.f - zz.f);                            \
-    qr.f = qn.f * gh.f * rr.f * (1.f - rr.f);                    \
-    qnr.f = qn.f * rr.f;                                         \
+    if (ok) {
+      hv = x.hv;
+#define BWDQ(f)                                                      \
+  {                                                                  \
+    const float dz_ = x.d.f * (x.hv.f - x.nn.f);                     \
+    const float dn_ = x.d.f * (1.f - x.zz.f);                        \
+    qn.f = dn_ * (1.f - x.nn.f * x.nn.f);                            \
+    qz.f = dz_ * x.zz.f * (1.f - x.zz.f);                            \
+    qr.f = qn.f * x.gh.f * x.rr.f * (1.f - x.rr.f);                  \
+    qnr.f = qn.f * x.rr.f;                                           \
   }
       BWDQ(x) BWDQ(y) BWDQ(z) BWDQ(w)
 #undef BWDQ
       f4_add(sum[0], qr); f4_add(sum[1], qz); f4_add(sum[2], qn); f4_add(sum[3], qnr);
-      f4_fma(sum[4], deg, qr); f4_fma(sum[5], deg, qz); f4_fma(sum[6], deg, qn);
+      f4_fma(sum[4], x.deg, qr); f4_fma(sum[5], x.deg, qz); f4_fma(sum[6], x.deg, qn);
     }
     // images: rows N..Npad-1 are written as zeros (the weight-gradient GEMM sums over all 128 rows of a tile)
     const size_t o_hi = image_offset(node, col, 0), o_lo = image_offset(node, col, 1);
@@ -78,15 +90,24 @@ __global__ void __launch_bounds__(256) gate_bwd_image_kernel(const float *__rest
     if (h_img) {   // only when the caller did not keep the forward pass's image of h_t
       split4(hv, ph, pl); *reinterpret_cast<uint2 *>(h_img + o_hi) = ph; *reinterpret_cast<uint2 *>(h_img + o_lo) = pl;
     }
+  };
+
+  for (int64_t node = (int64_t)blockIdx.x * kGbWarps + warp; node < Npad; node += 2 * stride) {
+    const int64_t node2 = node + stride;
+    GbRow a, b;
+    const bool ok_a = node < N, ok_b = node2 < N;
+    gb_load(a, dh_out, h, gates, indptr, plane, node, col, ok_a);
+    gb_load(b, dh_out, h, gates, indptr, plane, node2, col, ok_b);
+    finish(a, node, ok_a);
+    if (node2 < Npad) finish(b, node2, ok_b);
   }
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    atomicAdd(&red[i * kD + col + 0], sum[i].x); atomicAdd(&red[i * kD + col + 1], sum[i].y);
-    atomicAdd(&red[i * kD + col + 2], sum[i].z); atomicAdd(&red[i * kD + col + 3], sum[i].w);
-  }
+  for (int i = 0; i < 7; ++i) *reinterpret_cast<float4 *>(&red[warp][i * kD + col]) = sum[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < 7 * kD; i += 256) {
-    const float v_ = red[i];
+  for (int i = threadIdx.x; i < 7 * kD; i += 32 * kGbWarps) {
+    float v_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGbWarps; ++w) v_ += red[w][i];
     const int which = i >> 7, c_ = i & 127;
     // 0:S(q_r) 1:S(q_z) 2:S(q_n) 3:S(q_nr) 4:S(deg q_r) 5:S(deg q_z) 6:S(deg q_n)
     if (which == 0) { atomicAdd(db_ih + c_, v_); atomicAdd(db_hh + c_, v_); }
@@ -793,7 +814,12 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
   float *partial = reinterpret_cast<float *>(h_img_ws + img);
   const uint8_t *h_img = h_img_in ? static_cast<const uint8_t *>(h_img_in) : h_img_ws;
   const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
-  tc2b::gate_bwd_image_kernel<<<(unsigned)((rows + tc2b::kGbRows - 1) / tc2b::kGbRows), 256, 0, stream>>>(
+  unsigned gb_grid = 1;
+  {
+    const int64_t want = (rows + tc2b::kGbWarps - 1) / tc2b::kGbWarps;
+    gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
+  }
+  tc2b::gate_bwd_image_kernel<<<gb_grid, 32 * tc2b::kGbWarps, 0, stream>>>(
       dh_out, h, gates, indptr, N, q_img, img, h_img_in ? nullptr : h_img_ws, db_fold, db_ih, db_hh);
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));

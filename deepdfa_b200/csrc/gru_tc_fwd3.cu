@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     // h and the in-degree of the 8 nodes this thread finishes per tile (two 16-node chunks x nodes g, g+4, g+8, g+12) are
     // fetched one tile ahead, so their latency hides behind the current tile's work
     float hp_n[8];
-    int dg_n[8];
+    int ip0_n[8], ip1_n[8];      // raw indptr entries: the subtraction waits until the values are used, not when they are requested
     auto prefetch = [&](int kk) {
       const int64_t nw = (int64_t)(group + kk * num_groups) * kTileM + e * 32;
 #pragma unroll
@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
         const int64_t node = nw + (i >> 2) * 16 + g + 4 * (i & 3);
         const bool ok = kk < my_tiles && node < N;
         hp_n[i] = ok ? __ldg(h + node * kD + gcol) : 0.f;
-        dg_n[i] = ok ? (__ldg(indptr + node + 1) - __ldg(indptr + node)) : 0;
+        ip0_n[i] = ok ? __ldg(indptr + node) : 0;
+        ip1_n[i] = ok ? __ldg(indptr + node + 1) : 0;
       }
     };
     prefetch(0);
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       if (tr) trace_stamp(tron, k, 7);
       float hp[8], deg[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { hp[i] = hp_n[i]; deg[i] = (float)dg_n[i]; }
+      for (int i = 0; i < 8; ++i) { hp[i] = hp_n[i]; deg[i] = (float)(ip1_n[i] - ip0_n[i]); }
       prefetch(k + 1);
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();

@@ -147,29 +147,41 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_small_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
                                                           const float *__restrict__ B, int ldb, float beta, float *__restrict__ C,
                                                           int ldc) {
-  __shared__ float As[32][33];  // [k][m]
-  __shared__ float Bs[32][33];  // [k][n]
+  constexpr int KB = 64;            // K staged 64 at a time; the next stage is fetched into registers while this one is used
+  __shared__ float As[KB][33];      // [k][m]
+  __shared__ float Bs[KB][33];      // [k][n]
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = threadIdx.x + i * 256;      // 1024 elements per tile
-      {  // A tile: element (m, k); the fastest-varying index follows the memory layout for coalescing
-        const int m = TA ? (e & 31) : (e >> 5), k = TA ? (e >> 5) : (e & 31);
+    for (int i = 0; i < 8; ++i) {
+      const int e = threadIdx.x + i * 256;      // 2048 elements per operand stage
+      {  // A element (m, k); the fastest-varying index follows the memory layout for coalescing
+        const int m = TA ? (e & 31) : (e >> 6), k = TA ? (e >> 5) : (e & 63);
         const int gm = m0 + m, gk = k0 + k;
-        As[k][m] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.f;
+        ra[i] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.f;
       }
-      {  // B tile: element (k, n)
-        const int n = TB ? (e >> 5) : (e & 31), k = TB ? (e & 31) : (e >> 5);
+      {  // B element (k, n)
+        const int n = TB ? (e >> 6) : (e & 31), k = TB ? (e & 63) : (e >> 5);
         const int gn = n0 + n, gk = k0 + k;
-        Bs[k][n] = (gn < N && gk < K) ? (TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]) : 0.f;
+        rb[i] = (gn < N && gk < K) ? (TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]) : 0.f;
       }
     }
-    __syncthreads();
+  };
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KB) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    for (int i = 0; i < 8; ++i) {
+      const int e = threadIdx.x + i * 256;
+      As[TA ? (e >> 5) : (e & 63)][TA ? (e & 31) : (e >> 6)] = ra[i];
+      Bs[TB ? (e & 63) : (e >> 5)][TB ? (e >> 6) : (e & 31)] = rb[i];
+    }
+    __syncthreads();
+    if (k0 + KB < K) fetch(k0 + KB);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
       const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);

@@ -32,7 +32,7 @@ for STAGE in "$@"; do
       DDFA_BENCH_MIN_WARMUP=1 DDFA_BENCH_SKIP_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
         --log-file $OUT/${TAG}_launches_tc.csv python bench.py --steps 2 --warmup 1 --engine tcgen05 > $OUT/${TAG}_ncu_bench_tc.log 2>&1
       echo "ncu launches exit: $?"
-      DDFA_BENCH_MIN_WARMUP=1 DDFA_BENCH_SKIP_CPU=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gru_fwd_kernel|dgrad_kernel|wgrad_kernel|gate_bwd_image" -s 16 -c 6 \
+      DDFA_BENCH_MIN_WARMUP=1 DDFA_BENCH_SKIP_CPU=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image" -s 16 -c 6 \
         -f -o $OUT/${TAG}_prof_gru_tc python bench.py --steps 2 --warmup 1 --engine tcgen05 > $OUT/${TAG}_ncu_gru_tc.log 2>&1
       echo "ncu gru_tc exit: $?" ;;
     ncu-gather)
