@@ -354,31 +354,45 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the edge-gather kernel (BASELINE metric (ii)) + the GRU GEMM share --------------
+    # ---- rooflines, from the CUDA-event spans of the instrumented region ----------------------------------------------
+    # P = one [N,128] fp32 plane = one activation image (hi+lo bf16).  Algorithmic bytes per launch:
+    #   forward GRU step (train): read s image, h image, h (3P); write h', h' image, 4 gate planes (6P)            = 9P
+    #   backward GRU step: gate_bwd 6P in + 4P out; dgrad 4P (q) + 2P in, 2P out; wgrad 4P (q) + 2P (s, h images)  = 24P
+    #   edge gather: SURVEY.md §8(d) — E rows gathered + N rows written (+ the CSR arrays)
     peaks = measured_peaks()
-    gather_bytes = Eg * Dh * 4 + N * Dh * 4 + Eg * 4 + (N + 1) * 4          # SURVEY.md §8(d), per launch
+    P = N * Dh * 4
+    share = {k: prof.total_ms(k) / ms for k in prof.spans}
+    gather_bytes = Eg * Dh * 4 + N * Dh * 4 + Eg * 4 + (N + 1) * 4
     gf_ms, gf_n = prof.mean_ms("gather_fwd")
     gb_ms, gb_n = prof.mean_ms("gather_bwd")
     g_all = [a.elapsed_time(b) for a, b in prof.spans["gather_fwd"] + prof.spans["gather_bwd"]]
     g_ms = sum(g_all) / len(g_all)
-    achieved = gather_bytes / (g_ms * 1e-3) / 1e9
-    share = {k: prof.total_ms(k) / ms for k in prof.spans}
+    gru_f_ms, gru_f_n = prof.mean_ms("ddfa_gru_step_fwd")
+    gru_b_ms, gru_b_n = prof.mean_ms("ddfa_gru_step_bwd")
     flops_fwd_step = 2.0 * N * (6 * Dh * Dh)                                  # folded GRU GEMMs per propagation step
-    gru_f_ms, _ = prof.mean_ms("ddfa_gru_step_fwd")
-    gru_b_ms, _ = prof.mean_ms("ddfa_gru_step_bwd")
-    roofline = {"kernel": "gather_sum_kernel (CSR edge gather, fwd over CSR + bwd over transposed CSR)", "bound": "hbm",
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "peak_source": peaks["source"], "traffic": None, "bytes_per_launch": gather_bytes,
-                "avg_launch_us": g_ms * 1e3, "launches_timed": len(g_all),
-                "fwd_us": gf_ms * 1e3, "bwd_us": gb_ms * 1e3, "share_of_step": share["gather_fwd"] + share["gather_bwd"],
-                "storage_dtype": "f32"}
-    gru = {"kernel": f"GRU step ({args.engine} engine)", "bound": "tensor", "unit": "TFLOP/s",
-           "fwd_achieved": flops_fwd_step / (gru_f_ms * 1e-3) / 1e12, "bwd_achieved": 2 * flops_fwd_step / (gru_b_ms * 1e-3) / 1e12,
-           "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"],
-           "fwd_us": gru_f_ms * 1e3, "bwd_us": gru_b_ms * 1e3,
-           "share_of_step": share["ddfa_gru_step_fwd"] + share["ddfa_gru_step_bwd"],
-           "flops_per_launch_fwd": flops_fwd_step}
-    gru["frac_fwd"] = gru["fwd_achieved"] / gru["peak"]
+
+    def hbm_line(kernel, nbytes, t_ms, launches, sh, **extra):
+        ach = nbytes / (t_ms * 1e-3) / 1e9
+        return dict({"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"], "bytes_per_launch": int(nbytes),
+                     "avg_launch_us": t_ms * 1e3, "launches_timed": launches, "share_of_step": sh}, **extra)
+
+    tc = args.engine == "tcgen05"
+    fwd_line = hbm_line("gru_fwd3_kernel (GRU step forward, tcgen05: weights in TMEM, bf16x3)" if tc else "GRU step forward (simt engine)",
+                        9 * P, gru_f_ms, gru_f_n, share["ddfa_gru_step_fwd"],
+                        # dram__bytes_read.sum + dram__bytes_write.sum of the training-mode launch, profiles/r01s_ncu_fwd3_bwd.txt
+                        traffic=(59736576 + 64268800) if tc else None,
+                        tensor_tflops=3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 if tc else None,
+                        tensor_frac=(3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if tc else None)
+    bwd_line = hbm_line("GRU step backward: gate_bwd_image + dgrad3 + wgrad kernels" if tc else "GRU step backward (simt engine)",
+                        24 * P, gru_b_ms, gru_b_n, share["ddfa_gru_step_bwd"], traffic=None,
+                        tensor_tflops=6 * flops_fwd_step / (gru_b_ms * 1e-3) / 1e12 if tc else None)
+    gather_line = hbm_line("gather_sum_kernel / gather_sum_image_kernel (CSR edge gather, fwd over CSR + bwd over transposed CSR)",
+                           gather_bytes, g_ms, len(g_all), share["gather_fwd"] + share["gather_bwd"], traffic=None,
+                           fwd_us=gf_ms * 1e3, bwd_us=gb_ms * 1e3, storage_dtype="f32")
+    lines = [fwd_line, bwd_line, gather_line]
+    # the dominant single kernel of the step is the forward GRU kernel (one launch per span); the backward span is three kernels
+    roofline = dict(fwd_line, note="dominant single kernel by time; the other hot kernels are in roofline_kernels")
 
     # ---- cpu baseline on this box's host cores (bounded sample) ----------------------------------------
     if os.environ.get("DDFA_BENCH_SKIP_CPU") == "1":     # profiler runs only
@@ -397,7 +411,7 @@ def run_ours(args):
                 "path": "pinned host COO + node indices -> H2D -> ddfa_build_csr -> fused train step -> loss .item()"},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
         "cuda_graph": graph_note, "ms_per_step_eager_instrumented": ms_eager_per_step,
-        "roofline": roofline, "roofline_gru": gru,
+        "roofline": roofline, "roofline_kernels": lines,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_done} full train steps of one {args.graphs}-graph C0 batch, oracle/ggnn_oracle.py (torch CPU)"},
         "final_loss": final_loss, "e2e_last_loss": loss_val,

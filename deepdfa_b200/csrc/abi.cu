@@ -34,12 +34,8 @@ int ddfa_engine_available(int engine) {
 
 int ddfa_debug_set(int key, int value) {
   switch (key) {
-    case 1: ddfa::gru_tc2_set_cluster(value); return DDFA_OK;   // forward GRU kernel: cluster-multicast operand feed on/off
-    case 4: ddfa::gru_tc2_set_fwd3(value); return DDFA_OK;      // forward kernel variant (takes effect at the next prepare)
-    case 3: ddfa::gru_tc2_set_dgrad3(value); return DDFA_OK;    // dgrad kernel variant (takes effect at the next prepare_bwd)
-    case 2: {                                                    // pipeline timeline stamps of the tcgen05 kernels on/off
-      int rc = ddfa::gru_tc2_trace_enable(value);
-      if (rc == DDFA_OK) rc = ddfa::gru_tc3_trace_enable(value);
+    case 2: {   // pipeline timeline stamps of the tcgen05 kernels: 0 off, 1 = gru_fwd3 + dgrad3, 2 = gru_fwd3 + wgrad
+      int rc = ddfa::gru_tc3_trace_enable(value);
       return rc != DDFA_OK ? rc : ddfa::gru_tc2b_trace_enable(value);
     }
     default: ddfa::set_error("ddfa_debug_set: unknown key %d", key); return DDFA_ERR_INVALID_ARG;
@@ -48,9 +44,8 @@ int ddfa_debug_set(int key, int value) {
 
 int ddfa_debug_read(int key, void *host_out, size_t bytes) {
   DDFA_REQUIRE(host_out != nullptr, "ddfa_debug_read: null output");
-  switch (key) {
-    case 1: return ddfa::gru_tc2_trace_read(host_out, bytes);    // [148 CTAs][12 tiles][12 events] int64 SM-clock stamps
-    case 2: return ddfa::gru_tc2b_trace_read(host_out, bytes);
+  switch (key) {   // [148 CTAs][12 tiles][12 events] int64 SM-clock stamps
+    case 2: return ddfa::gru_tc2b_trace_read(host_out, bytes);    // dgrad3_kernel / wgrad_kernel
     case 3: return ddfa::gru_tc3_trace_read(host_out, bytes);     // gru_fwd3_kernel
     default: ddfa::set_error("ddfa_debug_read: unknown key %d", key); return DDFA_ERR_INVALID_ARG;
   }

@@ -50,20 +50,15 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
 // gru_tc_fwd.cu — tcgen05 engine, forward (D == 128; weight-stationary, activation images)
 size_t act_image_bytes(int64_t n);
 int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
-void gru_tc2_set_cluster(int on);
-void gru_tc2_set_fwd3(int on);      // forward GRU kernel: weights in tensor memory (1, default) or weight slices in shared memory (0)
 // gru_tc_fwd3.cu — forward, weights-in-TMEM orientation
 size_t gru_tc3_packed_bytes();
 int gru_tc3_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, void *packed,
                     cudaStream_t stream);
 int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
                      void *h_out_img, float *save_gates, const void *packed, cudaStream_t stream);
-int gru_tc3_trace_enable(int on);
+int gru_tc3_trace_enable(int on);   // pipeline timeline of gru_fwd3_kernel (development aid)
 int gru_tc3_trace_read(void *host, size_t bytes);
-void gru_tc2_set_dgrad3(int on);    // backward dgrad: weights in tensor memory (1, default) or weight slices in shared memory (0)
-int gru_tc2_trace_enable(int on);   // pipeline timeline of gru_fwd_kernel (development aid)
-int gru_tc2_trace_read(void *host, size_t bytes);
-int gru_tc2b_trace_enable(int on);  // same for dgrad_kernel
+int gru_tc2b_trace_enable(int on);  // pipeline timeline of dgrad3_kernel (value 1) / wgrad_kernel (value 2) — development aid
 int gru_tc2b_trace_read(void *host, size_t bytes);
 size_t gru_tc2_workspace_bytes();
 int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,

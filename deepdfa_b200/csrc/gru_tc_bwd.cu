@@ -1,15 +1,16 @@
-// tcgen05 engine, backward of one GRU step (D == 128), v2 — activation images in, TMA-fed, persistent.
+// tcgen05 engine, backward of one GRU step (D == 128) — activation images in, TMA-fed, persistent kernels.
+// Backward of the same math the forward kernel implements (gru_tc_fwd3.cu; reference: DDFA/code_gnn/models/flow_gnn/
+// ggnn.py:60-63 through dgl.nn.GatedGraphConv / torch.nn.GRUCell autograd).
 //
 //   (1) gate_bwd_image_kernel   q_r, q_z, q_n, q_nr  <-  (dh', h, r, z, n, gh_n)      elementwise, HBM-bound
-//         writes the four q matrices and h_t as activation IMAGES + the bias gradients (column sums)
-//   (2) dgrad_kernel            ds = [q_r q_z q_n] W' ;  dh = dh' * z + [q_r q_z q_nr] Whh      K = 3D
-//         weight-stationary like the forward kernel: a CTA owns 32 output columns of ds AND dh; the bf16 hi/lo
-//         images of the transposed weight slices (96 KB) stay in shared memory, the q images stream through a
-//         TMA ring, accumulators [ds | dh] = 64 TMEM columns per tile, four tiles in flight.
+//         writes the four q matrices as activation IMAGES + the bias gradients (column sums)
+//   (2) dgrad3_kernel           ds = [q_r q_z q_n] W' ;  dh = dh' * z + [q_r q_z q_nr] Whh      K = 3D
+//         transposed GEMM: the weights live in tensor memory as the A operand, the q images stream through three 64 KB
+//         stages as the B operand, a CTA owns all 128 columns of ds or of dh (see the comment at the kernel)
 //   (3) wgrad_kernel            dW' += [q_r q_z q_n]^T s ;  dWhh += [q_r q_z q_nr]^T h            K = nodes
-//         both operands are read "MN-major" straight from the images (64-node half tiles, 32 KB per operand,
-//         6-slot TMA ring); a CTA keeps its [384 x 128] fp32 partial sum in TMEM over all its tiles and adds it to
-//         the global gradient with RED.ADD at the end.
+//         both operands are read "MN-major" straight from the images (whole 128-node tiles, three 64 KB slots); a CTA keeps
+//         its [384 x 128] fp32 partial sum in TMEM over all its tiles and folds it into a private global partial at the
+//         end; wgrad_reduce_kernel sums the partials once per backward pass.
 // Precision: bf16x3 everywhere (hi*hi + hi*lo + lo*hi), fp32 accumulate.
 #include "tc_common.cuh"
 
@@ -17,7 +18,6 @@ namespace ddfa {
 namespace tc2b {
 using namespace tcc;
 
-constexpr int kSlices = 4, kSliceCols = 32;
 constexpr int kThreads = 320, kEpiWarps = 8;
 
 // =================================================================================================
@@ -119,217 +119,7 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
 }
 
 // =================================================================================================
-// (2) dgrad
-// =================================================================================================
-constexpr int kDgWImgBytes = 64 * 128;                  // [rows 0-31: W'^T slice | rows 32-63: Whh^T slice] x 64 k = 8 KB
-constexpr int kDgWSliceBytes = 12 * kDgWImgBytes;       // (gate*2 + kb)*2 + v  -> 96 KB
-constexpr int kDgAStages = 2;                           // 2 x 32 KB stages: one variant (hi | lo) of one q-matrix tile
-constexpr int kDgAStageBytes = 2 * kChunkBytes;
-constexpr int kDgAccBufs = 4;
-constexpr int kDgOffA = kDgWSliceBytes;
-// epilogue staging (tc_common.cuh "coalesced epilogue I/O"): per warp pair 2 planes, used first for the inputs
-// (dh', z rows) and then for the outputs (ds, dh rows)
-constexpr int kDgOffStage = kDgOffA + kDgAStages * kDgAStageBytes;
-constexpr int kDgStageBytes = 4 * 2 * kStagePlaneFloats * 4;
-constexpr int kDgOffBar = kDgOffStage + kDgStageBytes;
-constexpr int kDgNumBars = 1 + 2 * kDgAStages + 2 * kDgAccBufs;
-constexpr int kDgOffTmemPtr = kDgOffBar + kDgNumBars * 8;
-constexpr int kDgSmemAlloc = kDgOffTmemPtr + 16 + 1024;
-constexpr size_t kDgPackedBytes = (size_t)kSlices * kDgWSliceBytes;
-
-// packed[j][(g*2+kb)*2+v][64 rows x 64 k]: row n < 32: w_fold[g*128 + kb*64 + k][32j + n] ; row 32+n: w_hh[...][32j + n]
-__global__ void __launch_bounds__(256) dgrad_pack_kernel(const float *__restrict__ w_fold, const float *__restrict__ w_hh,
-                                                         uint8_t *__restrict__ packed) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = kSlices * 3 * 2 * 8 * 64;   // (j, g, kb, k8, row): row fastest -> coalesced source reads
-  if (t >= total) return;
-  const int row = t & 63, k8 = (t >> 6) & 7, kb = (t >> 9) & 1;
-  const int g = (t >> 10) % 3, j = (t >> 10) / 3;
-  const float *W = (row < 32) ? w_fold : w_hh;
-  const int n = row & 31;
-  float x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = W[(size_t)(g * kD + kb * 64 + k8 * 8 + i) * kD + j * kSliceCols + n];
-  uint4 ph, pl;
-  split8(x, ph, pl);
-  uint8_t *base = packed + (size_t)j * kDgWSliceBytes + (size_t)((g * 2 + kb) * 2) * kDgWImgBytes + sw128_offset(row, k8 * 8);
-  *reinterpret_cast<uint4 *>(base) = ph;
-  *reinterpret_cast<uint4 *>(base + kDgWImgBytes) = pl;
-}
-
-__global__ void __launch_bounds__(kThreads, 1) dgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
-                                                            const float *__restrict__ dh_out, const float *__restrict__ gates,
-                                                            const uint8_t *__restrict__ packed, int32_t N,
-                                                            float *__restrict__ ds, float *__restrict__ dh) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + kDgOffBar;
-  const uint32_t w_full = bar0;
-  auto a_full = [&](int i) { return bar0 + 8u * (1 + i); };
-  auto a_empty = [&](int i) { return bar0 + 8u * (1 + kDgAStages + i); };
-  auto acc_full = [&](int i) { return bar0 + 8u * (1 + 2 * kDgAStages + i); };
-  auto acc_empty = [&](int i) { return bar0 + 8u * (1 + 2 * kDgAStages + kDgAccBufs + i); };
-  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kDgOffTmemPtr);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slice = blockIdx.x % kSlices;
-  const int group = blockIdx.x / kSlices, num_groups = gridDim.x / kSlices;
-  const int num_tiles = (N + kTileM - 1) / kTileM;
-  const int my_tiles = (num_tiles > group) ? (num_tiles - 1 - group) / num_groups + 1 : 0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(w_full, 1);
-    for (int i = 0; i < kDgAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < kDgAccBufs; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
-    mbar_fence_init();
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 256);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  const int tron = (g_trace_on == 1);
-  if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
-
-  if (warp == 0) {
-    if (my_tiles > 0 && elect_one()) {
-      mbar_arrive_expect_tx(w_full, kDgWSliceBytes);
-      bulk_g2s(sbase, packed + (size_t)slice * kDgWSliceBytes, kDgWSliceBytes, w_full);   // one 96 KB copy
-      int cc = 0;
-      for (int k = 0; k < my_tiles; ++k) {
-        const int tile = group + k * num_groups;
-        for (int mv = 0; mv < 8; ++mv, ++cc) {        // (q matrix m: q_r, q_z, q_n, q_nr) x (variant hi, lo): 32 KB each
-          const int m = mv >> 1, v = mv & 1;
-          const int stage = cc % kDgAStages, use = cc / kDgAStages;
-          if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
-          if (mv == 0) trace_stamp(tron, k, 1);
-          mbar_arrive_expect_tx(a_full(stage), kDgAStageBytes);
-          bulk_g2s(sbase + kDgOffA + stage * kDgAStageBytes,
-                   q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes + (size_t)v * kDgAStageBytes, kDgAStageBytes,
-                   a_full(stage));
-          if (mv == 7) trace_stamp(tron, k, 2);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (my_tiles > 0 && elect_one()) {
-      constexpr uint32_t kIdesc64 = make_idesc(64), kIdesc32 = make_idesc(32);
-      mbar_wait(w_full, 0);
-      int cc = 0;
-      for (int k = 0; k < my_tiles; ++k) {
-        const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
-        if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
-        tc_fence_after();
-        trace_stamp(tron, k, 3);
-        const uint32_t d_base = tmem_base + (uint32_t)buf * 64u;   // [ds 0-31 | dh 32-63]
-        for (int mv = 0; mv < 8; ++mv, ++cc) {
-          const int m = mv >> 1, v = mv & 1;
-          const int g = m < 2 ? m : 2;
-          const int stage = cc % kDgAStages, use = cc / kDgAStages;
-          mbar_wait(a_full(stage), use & 1);
-          tc_fence_after();
-          if (mv == 0) trace_stamp(tron, k, 4);
-          if (mv == 7) trace_stamp(tron, k, 5);
-          const int n_wv = (v == 0) ? 2 : 1;
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint32_t a_addr = sbase + kDgOffA + stage * kDgAStageBytes + (uint32_t)kb * kChunkBytes;
-            for (int wv = 0; wv < n_wv; ++wv) {
-              const uint32_t w_addr = sbase + (uint32_t)(((g * 2 + kb) * 2 + wv) * kDgWImgBytes);
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const uint64_t ad = make_desc(a_addr + k4 * 32);
-                if (m < 2) {        // q_r, q_z feed both ds and dh: one N = 64 MMA
-                  const bool first = (mv == 0 && kb == 0 && wv == 0 && k4 == 0);
-                  umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc64, first ? 0u : 1u);
-                } else if (m == 2)  // q_n -> ds only (rows 0..31 of the image)
-                  umma_f16(d_base, ad, make_desc(w_addr + k4 * 32), kIdesc32, 1u);
-                else                // q_nr -> dh only (rows 32..63)
-                  umma_f16(d_base + 32, ad, make_desc(w_addr + 32 * 128 + k4 * 32), kIdesc32, 1u);
-              }
-            }
-          }
-          umma_commit(a_empty(stage));
-        }
-        umma_commit(acc_full(buf));
-        trace_stamp(tron, k, 6);
-      }
-    }
-  } else {
-    // epilogue: ds = acc_ds ; dh = acc_dh + dh' * z — all global I/O as full 128-byte rows through the pair staging planes
-    const int lw = warp - 2, q = warp & 3, csub = lw >> 2;
-    const int bar_id = 1 + q;
-    float *P0 = reinterpret_cast<float *>(smem + kDgOffStage) + (size_t)q * 2 * kStagePlaneFloats;
-    float *P1 = P0 + kStagePlaneFloats;
-    const int lc0 = csub * 16, gcs = slice * kSliceCols;
-    const size_t plane = (size_t)N * kD;
-    auto rows_of = [&](int kk) -> int {
-      if (kk >= my_tiles) return 0;
-      const int64_t r0 = (int64_t)(group + kk * num_groups) * kTileM + q * 32;
-      const int64_t rem = (int64_t)N - r0;
-      return rem <= 0 ? 0 : (rem > 32 ? 32 : (int)rem);
-    };
-    float4 dreg[4], zreg[4];
-    {
-      const int64_t r0 = (int64_t)group * kTileM + q * 32;
-      stage_fetch_rows(dh_out + r0 * kD + gcs, kD, lane, csub, rows_of(0), dreg);
-      stage_fetch_rows(gates + plane + r0 * kD + gcs, kD, lane, csub, rows_of(0), zreg);
-    }
-    for (int k = 0; k < my_tiles; ++k) {
-      const int tile = group + k * num_groups;
-      const int buf = k % kDgAccBufs, buse = k / kDgAccBufs;
-      const int64_t r0 = (int64_t)tile * kTileM + q * 32;
-      const int rows_valid = rows_of(k);
-      const bool tr = (warp == 2 && lane == 0);
-      if (tr) trace_stamp(tron, k, 7);
-      stage_put_rows(P0, lane, csub, dreg);
-      stage_put_rows(P1, lane, csub, zreg);
-      pair_sync(bar_id);
-      float dv[16], zv[16];
-      stage_read16(P0, lane, csub, dv);
-      stage_read16(P1, lane, csub, zv);
-      pair_sync(bar_id);                               // both warps have read the inputs: the planes may be overwritten
-      {
-        const int64_t rn = (int64_t)(group + (k + 1) * num_groups) * kTileM + q * 32;
-        stage_fetch_rows(dh_out + rn * kD + gcs, kD, lane, csub, rows_of(k + 1), dreg);
-        stage_fetch_rows(gates + plane + rn * kD + gcs, kD, lane, csub, rows_of(k + 1), zreg);
-      }
-      mbar_wait(acc_full(buf), buse & 1);
-      tc_fence_after();
-      if (tr) trace_stamp(tron, k, 8);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + lc0);
-      float a_ds[16], a_dh[16];
-      tmem_ld16(taddr + 0, a_ds);
-      tmem_ld16(taddr + 32, a_dh);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(buf));
-      if (tr) trace_stamp(tron, k, 9);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a_dh[i] = fmaf(dv[i], zv[i], a_dh[i]);
-      stage_write16(P0, lane, csub, a_ds);
-      stage_write16(P1, lane, csub, a_dh);
-      pair_sync(bar_id);
-      stage_store_rows(P0, ds + r0 * kD + gcs, kD, lane, csub, rows_valid);
-      stage_store_rows(P1, dh + r0 * kD + gcs, kD, lane, csub, rows_valid);
-      pair_sync(bar_id);
-      if (tr) trace_stamp(tron, k, 10);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// =================================================================================================
-// (2b) dgrad, weight-in-TMEM orientation ("dgrad3")
+// (2) dgrad, weight-in-TMEM orientation ("dgrad3")
 // =================================================================================================
 // The in-kernel timeline of dgrad_kernel (profiles/r01l_trace_dgrad.log) shows it is bound by the operand feed: 96 KB of
 // shared memory hold the weight slice, only 2 x 32 KB are left for activations, and with ~1 us per copy in flight that
@@ -759,28 +549,19 @@ int gru_tc2b_trace_read(void *host, size_t bytes) {
   return DDFA_OK;
 }
 
-// workspace: [dgrad_kernel weight slices 384 KB][dgrad3 packed weights 384 KB][q images x 4][h image][wgrad partial sums]
-static constexpr size_t kPackedTotal = tc2b::kDgPackedBytes + tc2b::kD3PackedBytes;
+// workspace: [dgrad3 packed weights 384 KB][q images x 4][h image][wgrad partial sums]
+static constexpr size_t kPackedTotal = tc2b::kD3PackedBytes;
 size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return kPackedTotal + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
 
-static int g_dgrad_v3 = 1;   // ddfa_debug_set key 3: 1 = weights-in-TMEM dgrad3_kernel, 0 = weight-slices-in-smem dgrad_kernel
-void gru_tc2_set_dgrad3(int on) { g_dgrad_v3 = on; }
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < kPackedTotal) {
     set_error("tcgen05 engine (bwd): workspace too small");
     return DDFA_ERR_WORKSPACE;
   }
-  if (g_dgrad_v3) {
-    const int total = 2 * tc2b::kD3Chunks * 128;
-    tc2b::dgrad3_pack_kernel<<<(total + 127) / 128, 128, 0, stream>>>(
-        w_fold, w_hh, reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace) + tc2b::kDgPackedBytes));
-    DDFA_CHECK_LAUNCH("tc2b::dgrad3_pack_kernel");
-  } else {
-    const int total = tc2b::kSlices * 3 * 2 * 8 * 64;
-    tc2b::dgrad_pack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_fold, w_hh, static_cast<uint8_t *>(workspace));
-    DDFA_CHECK_LAUNCH("tc2b::dgrad_pack_kernel");
-  }
+  const int total = 2 * tc2b::kD3Chunks * 128;
+  tc2b::dgrad3_pack_kernel<<<(total + 127) / 128, 128, 0, stream>>>(w_fold, w_hh, static_cast<uint32_t *>(workspace));
+  DDFA_CHECK_LAUNCH("tc2b::dgrad3_pack_kernel");
   return DDFA_OK;
 }
 
@@ -824,19 +605,13 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
-  if (g_dgrad_v3) {
+  {
     DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kD3SmemAlloc));
     int groups = kNumSMs / 2;
     if (groups > tiles) groups = tiles;
-    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(
-        q_img, img, dh_out, gates, reinterpret_cast<const uint32_t *>(packed + tc2b::kDgPackedBytes), N, ds, dh);
+    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(q_img, img, dh_out, gates,
+                                                                                 reinterpret_cast<const uint32_t *>(packed), N, ds, dh);
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
-  } else {
-    DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kDgSmemAlloc));
-    int groups = kNumSMs / tc2b::kSlices;
-    if (groups > tiles) groups = tiles;
-    tc2b::dgrad_kernel<<<groups * tc2b::kSlices, tc2b::kThreads, tc2b::kDgSmemAlloc, stream>>>(q_img, img, dh_out, gates, packed, N, ds, dh);
-    DDFA_CHECK_LAUNCH("tc2b::dgrad_kernel");
   }
   // every one of the 74 x 2 CTAs writes its partial slot (zeros if it owns no tile), so the reduction can sum all of them
   tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,

@@ -54,48 +54,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
-// ---- thread-block clusters: multicast bulk copy + cluster-scope barrier operations ----------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(local_bar),
-      "r"(cta)
-      : "memory");
-}
-// wait with cluster-scope acquire (the arrivals come from other CTAs)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAITC_DONE;\n"
-      "bra WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-// TMA 1-D bulk copy global -> the SAME shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier (same
-// offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-               : "memory");
-}
-
 // true in exactly one lane of a fully converged warp (lets ptxas issue the uniform-datapath tcgen05 / bulk-copy instructions
 // straight-line instead of wrapping each one in a loop over "any active lane")
 __device__ __forceinline__ bool elect_one() {

@@ -48,9 +48,10 @@ const char *ddfa_last_error(void);
 int ddfa_device_supported(void);
 /* 1 if the given DDFA_ENGINE_* is compiled into this library, else 0 */
 int ddfa_engine_available(int engine);
-/* tuning / A-B knobs for the benchmark scripts (key 1: tcgen05 forward kernel, cluster-multicast feed 1/0) */
+/* development aid: in-kernel pipeline timeline of the tcgen05 kernels (SM-clock stamps per CTA / tile / event).
+ * ddfa_debug_set(2, v): v = 0 off, 1 = forward + dgrad kernels, 2 = forward + wgrad kernels;
+ * ddfa_debug_read(2 | 3, host, bytes): stamps of the backward (2) or forward (3) kernel's last launch. */
 int ddfa_debug_set(int key, int value);
-/* development aid: key 1 / 2 = pipeline timeline of the tcgen05 forward / dgrad kernel (after ddfa_debug_set(2, 1)) */
 int ddfa_debug_read(int key, void *host_out, size_t bytes);
 /* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
 long long ddfa_launch_count(void);

@@ -160,15 +160,6 @@ def main():
         fl = 2.0 * Nb * 6 * D * D
         print(f"image path N={Nb}: gather fp32 {t_g:.1f} us | gather->image {t_gi:.1f} us | gather->image+fp32 {t_gif:.1f} us | to_image {t_ti:.1f} us | "
               f"gru_fwd_image infer {t_f0:.1f} us ({fl / t_f0 / 1e6:.0f} TFLOP/s alg) | train(+img+gates) {t_f1:.1f} us ({fl / t_f1 / 1e6:.0f} TFLOP/s alg)")
-        # A/B: the same kernel without the cluster-multicast operand feed (results must be bit-identical)
-        ob_c = ob.clone(); img_c = o_img.clone(); gt_c = gt.clone()
-        L.call("ddfa_debug_set", 1, 0)
-        t_n0 = timeit(lambda: L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hb), _p(dgb.indptr), Nb, D, _p(ob), None, None, _p(ws), wsb, _stream_ptr()))
-        t_n1 = timeit(lambda: L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hb), _p(dgb.indptr), Nb, D, _p(ob), _p(o_img), _p(gt), _p(ws), wsb, _stream_ptr()))
-        torch.cuda.synchronize()
-        L.call("ddfa_debug_set", 1, 1)
-        print(f"   no-cluster feed: infer {t_n0:.1f} us | train {t_n1:.1f} us | cluster vs no-cluster identical: "
-              f"h {bool(torch.equal(ob, ob_c))} image {bool(torch.equal(o_img, img_c))} gates {bool(torch.equal(gt, gt_c))}")
         # correctness of the image chain vs the fp32-in entry point
         ref_out = torch.empty(Nb, D, device=DEV)
         wsb2 = L.call("ddfa_gru_step_workspace_bytes", Nb, D, ENGINE_TCGEN05); ws2 = torch.zeros(wsb2, dtype=torch.uint8, device=DEV)
