@@ -57,7 +57,7 @@ _SIGNATURES = {
     "ddfa_act_to_image": (_int, [_vp, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum_image": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ddfa_gru_step_fwd_image": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "ddfa_gru_step_bwd_image": (_int, [_vp] * 6 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
+    "ddfa_gru_step_bwd_image": (_int, [_vp] * 9 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd_finish": (_int, [_i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "ddfa_gru_step_prepare_bwd": (_int, [_vp, _vp, _i32, _int, _vp, _sz, _vp]),

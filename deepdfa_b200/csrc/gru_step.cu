@@ -296,7 +296,8 @@ size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
   return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // dgi | dgh
 }
 
-int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *h_image, const void *s_image, const float *gates,
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int32_t *indptr_t, const int32_t *indices_t,
+                            const float *h, const void *h_image, const void *s_image, const float *gates,
                             const int32_t *indptr, int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold,
                             float *db_ih, float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode,
                             void *stream_) {
@@ -307,7 +308,9 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *h_i
   DDFA_REQUIRE(dh_out && h && s_image && gates && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
                "ddfa_gru_step_bwd_image: NULL pointer");
   DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image: dh must not alias dh_out");
-  return gru_tc2_step_bwd(dh_out, h, h_image, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+  DDFA_REQUIRE(ds_prev == nullptr || (indptr_t && indices_t), "ddfa_gru_step_bwd_image: ds_prev given without the transposed CSR");
+  DDFA_REQUIRE(ds_prev == nullptr || ds_prev != ds, "ddfa_gru_step_bwd_image: ds must not alias ds_prev");
+  return gru_tc2_step_bwd(dh_out, ds_prev, indptr_t, indices_t, h, h_image, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
                           workspace_bytes, wgrad_mode, as_stream(stream_));
 }
 
@@ -351,7 +354,7 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
     void *s_img = static_cast<uint8_t *>(workspace) + gru_tc2_bwd_workspace_bytes(N);
     rc = act_to_image(s, N, s_img, stream);
     if (rc) return rc;
-    return gru_tc2_step_bwd(dh_out, h, /*h_img_in=*/nullptr, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,
+    return gru_tc2_step_bwd(dh_out, nullptr, nullptr, nullptr, h, /*h_img_in=*/nullptr, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,
                             workspace, workspace_bytes, /*wgrad_mode=*/0, stream);
   }
   float *dgi = static_cast<float *>(workspace);

@@ -3,7 +3,10 @@
 // ggnn.py:60-63 through dgl.nn.GatedGraphConv / torch.nn.GRUCell autograd).
 //
 //   (1) gate_bwd_image_kernel   q_r, q_z, q_n, q_nr  <-  (dh', h, r, z, n, gh_n)      elementwise, HBM-bound
-//         writes the four q matrices as activation IMAGES + the bias gradients (column sums)
+//         writes the four q matrices as activation IMAGES, the plane dh' * z (dgrad's elementwise term) and the bias
+//         gradients (column sums).  The incoming gradient may be given in two parts, dh' = dh_part + A^T ds_prev: the
+//         transposed edge gather of the previous step's ds is folded into this kernel's row loop (no dh' round trip
+//         through HBM and one launch less per step).
 //   (2) dgrad3_kernel           ds = [q_r q_z q_n] W' ;  dh = dh' * z + [q_r q_z q_nr] Whh      K = 3D
 //         transposed GEMM: the weights live in tensor memory as the A operand, the q images stream through three 64 KB
 //         stages as the B operand, a CTA owns all 128 columns of ds or of dh (see the comment at the kernel)
@@ -31,11 +34,14 @@ constexpr int kGbWarps = 8;
 struct GbRow {
   float4 d, hv, rr, zz, nn, gh;
   float deg;
+  int tb, te;      // this row's neighbour range in the transposed CSR (fused gather)
 };
 __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_out, const float *__restrict__ h,
-                                        const float *__restrict__ gates, const int32_t *__restrict__ indptr, size_t plane, int64_t node,
-                                        int col, bool ok) {
+                                        const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                        const int32_t *__restrict__ indptr_t, size_t plane, int64_t node, int col, bool ok) {
+  x.tb = x.te = 0;
   if (ok) {
+    if (indptr_t) { x.tb = __ldg(indptr_t + node); x.te = __ldg(indptr_t + node + 1); }
     const size_t off = (size_t)node * kD + col;
     x.d = ldg_nc_f4(dh_out + off);
     x.hv = ldg_nc_f4(h + off);
@@ -49,8 +55,11 @@ __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_o
 
 __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
                                                                           const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                                                          const float *__restrict__ ds_in, const int32_t *__restrict__ indptr_t,
+                                                                          const int32_t *__restrict__ indices_t,
                                                                           int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
-                                                                          uint8_t *__restrict__ h_img, float *__restrict__ db_fold,
+                                                                          uint8_t *__restrict__ h_img, float *__restrict__ dhz,
+                                                                          float *__restrict__ db_fold,
                                                                           float *__restrict__ db_ih, float *__restrict__ db_hh) {
   __shared__ float red[kGbWarps][7 * kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,6 +75,7 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr, hv = qr;
     if (ok) {
       hv = x.hv;
+      *reinterpret_cast<float4 *>(dhz + (size_t)node * kD + col) = make_float4(x.d.x * x.zz.x, x.d.y * x.zz.y, x.d.z * x.zz.z, x.d.w * x.zz.w);
 #define BWDQ(f)                                                      \
   {                                                                  \
     const float dz_ = x.d.f * (x.hv.f - x.nn.f);                     \
@@ -96,8 +106,28 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
     const int64_t node2 = node + stride;
     GbRow a, b;
     const bool ok_a = node < N, ok_b = node2 < N;
-    gb_load(a, dh_out, h, gates, indptr, plane, node, col, ok_a);
-    gb_load(b, dh_out, h, gates, indptr, plane, node2, col, ok_b);
+    gb_load(a, dh_out, h, gates, indptr, indptr_t, plane, node, col, ok_a);
+    gb_load(b, dh_out, h, gates, indptr, indptr_t, plane, node2, col, ok_b);
+    if (indptr_t) {
+      // dh' += sum over the transposed-graph neighbours of ds_in: first up to 4 neighbour ids of both rows, then their
+      // rows, all loads of a phase in flight together; longer lists finish in a plain loop (deterministic order)
+      int ia[4], ib[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ia[k] = (a.tb + k < a.te) ? __ldg(indices_t + a.tb + k) : -1;
+        ib[k] = (b.tb + k < b.te) ? __ldg(indices_t + b.tb + k) : -1;
+      }
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        va[k] = ia[k] >= 0 ? ldg_nc_f4(ds_in + (size_t)ia[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[k] = ib[k] >= 0 ? ldg_nc_f4(ds_in + (size_t)ib[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { f4_add(a.d, va[k]); f4_add(b.d, vb[k]); }
+      for (int j = a.tb + 4; j < a.te; ++j) f4_add(a.d, ldg_nc_f4(ds_in + (size_t)__ldg(indices_t + j) * kD + col));
+      for (int j = b.tb + 4; j < b.te; ++j) f4_add(b.d, ldg_nc_f4(ds_in + (size_t)__ldg(indices_t + j) * kD + col));
+    }
     finish(a, node, ok_a);
     if (node2 < Npad) finish(b, node2, ok_b);
   }
@@ -170,7 +200,7 @@ __global__ void dgrad3_pack_kernel(const float *__restrict__ w_fold, const float
 }
 
 __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
-                                                             const float *__restrict__ dh_out, const float *__restrict__ gates,
+                                                             const float *__restrict__ dhz,
                                                              const uint32_t *__restrict__ packed3, int32_t N,
                                                              float *__restrict__ ds, float *__restrict__ dh) {
   extern __shared__ uint8_t smem_raw[];
@@ -212,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
     if (elect_one()) {
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
-        const int tile = group + k * num_groups;
+        const int tile = num_tiles - 1 - (group + k * num_groups);   // back to front: the q tiles written last are still in L2
         for (int g = 0; g < 3; ++g, ++cc) {
           const int m = g < 2 ? g : (role == 0 ? 2 : 3);      // q_r, q_z, then q_n (ds) or q_nr (dh)
           const int stage = cc % kD3Stages, use = cc / kD3Stages;
@@ -291,24 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
 
-    const size_t plane = (size_t)N * kD;
     float *out = role == 0 ? ds : dh;
     const bool tr = (warp == 2 && lane == 0);
     for (int k = 0; k < my_tiles; ++k) {
-      const int tile = group + k * num_groups;
+      const int tile = num_tiles - 1 - (group + k * num_groups);
       if (tr) trace_stamp(tron, k, 7);
       for (int half = 0; half < 2; ++half) {
         const int64_t node0 = (int64_t)tile * kTileM + half * 64 + e * 32;
         int rows_valid = (int)((int64_t)N - node0);
         rows_valid = rows_valid < 0 ? 0 : (rows_valid > 32 ? 32 : rows_valid);
-        float dv[32], zv[32];
-        if (role == 1) {       // dh = acc + dh' * z : fetch the elementwise operands while the MMAs run
+        float dv[32];
+        if (role == 1) {       // dh = acc + (dh' * z) : fetch the elementwise term (written by gate_bwd) while the MMAs run
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool ok = i < rows_valid;
-            dv[i] = ok ? __ldg(dh_out + (node0 + i) * kD + col) : 0.f;
-            zv[i] = ok ? __ldg(gates + plane + (node0 + i) * kD + col) : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) dv[i] = (i < rows_valid) ? __ldg(dhz + (node0 + i) * kD + col) : 0.f;
         }
         mbar_wait(acc_full(half), k & 1);
         tc_fence_after();
@@ -326,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
         if (role == 1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            v0[i] = fmaf(dv[i], zv[i], v0[i]);
-            v1[i] = fmaf(dv[16 + i], zv[16 + i], v1[i]);
+            v0[i] += dv[i];
+            v1[i] += dv[16 + i];
           }
         }
 #pragma unroll
@@ -549,9 +574,9 @@ int gru_tc2b_trace_read(void *host, size_t bytes) {
   return DDFA_OK;
 }
 
-// workspace: [dgrad3 packed weights 384 KB][q images x 4][h image][wgrad partial sums]
+// workspace: [dgrad3 packed weights 384 KB][q images x 4][h image][dh' * z plane (image-sized)][wgrad partial sums]
 static constexpr size_t kPackedTotal = tc2b::kD3PackedBytes;
-size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return kPackedTotal + 5 * tcc::image_bytes(N) + wg_partial_bytes(); }
+size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return kPackedTotal + 6 * tcc::image_bytes(N) + wg_partial_bytes(); }
 
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -571,7 +596,7 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
     set_error("tcgen05 engine (bwd finish): workspace too small");
     return DDFA_ERR_WORKSPACE;
   }
-  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + kPackedTotal + 5 * tcc::image_bytes(N));
+  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + kPackedTotal + 6 * tcc::image_bytes(N));
   const int n4 = (int)(tc2b::kWgPartialFloats / 4);
   tc2b::wgrad_reduce_kernel<<<dim3((n4 + 255) / 256, 2), 256, 0, stream>>>(partial, kWgCtas, dw_fold, dw_hh);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_reduce_kernel");
@@ -581,8 +606,9 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
 // wgrad_mode: 0 = immediate (dW += this step's contribution before returning), 1 = first step of a deferred accumulation
 // (partials overwritten), 2 = further deferred step (partials accumulated); deferred passes end with gru_tc2_bwd_finish.
 // h_img_in: the activation image of h (kept from the forward pass) or NULL (then it is rebuilt inside the workspace).
-int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, const void *s_img, const float *gates,
-                     const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+// ds_in / indptr_t / indices_t: NULL, or the incoming gradient is dh_out + A^T ds_in (A^T as a CSR over the transposed graph)
+int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *indptr_t, const int32_t *indices_t, const float *h,
+                     const void *h_img_in, const void *s_img, const float *gates, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
                      float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
     set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N));
@@ -592,7 +618,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
   const size_t img = tcc::image_bytes(N);
   uint8_t *q_img = packed + kPackedTotal;
   uint8_t *h_img_ws = q_img + 4 * img;
-  float *partial = reinterpret_cast<float *>(h_img_ws + img);
+  float *dhz = reinterpret_cast<float *>(h_img_ws + img);
+  float *partial = reinterpret_cast<float *>(h_img_ws + 2 * img);
   const uint8_t *h_img = h_img_in ? static_cast<const uint8_t *>(h_img_in) : h_img_ws;
   const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
   unsigned gb_grid = 1;
@@ -601,7 +628,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
   tc2b::gate_bwd_image_kernel<<<gb_grid, 32 * tc2b::kGbWarps, 0, stream>>>(
-      dh_out, h, gates, indptr, N, q_img, img, h_img_in ? nullptr : h_img_ws, db_fold, db_ih, db_hh);
+      dh_out, h, gates, indptr, ds_in, ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold,
+      db_ih, db_hh);
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
@@ -609,7 +637,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *h, const void *h_img_in, 
     DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kD3SmemAlloc));
     int groups = kNumSMs / 2;
     if (groups > tiles) groups = tiles;
-    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(q_img, img, dh_out, gates,
+    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(q_img, img, dhz,
                                                                                  reinterpret_cast<const uint32_t *>(packed), N, ds, dh);
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
   }

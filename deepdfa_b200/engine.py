@@ -8,6 +8,8 @@ replaced by the kernels documented in include/ddfa_b200.h.
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -336,15 +338,22 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     dw_fold.zero_()
     db_fold.zero_()
     ds = alloc.get("ds", (N, D))
+    ds_prev = None                     # tcgen05 engine: ds of the step after t, folded into step t's call (dh' = dh + A^T ds)
+    ds_alt = alloc.get("ds_b", (N, D)) if engine == ENGINE_TCGEN05 else None
+    fuse_gather = os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0"   # A/B switch for scripts; both paths are the CUDA kernels
     ws_bytes = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, engine)
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
         if engine == ENGINE_TCGEN05:     # saved.s[t] is the activation image of s_t
-            _call("ddfa_gru_step_bwd_image", _p(dh), _p(saved.h[t]), _p(saved.h_img[t]) if saved.h_img else None, _p(saved.s[t]),
-                  _p(saved.gates[t]), _p(dg.indptr), N, D,
+            _call("ddfa_gru_step_bwd_image", _p(dh), _p(ds_prev), _p(dg.indptr_t), _p(dg.indices_t), _p(saved.h[t]),
+                  _p(saved.h_img[t]) if saved.h_img else None, _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
                   _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
                   1 if t == T - 1 else 2, st, tag="ddfa_gru_step_bwd")   # deferred weight-gradient accumulation
+            if fuse_gather:
+                ds_prev, ds, ds_alt = ds, ds_alt, ds
+                dh, dh_alt = dh_alt, dh
+                continue
         else:
             _call("ddfa_gru_step_bwd", _p(dh), _p(saved.h[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr),
                   _p(saved.w_fold), _p(params.w_hh), N, D, _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih),
@@ -353,6 +362,8 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
         _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st, tag="gather_bwd")
         dh, dh_alt = dh_alt, dh
     if engine == ENGINE_TCGEN05 and T > 0:
+        if fuse_gather:     # the gather of the last ds (step 0) has no following step to ride on
+            _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds_prev), N, D, _p(dh), 1, st, tag="gather_bwd")
         L.call("ddfa_gru_step_bwd_finish", N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st)
     L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
            _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)

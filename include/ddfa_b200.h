@@ -158,8 +158,12 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
  * activation image (the one ddfa_gather_sum_image wrote in the forward pass); the q matrices and h are turned
  * into images inside the workspace.  workspace: ddfa_gru_step_bwd_workspace_bytes(N, D, TCGEN05), prepared by
  * ddfa_gru_step_prepare_bwd. */
-/* h_image: the image of h (step input) kept from the forward pass, or NULL (it is then rebuilt in the workspace). */
-int ddfa_gru_step_bwd_image(const float *dh_out, const float *h, const void *h_image, const void *s_image,
+/* h_image: the image of h (step input) kept from the forward pass, or NULL (it is then rebuilt in the workspace).
+ * ds_prev / indptr_t / indices_t: NULL, or the incoming gradient is dh_out + A^T ds_prev — the transposed edge gather
+ * (autograd of ggnn.py:95's message sum) of the ds the NEXT time step's call produced is folded into this call, with
+ * A^T given as the CSR of the transposed graph (ddfa_build_csr).  ds must not alias ds_prev. */
+int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int32_t *indptr_t, const int32_t *indices_t,
+                            const float *h, const void *h_image, const void *s_image,
                             const float *gates, const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
                             float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
                             void *workspace, size_t workspace_bytes, int wgrad_mode, void *stream);

@@ -44,11 +44,12 @@ else:
     ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
     L.call("ddfa_gru_step_prepare_bwd", _p(wf), _p(whh), D, ENGINE_TCGEN05, _p(ws), wsb, st)
     dh_o = torch.randn(N, D, device=DEV); ds = torch.empty(N, D, device=DEV); dh = torch.empty(N, D, device=DEV)
+    ds_p = torch.randn(N, D, device=DEV)     # the previous step's ds: its transposed gather is folded into the call
     acc = [torch.zeros(3 * D, D, device=DEV), torch.zeros(3 * D, device=DEV), torch.zeros(3 * D, device=DEV),
            torch.zeros(3 * D, D, device=DEV), torch.zeros(3 * D, device=DEV)]
     for i in range(4):
-        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
-               _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 1 if i == 0 else 2, st)
+        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(ds_p), _p(dg.indptr_t), _p(dg.indices_t), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr),
+               N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]), _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 1 if i == 0 else 2, st)
 torch.cuda.synchronize()
 print("done", which, N)
 
@@ -97,13 +98,13 @@ if os.environ.get("DDFA_TRACE"):
             torch.cuda.synchronize()
             dump_trace(3, "gru_fwd3_kernel " + ("train" if train else "infer"))
     else:
-        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
-               _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 2, st)
+        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(ds_p), _p(dg.indptr_t), _p(dg.indices_t), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr),
+               N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]), _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 2, st)
         torch.cuda.synchronize()
         dump_trace(2, "dgrad_kernel")
         L.call("ddfa_debug_set", 2, 2)
-        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]),
-               _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 2, st)
+        L.call("ddfa_gru_step_bwd_image", _p(dh_o), _p(ds_p), _p(dg.indptr_t), _p(dg.indices_t), _p(h), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr),
+               N, D, _p(ds), _p(dh), _p(acc[0]), _p(acc[1]), _p(acc[2]), _p(acc[3]), _p(acc[4]), _p(ws), wsb, 2, st)
         torch.cuda.synchronize()
         import numpy as np
         buf = np.zeros(148 * 12 * 12, dtype=np.int64)
