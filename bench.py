@@ -349,10 +349,20 @@ def run_ours(args):
     e2e_value = global_batch * e2e_steps / (float(t2.item()) * 1e-3)
     h2d = batch_bytes(host_batches[0])
 
-    if rank != 0:
+    def leave():
+        # Captured CUDA graphs hold NCCL kernels; tearing the communicator down under them can block (seen at N = 2:
+        # the JSON line was out, the process never exited).  Drop the graphs, drain the device and leave without the
+        # collective teardown — nothing else runs in this process.
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         return 0
+
+    if rank != 0:
+        return leave()
 
     # ---- rooflines, from the CUDA-event spans of the instrumented region ----------------------------------------------
     # P = one [N,128] fp32 plane = one activation image (hi+lo bf16).  Algorithmic bytes per launch:
@@ -417,9 +427,7 @@ def run_ours(args):
         "final_loss": final_loss, "e2e_last_loss": loss_val,
     }
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return leave()
 
 
 def main():
