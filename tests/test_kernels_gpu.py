@@ -257,6 +257,86 @@ def test_gru_step_fwd_bwd(D):
                    _p(h_out), None, _p(ws), wsb, ENGINE_TCGEN05, st())
 
 
+@pytest.mark.parametrize("graphs,nodes", [(3, 50), (24, 60), (40, 150)])     # N = 150 (2 tiles, ragged) .. 6000 (47 tiles)
+def test_gru_step_image_entries(graphs, nodes):
+    """The image-level entry points the training driver uses (tcgen05 engine): gather -> image, forward on images, backward
+    on images with the transposed gather of the previous step's ds folded in — against fp64 autograd of the same math."""
+    D = 128
+    g = synth.make_batch(graphs, nodes, seed=graphs, variable=True)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    src, dst = g.edges()
+    torch.manual_seed(graphs)
+    k = 1.0 / D ** 0.5
+    mk = lambda *sh: (torch.rand(*sh, dtype=torch.float64) * 2 - 1) * k
+    wf, bf, bih, whh, bhh = mk(3 * D, D) * 1.5, mk(3 * D), mk(3 * D), mk(3 * D, D), mk(3 * D)
+    h = torch.tanh(torch.randn(N, D, dtype=torch.float64))
+    deg = torch.bincount(dst, minlength=N).double()
+    dh_part = torch.randn(N, D, dtype=torch.float64)
+    ds_prev = torch.randn(N, D, dtype=torch.float64)
+    leaves = [t.requires_grad_(True) for t in (h, wf, bf, bih, whh, bhh)]
+    s_ref = torch.zeros(N, D, dtype=torch.float64).index_add(0, dst, leaves[0][src])            # s = A h
+    s_leaf = s_ref.detach().requires_grad_(True)
+    h_ref, r_ref, z_ref, n_ref, ghn_ref = _gru_reference(s_leaf, leaves[0], deg, *leaves[1:])
+    # incoming gradient of the step = dh_part + A^T ds_prev
+    dh_in = dh_part + torch.zeros(N, D, dtype=torch.float64).index_add(0, src, ds_prev[dst])
+    (h_ref * dh_in).sum().backward()
+    L = lib()
+    hd, wfd, bfd, bihd, whhd, bhhd = [dev(t.detach().float()) for t in leaves]
+    ib = L.call("ddfa_act_image_bytes", N)
+    assert ib == ((N + 127) // 128) * 65536
+    h_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); s_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    o_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); s_f = torch.empty(N, D, device=DEV)
+    L.call("ddfa_act_to_image", _p(hd), N, D, _p(h_img), st())
+    L.call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(hd), N, D, _p(s_img), _p(s_f), st())
+    assert (s_f.cpu().double() - s_ref.detach()).abs().max() < 1e-5
+    wsb = L.call("ddfa_gru_step_workspace_bytes", N, D, ENGINE_TCGEN05)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gru_step_prepare", _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), D, ENGINE_TCGEN05, _p(ws), wsb, st())
+    h_out = torch.empty(N, D, device=DEV); gates = torch.empty(4, N, D, device=DEV)
+    L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hd), _p(dg.indptr), N, D, _p(h_out), _p(o_img), _p(gates), _p(ws), wsb, st())
+    assert (h_out.cpu().double() - h_ref.detach()).abs().max() < 1e-4
+    for got, ref in zip(gates.cpu().double(), (r_ref, z_ref, n_ref, ghn_ref)):
+        assert (got - ref.detach()).abs().max() < 2.5e-4
+    # the image of h' the kernel wrote == the image ddfa_act_to_image makes of h' (including the zero tail rows)
+    ref_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_act_to_image", _p(h_out), N, D, _p(ref_img), st())
+    assert torch.equal(o_img, ref_img)
+    # inference form (no image, no gates) gives the same h'
+    h_out2 = torch.empty(N, D, device=DEV)
+    L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(hd), _p(dg.indptr), N, D, _p(h_out2), None, None, _p(ws), wsb, st())
+    assert torch.equal(h_out, h_out2)
+    # backward on images, with and without the folded transposed gather
+    wsb_b = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, ENGINE_TCGEN05)
+    ws_b = torch.empty(wsb_b, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gru_step_prepare_bwd", _p(wfd), _p(whhd), D, ENGINE_TCGEN05, _p(ws_b), wsb_b, st())
+    dpart_d, dsprev_d = dev(dh_part.float()), dev(ds_prev.float())
+    results = []
+    for fused in (True, False):
+        ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
+        acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
+        if fused:
+            d_in, args = dpart_d, (_p(dsprev_d), _p(dg.indptr_t), _p(dg.indices_t))
+        else:       # the caller gathers: d_in = dh_part + A^T ds_prev through ddfa_gather_sum (accumulate)
+            d_in = dpart_d.clone()
+            L.call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(dsprev_d), N, D, _p(d_in), 1, st())
+            args = (None, None, None)
+        L.call("ddfa_gru_step_bwd_image", _p(d_in), *args, _p(hd), _p(h_img), _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh),
+               _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]), _p(ws_b), wsb_b, 0, st())
+        torch.cuda.synchronize()
+        checks = [(ds, s_leaf.grad), (dh, leaves[0].grad),            # s_leaf is detached: h.grad is the GRU-only path, like the kernel's dh
+                  (acc["dwf"], wf.grad), (acc["dbf"], bf.grad), (acc["dbih"], bih.grad), (acc["dwhh"], whh.grad), (acc["dbhh"], bhh.grad)]
+        for got, ref in checks:
+            scale = max(1.0, float(ref.abs().max()))
+            assert (got.cpu().double() - ref).abs().max() < 3e-4 * scale, f"fused={fused}"
+        results.append((ds, dh))
+    assert (results[0][0] - results[1][0]).abs().max() < 1e-4 and (results[0][1] - results[1][1]).abs().max() < 1e-4
+    with pytest.raises(DdfaError, match="alias"):
+        L.call("ddfa_gru_step_bwd_image", _p(dpart_d), _p(ds), _p(dg.indptr_t), _p(dg.indices_t), _p(hd), _p(h_img), _p(s_img), _p(gates),
+               _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]),
+               _p(ws_b), wsb_b, 0, st())
+
+
 @pytest.mark.parametrize("D,L", [(128, 3), (128, 1), (32, 2), (64, 0), (256, 2)])
 def test_readout_mlp_fwd_bwd(D, L):
     sizes = [1, 2, 300, 40, 5, 0, 17]          # includes an EMPTY graph (pooled = 0) and a 1-node graph
