@@ -277,7 +277,7 @@ def run_ours(args):
     launches_per_step = L.call("ddfa_launch_count") - l0
 
     # ---- instrumented region (eager launches): CUDA-event pairs around every gather / GRU-step call -> roofline -----
-    prof = SpanProfiler(["gather_fwd", "gather_bwd", "ddfa_gru_step_fwd", "ddfa_gru_step_bwd"])
+    prof = SpanProfiler(["gather_fwd", "gather_bwd", "ddfa_gru_step_fwd", "ddfa_gru_step_bwd", "wgrad_batched"])
     E.profile_hook = prof
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,7 +369,10 @@ def run_ours(args):
     # ---- rooflines, from the CUDA-event spans of the instrumented region ----------------------------------------------
     # P = one [N,128] fp32 plane = one activation image (hi+lo bf16).  Algorithmic bytes per launch:
     #   forward GRU step (train): read s image, h image, h (3P); write h', h' image, 4 gate planes (6P)            = 9P
-    #   backward GRU step: gate_bwd 6P in + 4P out; dgrad 4P (q) + 2P in, 2P out; wgrad 4P (q) + 2P (s, h images)  = 24P
+    #   backward GRU step (tcgen05: gate_bwd with the transposed gather folded in + dgrad3): gate_bwd reads dh, gates x4, h
+    #     (6P) + E gathered ds rows, writes q x4 + dh'z (5P); dgrad reads q x4 + dh'z (5P), writes ds, dh (2P)   = 18P + E rows
+    #   weight gradient, ONE launch per backward pass over all T steps: per step q x4 + s image + h image          = 6P x T
+    #   (simt engine: the span holds its own gate / sgemm kernels; same byte model, 24P per step)
     #   edge gather: SURVEY.md §8(d) — E rows gathered + N rows written (+ the CSR arrays)
     peaks = measured_peaks()
     P = N * Dh * 4
@@ -396,13 +399,20 @@ def run_ours(args):
                         traffic=(59736576 + 64268800) if tc else None,
                         tensor_tflops=3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 if tc else None,
                         tensor_frac=(3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if tc else None)
-    bwd_line = hbm_line("GRU step backward: gate_bwd_image + dgrad3 + wgrad kernels" if tc else "GRU step backward (simt engine)",
-                        24 * P, gru_b_ms, gru_b_n, share["ddfa_gru_step_bwd"], traffic=None,
-                        tensor_tflops=6 * flops_fwd_step / (gru_b_ms * 1e-3) / 1e12 if tc else None)
+    wg_spans = prof.spans["wgrad_batched"]
+    batched = tc and len(wg_spans) > 0
+    bwd_line = hbm_line("GRU step backward: gate_bwd_image (+ folded transposed gather) + dgrad3 kernels" if tc else "GRU step backward (simt engine)",
+                        (18 * P + Eg * Dh * 4) if batched else 24 * P, gru_b_ms, gru_b_n, share["ddfa_gru_step_bwd"], traffic=None,
+                        tensor_tflops=(3 if batched else 6) * flops_fwd_step / (gru_b_ms * 1e-3) / 1e12 if tc else None)
     gather_line = hbm_line("gather_sum_kernel / gather_sum_image_kernel (CSR edge gather, fwd over CSR + bwd over transposed CSR)",
                            gather_bytes, g_ms, len(g_all), share["gather_fwd"] + share["gather_bwd"], traffic=None,
                            fwd_us=gf_ms * 1e3, bwd_us=gb_ms * 1e3, storage_dtype="f32")
     lines = [fwd_line, bwd_line, gather_line]
+    if batched:
+        wg_ms, wg_n = prof.mean_ms("wgrad_batched")
+        lines.insert(2, hbm_line(f"wgrad_kernel + wgrad_reduce_kernel (weight gradients of all {CFG['n_steps']} steps in one launch)",
+                                 6 * P * CFG["n_steps"], wg_ms, wg_n, share["wgrad_batched"], traffic=None,
+                                 tensor_tflops=3 * flops_fwd_step * CFG["n_steps"] / (wg_ms * 1e-3) / 1e12))
     # the dominant single kernel of the step is the forward GRU kernel (one launch per span); the backward span is three kernels
     roofline = dict(fwd_line, note="dominant single kernel by time; the other hot kernels are in roofline_kernels")
 

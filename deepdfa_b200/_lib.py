@@ -60,6 +60,8 @@ _SIGNATURES = {
     "ddfa_gru_step_bwd_image": (_int, [_vp] * 9 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd_finish": (_int, [_i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd_workspace_bytes": (_sz, [_i32, _i32, _int]),
+    "ddfa_gru_step_bwd_workspace_bytes_steps": (_sz, [_i32, _i32, _int, _i32]),
+    "ddfa_gru_bwd_wgrad_batched": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_prepare_bwd": (_int, [_vp, _vp, _i32, _int, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd": (_int, [_vp] * 7 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_readout_mlp_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32] + [_vp] * 6 + [_vp]),
@@ -71,7 +73,7 @@ _SIGNATURES = {
 }
 
 _NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
-              "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes",
+              "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
               "ddfa_act_image_bytes"}
 
 

@@ -291,9 +291,22 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
 
 size_t ddfa_gru_step_bwd_workspace_bytes(int32_t N, int32_t D, int engine) {
   if (N < 0 || D <= 0) return 0;
-  // tcgen05: [transposed weight images][q images x4][h image] + [s image] (the last one only for the fp32-s entry)
-  if (engine == DDFA_ENGINE_TCGEN05) return D == 128 ? ddfa::gru_tc2_bwd_workspace_bytes(N) + ddfa::act_image_bytes(N) : 16;
+  return ddfa_gru_step_bwd_workspace_bytes_steps(N, D, engine, 1);
+}
+
+size_t ddfa_gru_step_bwd_workspace_bytes_steps(int32_t N, int32_t D, int engine, int32_t steps) {
+  if (N < 0 || D <= 0) return 0;
+  if (engine == DDFA_ENGINE_TCGEN05) return D == 128 ? ddfa::gru_tc2_bwd_workspace_bytes(N, steps) : 16;   // layout: gru_tc_bwd.cu
   return sizeof(float) * 2 * (size_t)N * 3 * (size_t)D;  // dgi | dgh
+}
+
+int ddfa_gru_bwd_wgrad_batched(const void *const *s_images, const void *const *h_images, int32_t steps, int32_t N, int32_t D,
+                               float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_bwd_wgrad_batched: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  DDFA_REQUIRE(s_images && h_images && dw_fold && dw_hh, "ddfa_gru_bwd_wgrad_batched: NULL pointer");
+  if (N == 0) return DDFA_OK;
+  return gru_tc2_bwd_wgrad_batched(s_images, h_images, steps, N, dw_fold, dw_hh, workspace, workspace_bytes, as_stream(stream_));
 }
 
 int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int32_t *indptr_t, const int32_t *indices_t,
@@ -303,7 +316,8 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int
                             void *stream_) {
   using namespace ddfa;
   DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_bwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
-  DDFA_REQUIRE(wgrad_mode >= 0 && wgrad_mode <= 2, "ddfa_gru_step_bwd_image: wgrad_mode must be 0, 1 or 2 (got %d)", wgrad_mode);
+  DDFA_REQUIRE((wgrad_mode >= 0 && wgrad_mode <= 2) || (wgrad_mode >= 16 && wgrad_mode < 32),
+               "ddfa_gru_step_bwd_image: wgrad_mode must be 0, 1, 2 or DDFA_WGRAD_KEEP(slot < 16) (got %d)", wgrad_mode);
   if (N == 0) return DDFA_OK;
   DDFA_REQUIRE(dh_out && h && s_image && gates && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
                "ddfa_gru_step_bwd_image: NULL pointer");
@@ -351,7 +365,7 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
   }
   if (engine == DDFA_ENGINE_TCGEN05) {
     // fp32-s convenience path (tests, tools): build the s image at the end of the workspace, then the image kernels
-    void *s_img = static_cast<uint8_t *>(workspace) + gru_tc2_bwd_workspace_bytes(N);
+    void *s_img = gru_tc2_bwd_s_image_scratch(workspace, N);
     rc = act_to_image(s, N, s_img, stream);
     if (rc) return rc;
     return gru_tc2_step_bwd(dh_out, nullptr, nullptr, nullptr, h, /*h_img_in=*/nullptr, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,

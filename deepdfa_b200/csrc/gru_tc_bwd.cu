@@ -396,8 +396,17 @@ __device__ __forceinline__ int wg_slot(int tile_i, int w) {   // w: 0 = B, 1..3 
 // grid = (ctas, 2): blockIdx.y = role: 0: A in {q_r,q_z,q_n}, B = s image -> dW' ; 1: A in {q_r,q_z,q_nr}, B = h image -> dWhh.
 // partial: [2][ctas][384*128] fp32, private per CTA: accumulate (first == 0) or overwrite (first != 0); the sum over CTAs
 // is taken once per backward pass by wgrad_reduce_kernel (no atomics on the hot path).
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
-                                                            const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
+// One launch may cover several time steps (K = steps x nodes): the q images of step t are at q_img + t * step_stride, its
+// B operands are batch.s_img[t] / batch.h_img[t].  Batching all T steps of a backward pass into one launch removes T-1
+// epilogues (read-modify-write of the 58 MB of private partial sums), T-1 pipeline ramps and T-1 launches.
+constexpr int kWgMaxSteps = 16;
+struct WgBatch {
+  const uint8_t *s_img[kWgMaxSteps];
+  const uint8_t *h_img[kWgMaxSteps];
+  int32_t steps;
+};
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride, size_t step_stride,
+                                                            const __grid_constant__ WgBatch batch,
                                                             int32_t N, float *__restrict__ partial, int first) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -410,8 +419,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = blockIdx.y;
-  const int num_tiles = (N + kTileM - 1) / kTileM;
-  const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int num_tiles = (N + kTileM - 1) / kTileM;           // per time step
+  const int all_tiles = num_tiles * batch.steps;
+  const int my_tiles = (all_tiles > (int)blockIdx.x) ? (all_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgSlots; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
@@ -433,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
     if (elect_one()) {
       int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int idx = (int)blockIdx.x + i * (int)gridDim.x;
+        const int t = idx / num_tiles, tile = idx - t * num_tiles;
         for (int w = 0; w < 4; ++w) {
           const int slot = wg_slot(i, w);
           if (uses[slot] > 0) mbar_wait(empty_bar(slot), (uses[slot] - 1) & 1);
@@ -441,10 +452,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
           if (w == 0) trace_stamp(tron, i, 1);
           if (w == 3) trace_stamp(tron, i, 2);
           const uint8_t *src;
-          if (w == 0) src = (role == 0) ? s_img : h_img;
+          if (w == 0) src = (role == 0) ? batch.s_img[t] : batch.h_img[t];
           else {
             const int pl = (w == 3) ? (role == 0 ? 2 : 3) : (w - 1);
-            src = q_img + (size_t)pl * img_stride;
+            src = q_img + (size_t)t * step_stride + (size_t)pl * img_stride;
           }
           mbar_arrive_expect_tx(full_bar(slot), kWgSlotBytes);
           bulk_g2s(sbase + slot * kWgSlotBytes, src + (size_t)tile * kImageTileBytes, kWgSlotBytes, full_bar(slot));
@@ -574,9 +585,15 @@ int gru_tc2b_trace_read(void *host, size_t bytes) {
   return DDFA_OK;
 }
 
-// workspace: [dgrad3 packed weights 384 KB][q images x 4][h image][dh' * z plane (image-sized)][wgrad partial sums]
+// workspace: [dgrad3 packed weights 384 KB][h image][dh' * z plane (image-sized)][s image (fp32-s entry only)]
+//            [wgrad partial sums][q images x 4] x slots   (one slot, or one per time step when the weight-gradient GEMM of a
+//            whole backward pass is batched into one launch)
 static constexpr size_t kPackedTotal = tc2b::kD3PackedBytes;
-size_t gru_tc2_bwd_workspace_bytes(int32_t N) { return kPackedTotal + 6 * tcc::image_bytes(N) + wg_partial_bytes(); }
+static size_t bwd_fixed_bytes(int32_t N) { return kPackedTotal + 3 * tcc::image_bytes(N) + wg_partial_bytes(); }
+void *gru_tc2_bwd_s_image_scratch(void *workspace, int32_t N) { return static_cast<uint8_t *>(workspace) + kPackedTotal + 2 * tcc::image_bytes(N); }
+size_t gru_tc2_bwd_workspace_bytes(int32_t N, int32_t slots) {
+  return bwd_fixed_bytes(N) + (size_t)(slots < 1 ? 1 : slots) * 4 * tcc::image_bytes(N);
+}
 
 
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -592,11 +609,11 @@ int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace,
 
 // dW' += sum of the per-CTA partial sums, dWhh likewise (closes a deferred weight-gradient accumulation)
 int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
+  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N, 1)) {
     set_error("tcgen05 engine (bwd finish): workspace too small");
     return DDFA_ERR_WORKSPACE;
   }
-  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + kPackedTotal + 6 * tcc::image_bytes(N));
+  float *partial = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) + kPackedTotal + 3 * tcc::image_bytes(N));
   const int n4 = (int)(tc2b::kWgPartialFloats / 4);
   tc2b::wgrad_reduce_kernel<<<dim3((n4 + 255) / 256, 2), 256, 0, stream>>>(partial, kWgCtas, dw_fold, dw_hh);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_reduce_kernel");
@@ -605,21 +622,24 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
 
 // wgrad_mode: 0 = immediate (dW += this step's contribution before returning), 1 = first step of a deferred accumulation
 // (partials overwritten), 2 = further deferred step (partials accumulated); deferred passes end with gru_tc2_bwd_finish.
+// wgrad_mode >= 16: keep this step's q images in workspace slot (wgrad_mode - 16) and run no weight-gradient GEMM now —
+// gru_tc2_bwd_wgrad_batched does it for all kept steps in one launch.
 // h_img_in: the activation image of h (kept from the forward pass) or NULL (then it is rebuilt inside the workspace).
 // ds_in / indptr_t / indices_t: NULL, or the incoming gradient is dh_out + A^T ds_in (A^T as a CSR over the transposed graph)
 int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *indptr_t, const int32_t *indices_t, const float *h,
                      const void *h_img_in, const void *s_img, const float *gates, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
                      float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
-  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N)) {
-    set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N));
+  const int q_slot = wgrad_mode >= 16 ? wgrad_mode - 16 : 0;
+  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N, q_slot + 1)) {
+    set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N, q_slot + 1));
     return DDFA_ERR_WORKSPACE;
   }
   uint8_t *packed = static_cast<uint8_t *>(workspace);
   const size_t img = tcc::image_bytes(N);
-  uint8_t *q_img = packed + kPackedTotal;
-  uint8_t *h_img_ws = q_img + 4 * img;
+  uint8_t *h_img_ws = packed + kPackedTotal;
   float *dhz = reinterpret_cast<float *>(h_img_ws + img);
-  float *partial = reinterpret_cast<float *>(h_img_ws + 2 * img);
+  float *partial = reinterpret_cast<float *>(h_img_ws + 3 * img);
+  uint8_t *q_img = packed + bwd_fixed_bytes(N) + (size_t)q_slot * 4 * img;
   const uint8_t *h_img = h_img_in ? static_cast<const uint8_t *>(h_img_in) : h_img_ws;
   const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
   unsigned gb_grid = 1;
@@ -641,12 +661,48 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
                                                                                  reinterpret_cast<const uint32_t *>(packed), N, ds, dh);
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
   }
+  if (wgrad_mode >= 16) return DDFA_OK;       // q images kept; the batched weight-gradient launch follows the last step
   // every one of the 74 x 2 CTAs writes its partial slot (zeros if it owns no tile), so the reduction can sum all of them
-  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, static_cast<const uint8_t *>(s_img), h_img, N,
-                                                                                     partial, wgrad_mode == 2 ? 0 : 1);
+  tc2b::WgBatch one = {};
+  one.s_img[0] = static_cast<const uint8_t *>(s_img);
+  one.h_img[0] = h_img;
+  one.steps = 1;
+  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 0, one, N, partial, wgrad_mode == 2 ? 0 : 1);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
   if (wgrad_mode == 0) return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, stream);
   return DDFA_OK;
+}
+
+// dW' += sum_t [q_r q_z q_n]_t^T s_t, dWhh += sum_t [q_r q_z q_nr]_t^T h_t over the `steps` slots kept by gru_tc2_step_bwd
+// (wgrad_mode = 16 + slot): ONE weight-gradient launch with K = steps x nodes, then the reduction of the per-CTA partials.
+int gru_tc2_bwd_wgrad_batched(const void *const *s_imgs, const void *const *h_imgs, int32_t steps, int32_t N, float *dw_fold,
+                              float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (steps < 1 || steps > tc2b::kWgMaxSteps) {
+    set_error("tcgen05 engine (batched wgrad): 1 <= steps <= %d required (got %d)", tc2b::kWgMaxSteps, steps);
+    return DDFA_ERR_INVALID_ARG;
+  }
+  if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N, steps)) {
+    set_error("tcgen05 engine (batched wgrad): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N, steps));
+    return DDFA_ERR_WORKSPACE;
+  }
+  uint8_t *packed = static_cast<uint8_t *>(workspace);
+  const size_t img = tcc::image_bytes(N);
+  float *partial = reinterpret_cast<float *>(packed + kPackedTotal + 3 * img);
+  const uint8_t *q_img = packed + bwd_fixed_bytes(N);
+  tc2b::WgBatch b = {};
+  for (int t = 0; t < steps; ++t) {
+    if (!s_imgs[t] || !h_imgs[t]) {
+      set_error("tcgen05 engine (batched wgrad): NULL image pointer for step %d", t);
+      return DDFA_ERR_INVALID_ARG;
+    }
+    b.s_img[t] = static_cast<const uint8_t *>(s_imgs[t]);
+    b.h_img[t] = static_cast<const uint8_t *>(h_imgs[t]);
+  }
+  b.steps = steps;
+  DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
+  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 4 * img, b, N, partial, 1);
+  DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
+  return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, stream);
 }
 
 }  // namespace ddfa

@@ -341,7 +341,10 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     ds_prev = None                     # tcgen05 engine: ds of the step after t, folded into step t's call (dh' = dh + A^T ds)
     ds_alt = alloc.get("ds_b", (N, D)) if engine == ENGINE_TCGEN05 else None
     fuse_gather = os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0"   # A/B switch for scripts; both paths are the CUDA kernels
-    ws_bytes = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, engine)
+    # tcgen05: keep the q images of every step and run the weight-gradient GEMM of the whole pass as ONE launch at the end
+    batched_wgrad = (engine == ENGINE_TCGEN05 and bool(saved.h_img) and 0 < T <= 16
+                     and os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0")       # env: A/B switch for scripts
+    ws_bytes = L.call("ddfa_gru_step_bwd_workspace_bytes_steps", N, D, engine, T if batched_wgrad else 1)
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
@@ -349,7 +352,7 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
             _call("ddfa_gru_step_bwd_image", _p(dh), _p(ds_prev), _p(dg.indptr_t), _p(dg.indices_t), _p(saved.h[t]),
                   _p(saved.h_img[t]) if saved.h_img else None, _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
                   _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
-                  1 if t == T - 1 else 2, st, tag="ddfa_gru_step_bwd")   # deferred weight-gradient accumulation
+                  (16 + t) if batched_wgrad else (1 if t == T - 1 else 2), st, tag="ddfa_gru_step_bwd")   # deferred weight gradient
             if fuse_gather:
                 ds_prev, ds, ds_alt = ds, ds_alt, ds
                 dh, dh_alt = dh_alt, dh
@@ -364,7 +367,11 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     if engine == ENGINE_TCGEN05 and T > 0:
         if fuse_gather:     # the gather of the last ds (step 0) has no following step to ride on
             _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds_prev), N, D, _p(dh), 1, st, tag="gather_bwd")
-        L.call("ddfa_gru_step_bwd_finish", N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st)
+        if batched_wgrad:
+            _call("ddfa_gru_bwd_wgrad_batched", ptr_array([_p(saved.s[t]) for t in range(T)]), ptr_array([_p(saved.h_img[t]) for t in range(T)]),
+                  T, N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st, tag="wgrad_batched")
+        else:
+            L.call("ddfa_gru_step_bwd_finish", N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st)
     L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
            _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)
     _call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,

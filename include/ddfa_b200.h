@@ -172,6 +172,15 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int
  * (1 = first step, overwrites; 2 = later steps) and ddfa_gru_step_bwd_finish adds them to dw_fold / dw_hh once. */
 int ddfa_gru_step_bwd_finish(int32_t num_nodes, int32_t dim, float *dw_fold, float *dw_hh, void *workspace,
                              size_t workspace_bytes, void *stream);
+/* wgrad_mode = DDFA_WGRAD_KEEP(slot): run no weight-gradient GEMM in the step call; its q images stay in slot `slot` of a
+ * workspace sized by ddfa_gru_step_bwd_workspace_bytes_steps(N, D, TCGEN05, steps).  After the last step ONE call does the
+ * weight-gradient GEMM of all kept steps (K = steps x nodes) and adds it to dw_fold / dw_hh:
+ * s_images / h_images = host arrays of `steps` device pointers, entry t = the images of s_t and h_t that belong to slot t. */
+#define DDFA_WGRAD_KEEP(slot) (16 + (slot))
+#define DDFA_WGRAD_MAX_STEPS 16
+size_t ddfa_gru_step_bwd_workspace_bytes_steps(int32_t num_nodes, int32_t dim, int engine, int32_t steps);
+int ddfa_gru_bwd_wgrad_batched(const void *const *s_images, const void *const *h_images, int32_t steps, int32_t num_nodes,
+                               int32_t dim, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Backward of one step.  In: dh_out, h (step input), s, gates.  Out: ds [N,D] (to be
  * transposed-gathered by the caller), dh [N,D] = dh_out*z + dgh W_hh (overwritten).
