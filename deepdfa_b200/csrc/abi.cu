@@ -1,5 +1,6 @@
 // Error plumbing and library-level queries of the C ABI (include/ddfa_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -11,6 +12,14 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("DDFA_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 void set_error(const char *fmt, ...) {
   va_list ap;

@@ -40,6 +40,32 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
     }                                                                                  \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The per-step kernels form a chain in one stream.  Launched with the programmatic-serialization attribute, kernel i+1's CTAs
+// may start as soon as every CTA of kernel i has called pdl_launch_dependents() and an SM has room — i.e. in kernel i's tail
+// (the persistent GEMM kernels leave 10-19 % of the SMs idle at the end: 300 tiles over 37 / 74 CTA groups) — run their
+// prologue (barrier init, TMEM allocation, weights -> TMEM) and then block in pdl_wait() until kernel i has completed and its
+// writes are visible.  Rule for every kernel launched this way: nothing written by an earlier kernel of the chain is read,
+// and nothing is written, before pdl_wait().  Both instructions are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // abi.cu: $DDFA_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t v0 = warp_global * ROWS;
   const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
+  pdl_launch_dependents();
   if (v0 >= Npad) return;
   const int nrows = (int)min((int64_t)ROWS, Npad - v0);
   int32_t myptr = 0;
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
   const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
   const int32_t total = __shfl_sync(0xffffffffu, myptr, nrows) - beg0;
   const int32_t pre = (lane < total) ? __ldg(indices + beg0 + lane) : 0;
+  pdl_wait();     // the CSR arrays above are constant during a pass; h comes from the previous kernel of the chain
 #pragma unroll 1
   for (int p = 0; p < PASSES; ++p) {
     const int r0 = p * RW;
@@ -287,7 +289,8 @@ int ddfa_gather_sum_image(const int32_t *indptr, const int32_t *indices, const f
   const int64_t rows = ((int64_t)N + 127) / 128 * 128;
   const int64_t warps = (rows + 3) / 4;
   const int64_t blocks = (warps * 32 + 127) / 128;
-  gather_sum_image_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream_)>>>(indptr, indices, h, N, static_cast<uint8_t *>(out_image), out_f32);
+  DDFA_CUDA(launch_chain(gather_sum_image_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices, h, N,
+                         static_cast<uint8_t *>(out_image), out_f32));
   DDFA_CHECK_LAUNCH("gather_sum_image_kernel");
   return DDFA_OK;
 }

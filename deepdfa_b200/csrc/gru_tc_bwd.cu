@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
   __shared__ float red[kGbWarps][7 * kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = lane * 4;
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t plane = (size_t)N * kD;
   float4 sum[7];
 #pragma unroll
@@ -236,10 +238,12 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tron = (g_trace_on == 1);
   if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== producer: per tile the three q matrices of this role, one 64 KB copy each =====
     if (elect_one()) {
+      pdl_wait();      // the q images come from gate_bwd_image_kernel, the previous kernel of the chain
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = num_tiles - 1 - (group + k * num_groups);   // back to front: the q tiles written last are still in L2
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
+    pdl_wait();
 
     float *out = role == 0 ? ds : dh;
     const bool tr = (warp == 2 && lane == 0);
@@ -647,9 +652,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     const int64_t want = (rows + tc2b::kGbWarps - 1) / tc2b::kGbWarps;
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
-  tc2b::gate_bwd_image_kernel<<<gb_grid, 32 * tc2b::kGbWarps, 0, stream>>>(
-      dh_out, h, gates, indptr, ds_in, ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold,
-      db_ih, db_hh);
+  DDFA_CUDA(launch_chain(tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h, gates, indptr, ds_in,
+                         ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh));
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
@@ -657,8 +661,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kD3SmemAlloc));
     int groups = kNumSMs / 2;
     if (groups > tiles) groups = tiles;
-    tc2b::dgrad3_kernel<<<groups * 2, tc2b::kThreads, tc2b::kD3SmemAlloc, stream>>>(q_img, img, dhz,
-                                                                                 reinterpret_cast<const uint32_t *>(packed), N, ds, dh);
+    DDFA_CUDA(launch_chain(tc2b::dgrad3_kernel, dim3(groups * 2), dim3(tc2b::kThreads), tc2b::kD3SmemAlloc, stream, q_img, img, dhz,
+                           reinterpret_cast<const uint32_t *>(packed), N, ds, dh));
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
   }
   if (wgrad_mode >= 16) return DDFA_OK;       // q images kept; the batched weight-gradient launch follows the last step

@@ -131,10 +131,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tron = g_trace_on;
   if (threadIdx.x == 0) trace_stamp(tron, 0, 0);
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== producer: per tile the s tile and the h tile, one 64 KB bulk copy each =====
     if (my_tiles > 0 && elect_one()) {
+      pdl_wait();      // the images are written by the previous kernels of the chain
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_ready);
+    pdl_wait();        // everything above (barriers, TMEM, the packed weights) is independent of the previous kernel
 
     const size_t plane = (size_t)N * kD;
     float *X = reinterpret_cast<float *>(smem + kOffX) + (size_t)(warp - 2) * kXFloats;   // warp-private exchange tile
@@ -327,9 +330,9 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
   DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc));
   int groups = kNumSMs / tc3::kSlices;
   if (groups > tiles) groups = tiles;
-  tc3::gru_fwd3_kernel<<<groups * tc3::kSlices, tc3::kThreads, tc3::kSmemAlloc, stream>>>(
-      static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr, static_cast<const uint8_t *>(packed), N, h_out,
-      static_cast<uint8_t *>(h_out_img), save_gates);
+  DDFA_CUDA(launch_chain(tc3::gru_fwd3_kernel, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc, stream,
+                         static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,
+                         static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates));
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
   return DDFA_OK;
 }
