@@ -13,12 +13,20 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 
-bool pdl_enabled() {
-  static const bool on = [] {
+static thread_local bool g_chain_break = true;
+void chain_break() { g_chain_break = true; }
+bool chain_take_break() {
+  const bool b = g_chain_break;
+  g_chain_break = false;
+  return b;
+}
+
+int pdl_mask() {
+  static const int mask = [] {
     const char *e = getenv("DDFA_PDL");
-    return !(e && e[0] == '0');
+    return e ? atoi(e) : 15;
   }();
-  return on;
+  return mask;
 }
 
 void set_error(const char *fmt, ...) {

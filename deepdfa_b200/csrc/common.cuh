@@ -45,14 +45,25 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 // may start as soon as every CTA of kernel i has called pdl_launch_dependents() and an SM has room — i.e. in kernel i's tail
 // (the persistent GEMM kernels leave 10-19 % of the SMs idle at the end: 300 tiles over 37 / 74 CTA groups) — run their
 // prologue (barrier init, TMEM allocation, weights -> TMEM) and then block in pdl_wait() until kernel i has completed and its
-// writes are visible.  Rule for every kernel launched this way: nothing written by an earlier kernel of the chain is read,
-// and nothing is written, before pdl_wait().  Both instructions are no-ops in a normal launch.
+// writes are visible.  Rules for every kernel launched this way:
+//   * nothing is written before pdl_wait();
+//   * the only global data read before pdl_wait() are the packed weights of the pass;
+//   * EVERY global load of a chain kernel is ld.global.cg (L2 only), before and after the wait: between two kernels chained
+//     this way the SM's L1 is not invalidated, so an L1-cached load (ld.global.nc / __ldg, or a default ld.global) can return
+//     a line fetched before an earlier kernel rewrote that address.  Measured: with gather_image AND gru_fwd3 chained and
+//     __ldg loads, a training run over per-shape static input buffers read the previous batch's CSR arrays
+//     (tests/test_parity_gpu.py::test_fused_trainer_cuda_graph_paths_match_eager caught it; either kernel alone passed);
+//   * the kernel that follows a weight-packing kernel is launched normally (chain_break()), so the packed weights are
+//     complete and flushed before any chain kernel can start its prologue.
+// Both instructions are no-ops in a normal launch.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-bool pdl_enabled();   // abi.cu: $DDFA_PDL != "0"
+int pdl_mask();       // abi.cu: $DDFA_PDL — unset: all chain kernels; "0": none; else a bit mask (1 gather_image, 2 gru_fwd3, 4 gate_bwd, 8 dgrad3)
+void chain_break();   // abi.cu: the next launch_chain() on this thread is a normal (fully serialised) launch
+bool chain_take_break();
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -62,7 +73,8 @@ inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const bool brk = chain_take_break();
+  cfg.numAttrs = ((pdl_mask() & which) && !brk) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -109,6 +121,9 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
                : "l"(p));
   return v;
 }
+
+// L2-only load (ld.global.cg): for kernels of the PDL chain, whose L1 may hold lines from before the predecessor's writes
+__device__ __forceinline__ float4 ldg_cg_f4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

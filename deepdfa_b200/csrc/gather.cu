@@ -154,14 +154,14 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
   const int64_t v0 = warp_global * ROWS;
   const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
   pdl_launch_dependents();
+  pdl_wait();     // before ANY global read: the CSR arrays may have been rebuilt in place for this step (common.cuh, PDL rules)
   if (v0 >= Npad) return;
   const int nrows = (int)min((int64_t)ROWS, Npad - v0);
   int32_t myptr = 0;
-  if (lane <= nrows) myptr = __ldg(indptr + min(v0 + lane, (int64_t)N));   // padded rows: empty neighbour list
+  if (lane <= nrows) myptr = __ldcg(indptr + min(v0 + lane, (int64_t)N));   // padded rows: empty neighbour list
   const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
   const int32_t total = __shfl_sync(0xffffffffu, myptr, nrows) - beg0;
-  const int32_t pre = (lane < total) ? __ldg(indices + beg0 + lane) : 0;
-  pdl_wait();     // the CSR arrays above are constant during a pass; h comes from the previous kernel of the chain
+  const int32_t pre = (lane < total) ? __ldcg(indices + beg0 + lane) : 0;
 #pragma unroll 1
   for (int p = 0; p < PASSES; ++p) {
     const int r0 = p * RW;
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
       for (int j = 0; j < UNROLL; ++j) {
         const int32_t pos = min(b + j, pend - 1);
         int32_t u = __shfl_sync(0xffffffffu, pre, pos & 31);
-        if (pos >= 32) u = __ldg(indices + beg0 + pos);
-        v[j] = (b + j < pend) ? ldg_nc_f4(h + (int64_t)u * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pos >= 32) u = __ldcg(indices + beg0 + pos);
+        v[j] = (b + j < pend) ? __ldcg(reinterpret_cast<const float4 *>(h + (int64_t)u * D + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
@@ -289,7 +289,7 @@ int ddfa_gather_sum_image(const int32_t *indptr, const int32_t *indices, const f
   const int64_t rows = ((int64_t)N + 127) / 128 * 128;
   const int64_t warps = (rows + 3) / 4;
   const int64_t blocks = (warps * 32 + 127) / 128;
-  DDFA_CUDA(launch_chain(gather_sum_image_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices, h, N,
+  DDFA_CUDA(launch_chain(1, gather_sum_image_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices, h, N,
                          static_cast<uint8_t *>(out_image), out_f32));
   DDFA_CHECK_LAUNCH("gather_sum_image_kernel");
   return DDFA_OK;

@@ -41,15 +41,15 @@ __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_o
                                         const int32_t *__restrict__ indptr_t, size_t plane, int64_t node, int col, bool ok) {
   x.tb = x.te = 0;
   if (ok) {
-    if (indptr_t) { x.tb = __ldg(indptr_t + node); x.te = __ldg(indptr_t + node + 1); }
+    if (indptr_t) { x.tb = __ldcg(indptr_t + node); x.te = __ldcg(indptr_t + node + 1); }
     const size_t off = (size_t)node * kD + col;
-    x.d = ldg_nc_f4(dh_out + off);
-    x.hv = ldg_nc_f4(h + off);
-    x.rr = ldg_nc_f4(gates + off);
-    x.zz = ldg_nc_f4(gates + plane + off);
-    x.nn = ldg_nc_f4(gates + 2 * plane + off);
-    x.gh = ldg_nc_f4(gates + 3 * plane + off);
-    x.deg = (float)(__ldg(indptr + node + 1) - __ldg(indptr + node));
+    x.d = ldg_cg_f4(dh_out + off);
+    x.hv = ldg_cg_f4(h + off);
+    x.rr = ldg_cg_f4(gates + off);
+    x.zz = ldg_cg_f4(gates + plane + off);
+    x.nn = ldg_cg_f4(gates + 2 * plane + off);
+    x.gh = ldg_cg_f4(gates + 3 * plane + off);
+    x.deg = (float)(__ldcg(indptr + node + 1) - __ldcg(indptr + node));
   }
 }
 
@@ -116,19 +116,19 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
       int ia[4], ib[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        ia[k] = (a.tb + k < a.te) ? __ldg(indices_t + a.tb + k) : -1;
-        ib[k] = (b.tb + k < b.te) ? __ldg(indices_t + b.tb + k) : -1;
+        ia[k] = (a.tb + k < a.te) ? __ldcg(indices_t + a.tb + k) : -1;
+        ib[k] = (b.tb + k < b.te) ? __ldcg(indices_t + b.tb + k) : -1;
       }
       float4 va[4], vb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        va[k] = ia[k] >= 0 ? ldg_nc_f4(ds_in + (size_t)ia[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[k] = ib[k] >= 0 ? ldg_nc_f4(ds_in + (size_t)ib[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[k] = ia[k] >= 0 ? ldg_cg_f4(ds_in + (size_t)ia[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[k] = ib[k] >= 0 ? ldg_cg_f4(ds_in + (size_t)ib[k] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) { f4_add(a.d, va[k]); f4_add(b.d, vb[k]); }
-      for (int j = a.tb + 4; j < a.te; ++j) f4_add(a.d, ldg_nc_f4(ds_in + (size_t)__ldg(indices_t + j) * kD + col));
-      for (int j = b.tb + 4; j < b.te; ++j) f4_add(b.d, ldg_nc_f4(ds_in + (size_t)__ldg(indices_t + j) * kD + col));
+      for (int j = a.tb + 4; j < a.te; ++j) f4_add(a.d, ldg_cg_f4(ds_in + (size_t)__ldcg(indices_t + j) * kD + col));
+      for (int j = b.tb + 4; j < b.te; ++j) f4_add(b.d, ldg_cg_f4(ds_in + (size_t)__ldcg(indices_t + j) * kD + col));
     }
     finish(a, node, ok_a);
     if (node2 < Npad) finish(b, node2, ok_b);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
       for (int c = 0; c < kD3Chunks / 2; ++c) {
         const int chunk = e * (kD3Chunks / 2) + c;
         const uint4 *p = src + (size_t)chunk * 128 * 4;
-        const uint4 x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3);
+        const uint4 x0 = __ldcg(p), x1 = __ldcg(p + 1), x2 = __ldcg(p + 2), x3 = __ldcg(p + 3);   // L2 loads: PDL rules, common.cuh
         const uint32_t w[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
         tmem_st16(lane_addr + (uint32_t)(chunk * 16), w);
       }
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
         float dv[32];
         if (role == 1) {       // dh = acc + (dh' * z) : fetch the elementwise term (written by gate_bwd) while the MMAs run
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dv[i] = (i < rows_valid) ? __ldg(dhz + (node0 + i) * kD + col) : 0.f;
+          for (int i = 0; i < 32; ++i) dv[i] = (i < rows_valid) ? __ldcg(dhz + (node0 + i) * kD + col) : 0.f;
         }
         mbar_wait(acc_full(half), k & 1);
         tc_fence_after();
@@ -609,6 +609,7 @@ int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace,
   const int total = 2 * tc2b::kD3Chunks * 128;
   tc2b::dgrad3_pack_kernel<<<(total + 127) / 128, 128, 0, stream>>>(w_fold, w_hh, static_cast<uint32_t *>(workspace));
   DDFA_CHECK_LAUNCH("tc2b::dgrad3_pack_kernel");
+  chain_break();
   return DDFA_OK;
 }
 
@@ -652,7 +653,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     const int64_t want = (rows + tc2b::kGbWarps - 1) / tc2b::kGbWarps;
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
-  DDFA_CUDA(launch_chain(tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h, gates, indptr, ds_in,
+  DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h, gates, indptr, ds_in,
                          ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh));
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
@@ -661,7 +662,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     DDFA_CUDA(cudaFuncSetAttribute(tc2b::dgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kD3SmemAlloc));
     int groups = kNumSMs / 2;
     if (groups > tiles) groups = tiles;
-    DDFA_CUDA(launch_chain(tc2b::dgrad3_kernel, dim3(groups * 2), dim3(tc2b::kThreads), tc2b::kD3SmemAlloc, stream, q_img, img, dhz,
+    DDFA_CUDA(launch_chain(8, tc2b::dgrad3_kernel, dim3(groups * 2), dim3(tc2b::kThreads), tc2b::kD3SmemAlloc, stream, q_img, img, dhz,
                            reinterpret_cast<const uint32_t *>(packed), N, ds, dh));
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
   }

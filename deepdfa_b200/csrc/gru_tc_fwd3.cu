@@ -21,6 +21,8 @@
 //     32-node quarter of the tile) each read 16 nodes per tcgen05.ld, swap them through a warp-private, conflict-free
 //     shared-memory tile (thread (gate, c) -> thread (node mod 4, c)), and finish nodes {g, g+4, g+8, g+12} x column c:
 //     no cross-warp barrier anywhere in the epilogue; global accesses are 32-byte row segments (full sectors).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ddfa {
@@ -205,14 +207,14 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       for (int cc = 0; cc < kChunks / 4; ++cc) {
         const int chunk = e * (kChunks / 4) + cc;
         const uint4 *p = src + (size_t)chunk * 128 * 4;
-        const uint4 x0 = __ldg(p), x1 = __ldg(p + 1), x2 = __ldg(p + 2), x3 = __ldg(p + 3);
+        const uint4 x0 = __ldcg(p), x1 = __ldcg(p + 1), x2 = __ldcg(p + 2), x3 = __ldcg(p + 3);   // L2 loads: PDL rules, common.cuh
         const uint32_t w[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
         tmem_st16(lane_addr + (uint32_t)(chunk * 16), w);
       }
       tmem_st_wait();
       const float *bias = reinterpret_cast<const float *>(packed + kPackedWBytes) + slice * kBiasSlice + scol;
-      b_gin = __ldg(bias); b_r = __ldg(bias + kSliceCols); b_z = __ldg(bias + 2 * kSliceCols); b_ghn = __ldg(bias + 3 * kSliceCols);
-      d_gin = __ldg(bias + 4 * kSliceCols); d_r = __ldg(bias + 5 * kSliceCols); d_z = __ldg(bias + 6 * kSliceCols);
+      b_gin = __ldcg(bias); b_r = __ldcg(bias + kSliceCols); b_z = __ldcg(bias + 2 * kSliceCols); b_ghn = __ldcg(bias + 3 * kSliceCols);
+      d_gin = __ldcg(bias + 4 * kSliceCols); d_r = __ldcg(bias + 5 * kSliceCols); d_z = __ldcg(bias + 6 * kSliceCols);
     }
     tc_fence_before();
     __syncwarp();
@@ -224,18 +226,21 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     const bool tr = (warp == 2 && lane == 0);
     // h and the in-degree of the 8 nodes this thread finishes per tile (two 16-node chunks x nodes g, g+4, g+8, g+12) are
     // fetched one tile ahead, so their latency hides behind the current tile's work
+    // All loads are L2 loads (PDL rules, common.cuh).  The in-degrees of the warp's 32 nodes come in as two coalesced loads
+    // (lane = node) and are handed to the threads that need them by shuffles at use time.
     float hp_n[8];
-    int ip0_n[8], ip1_n[8];      // raw indptr entries: the subtraction waits until the values are used, not when they are requested
+    int ip0_n = 0, ip1_n = 0;    // raw indptr entries of node nw + lane: the subtraction waits until the values are used
     auto prefetch = [&](int kk) {
       const int64_t nw = (int64_t)(group + kk * num_groups) * kTileM + e * 32;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t node = nw + (i >> 2) * 16 + g + 4 * (i & 3);
         const bool ok = kk < my_tiles && node < N;
-        hp_n[i] = ok ? __ldg(h + node * kD + gcol) : 0.f;
-        ip0_n[i] = ok ? __ldg(indptr + node) : 0;
-        ip1_n[i] = ok ? __ldg(indptr + node + 1) : 0;
+        hp_n[i] = ok ? __ldcg(h + node * kD + gcol) : 0.f;
       }
+      const bool okl = kk < my_tiles && nw + lane < N;
+      ip0_n = okl ? __ldcg(indptr + nw + lane) : 0;
+      ip1_n = okl ? __ldcg(indptr + nw + lane + 1) : 0;
     };
     prefetch(0);
     for (int k = 0; k < my_tiles; ++k) {
@@ -245,7 +250,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       if (tr) trace_stamp(tron, k, 7);
       float hp[8], deg[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { hp[i] = hp_n[i]; deg[i] = (float)(ip1_n[i] - ip0_n[i]); }
+      for (int i = 0; i < 8; ++i) hp[i] = hp_n[i];
+      {
+        const float dl = (float)(ip1_n - ip0_n);           // in-degree of node node_w + lane
+#pragma unroll
+        for (int i = 0; i < 8; ++i) deg[i] = __shfl_sync(0xffffffffu, dl, (i >> 2) * 16 + g + 4 * (i & 3));
+      }
       prefetch(k + 1);
       mbar_wait(acc_full(buf), buse & 1);
       tc_fence_after();
@@ -321,6 +331,7 @@ int gru_tc3_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
   const int total = tc3::kSlices * tc3::kChunks * 128;
   tc3::pack_kernel<<<(total + 127) / 128, 128, 0, stream>>>(w_fold, w_hh, b_fold, b_ih, b_hh, static_cast<uint8_t *>(packed));
   DDFA_CHECK_LAUNCH("tc3::pack_kernel");
+  chain_break();
   return DDFA_OK;
 }
 
@@ -330,7 +341,7 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
   DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc));
   int groups = kNumSMs / tc3::kSlices;
   if (groups > tiles) groups = tiles;
-  DDFA_CUDA(launch_chain(tc3::gru_fwd3_kernel, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc, stream,
+  DDFA_CUDA(launch_chain(2, tc3::gru_fwd3_kernel, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc, stream,
                          static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,
                          static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates));
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
