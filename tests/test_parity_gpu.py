@@ -270,3 +270,26 @@ def test_fused_trainer_cuda_graph_paths_match_eager(engine):
         for a, b in zip(losses["eager"], losses[mode]):
             assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (mode, losses["eager"], losses[mode])
     assert losses["eager"][0] != losses["eager"][3]      # the parameters did move
+
+
+@pytest.mark.gpu
+def test_batched_weight_gradient_matches_per_step(monkeypatch):
+    """tcgen05 engine: the one-launch weight-gradient GEMM over all T steps (default) and the per-step deferred accumulation give
+    the same parameter gradients; so do the backward with the transposed gather folded into gate_bwd and the unfused one."""
+    torch.manual_seed(3)
+    b = synth.make_batch(24, 60, seed=5, variable=True, vuln_rate=0.3)
+    grads = {}
+    for key, env in (("default", {}), ("per_step_wgrad", {"DDFA_BATCHED_WGRAD": "0"}), ("unfused_gather", {"DDFA_FUSE_GATHER_BWD": "0"})):
+        for k in ("DDFA_BATCHED_WGRAD", "DDFA_FUSE_GATHER_BWD"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        torch.manual_seed(11)
+        m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 6, 2, concat_all_absdf=True, engine="tcgen05").to(DEV)
+        loss = m.training_step((b, {}), 0)
+        loss.backward()
+        grads[key] = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    for key in ("per_step_wgrad", "unfused_gather"):
+        for n, gref in grads["default"].items():
+            scale = max(1e-6, float(gref.abs().max()))
+            assert float((grads[key][n] - gref).abs().max()) < 2e-4 * scale, (key, n)
