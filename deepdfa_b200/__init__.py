@@ -12,7 +12,8 @@ Importing the package does not load the CUDA library; the first kernel call does
 from .batched_graph import BatchedCFG, add_self_loop, as_batched_cfg, batch, collate, graph, unbatch  # noqa: F401
 from .module import FlowGNNGGNNModule, allfeats  # noqa: F401
 from .trainer import FusedTrainer  # noqa: F401
+from .arena import ArenaBatch, GraphArena  # noqa: F401
 from . import synth  # noqa: F401
 
-__all__ = ["FlowGNNGGNNModule", "FusedTrainer", "BatchedCFG", "batch", "unbatch", "graph", "add_self_loop",
+__all__ = ["FlowGNNGGNNModule", "FusedTrainer", "GraphArena", "ArenaBatch", "BatchedCFG", "batch", "unbatch", "graph", "add_self_loop",
            "collate", "as_batched_cfg", "synth", "allfeats"]

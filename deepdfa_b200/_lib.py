@@ -44,6 +44,8 @@ _SIGNATURES = {
     "ddfa_build_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "ddfa_build_csr": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_graph_ptr": (_int, [_vp, _i32, _vp, _vp]),
+    "ddfa_arena_batch_workspace_bytes": (_sz, [_i32]),
+    "ddfa_arena_batch": (_int, [_vp, _i32, _i32] + [_vp] * 6 + [_i32, _vp, _i32, _i32] + [_vp] * 7 + [_vp, _sz, _vp]),
     "ddfa_embed_concat_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "ddfa_embed_concat_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _int, _vp]),
@@ -73,7 +75,7 @@ _SIGNATURES = {
 }
 
 _NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
-              "ddfa_build_csr_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
+              "ddfa_build_csr_workspace_bytes", "ddfa_arena_batch_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
               "ddfa_act_image_bytes"}
 
 

@@ -129,6 +129,51 @@ class FusedTrainer:
                 slot["graph"].replay()
         return self.loss_slot
 
+    def step_ids(self, arena, ids, global_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on the graphs ``ids`` of a device-resident :class:`deepdfa_b200.arena.GraphArena` (SURVEY.md §8
+        f1: the batch producer).  With ``use_cuda_graph`` the batch is assembled into static per-shape buffers by
+        ``ddfa_arena_batch`` inside one captured graph, so a step costs the H2D copy of the id list plus one graph launch;
+        otherwise it is ``step(arena.batch(ids))``."""
+        if not self.use_cuda_graph:
+            return self.step(arena.batch(ids), global_batch)
+        import numpy as np
+        m = self.module
+        ids_np = np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else ids, dtype=np.int64).reshape(-1)
+        if ids_np.size == 0 or ids_np.min() < 0 or ids_np.max() >= arena.num_graphs:
+            raise IndexError("step_ids: empty id list or graph id out of range")
+        B = int(ids_np.shape[0])
+        N = int(arena.nodes_per_graph[ids_np].sum())
+        Eg = int(arena.edges_per_graph[ids_np].sum())
+        gb = global_batch if global_batch is not None else B * self.world
+        key = ("arena", id(arena), N, Eg, B, gb)
+        slot = self._stream_slots.get(key)
+        with torch.cuda.device(self.device):
+            if slot is None:
+                slot = {"out": arena.alloc_outputs(B, N, Eg), "stage": torch.empty(B, dtype=torch.int32).pin_memory(),
+                        "graph": None, "warm": False, "keep": None}
+                self._stream_slots[key] = slot
+            slot["stage"].copy_(torch.from_numpy(ids_np.astype(np.int32)))
+            slot["out"]["ids"].copy_(slot["stage"], non_blocking=True)
+
+            def enqueue():
+                g = arena._assemble(slot["out"]["ids"], B, N, Eg, slot["out"])
+                g_, dg, idx = m._prepare(g)
+                self._enqueue(g_, dg, idx, g.ndata["_VULN"], gb)
+                return (g, dg, idx)
+
+            if not slot["warm"]:
+                slot["keep"] = enqueue()
+                slot["warm"] = True
+            else:
+                if slot["graph"] is None:
+                    torch.cuda.synchronize(self.device)
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        slot["keep"] = enqueue()
+                    slot["graph"] = cg
+                slot["graph"].replay()
+        return self.loss_slot
+
     def step(self, batch, global_batch: Optional[int] = None) -> torch.Tensor:
         """One optimisation step on this rank's shard.  Returns the device tensor holding the
         global mean loss (valid after the step's stream work completes)."""

@@ -76,6 +76,26 @@ int ddfa_build_csr(const void *src, const void *dst, int idx_bytes, int64_t num_
 int ddfa_graph_ptr(const int64_t *batch_num_nodes, int32_t num_graphs, int32_t *graph_ptr,
                    void *stream);
 
+/* Batch producer: replaces the host-side collate — `dgl.batch([...])` in the GraphDataLoader
+ * (DDFA/sastvd/linevd/datamodule.py:116-141) and `BigVulDatasetLineVD.get_indices` (DDFA/sastvd/linevd/dataset.py:63-76,
+ * `dgl.batch([...]).to(device)`) — plus DGL's lazy CSR build, by slicing a device-resident ARENA of all graphs:
+ *   arena = the CSR by destination and the CSR of the transposed graph over ALL graphs as one disjoint batch (what
+ *   ddfa_build_csr produces for it), node_off int32[G+1] (first node of every graph), num_feats int64 feature vectors and
+ *   the int32 _VULN vector over all nodes.
+ * Out, for the graphs graph_ids[0..B) in that order: graph_ptr int32[B+1], indptr / indptr_t int32[N+1], indices /
+ * indices_t int32[E], the feature vectors and _VULN restricted to the batch — bit-identical to ddfa_build_csr +
+ * ddfa_graph_ptr on the collated COO of the same graphs.  batch_nodes / batch_edges = N and E of the batch (the caller
+ * knows them from its host copy of the graph sizes; they size the outputs).  A bad id or inconsistent totals leave the
+ * outputs untouched and raise the int32 counter at workspace[(B + 1) * 4].  feats / out_feats: host arrays of device
+ * pointers, num_feats <= 8. */
+size_t ddfa_arena_batch_workspace_bytes(int32_t batch_size);
+int ddfa_arena_batch(const int32_t *graph_ids, int32_t batch_size, int32_t num_graphs, const int32_t *node_off,
+                     const int32_t *indptr, const int32_t *indices, const int32_t *indptr_t, const int32_t *indices_t,
+                     const int64_t *const *feats, int32_t num_feats, const int32_t *vuln, int32_t batch_nodes,
+                     int32_t batch_edges, int32_t *out_graph_ptr, int32_t *out_indptr, int32_t *out_indices,
+                     int32_t *out_indptr_t, int32_t *out_indices_t, int64_t *const *out_feats, int32_t *out_vuln,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * K1  embedding + concat.  Replaces ggnn.py:84-92 (4x nn.Embedding + torch.cat, or one).
  * idx[k]: int64[N] with values in [0,V); tables[k]: fp32[V,H]; x: fp32[N, K*H].
