@@ -292,7 +292,7 @@ def run_ours(args):
 
     # ---- capture one CUDA graph per resident batch (launch-bound inner loop: ~100 kernels per step) ------------------
     graph_note = "off (--no-graphs)"
-    if args.graphs:
+    if args.cuda_graphs:
         try:
             trainer.use_cuda_graph = True
             for i in range(2 * NUM_BATCHES):        # first visit: capture, second visit: replay
@@ -473,7 +473,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--graphs", type=int, default=CFG["graphs"], help="graphs per GPU per step")
     ap.add_argument("--engine", choices=["simt", "tcgen05"], default=os.environ.get("DDFA_B200_ENGINE", "tcgen05"))
-    ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="launch every kernel eagerly in the timed region")
+    ap.add_argument("--no-graphs", dest="cuda_graphs", action="store_false", help="launch every kernel eagerly in the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
