@@ -66,6 +66,9 @@ _SIGNATURES = {
     "ddfa_gru_bwd_wgrad_batched": (_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_prepare_bwd": (_int, [_vp, _vp, _i32, _int, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd": (_int, [_vp] * 7 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
+    "ddfa_ggnn_workspace_bytes": (_sz, [_i32, _i32, _i32, _int, _int]),
+    "ddfa_ggnn_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _int, _vp]),
+    "ddfa_ggnn_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 12 + [_vp, _sz, _int, _vp]),
     "ddfa_readout_mlp_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32] + [_vp] * 6 + [_vp]),
     "ddfa_mlp_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ddfa_readout_bwd": (_int, [_vp] * 5 + [_i32, _i32] + [_vp] * 8 + [_vp]),
@@ -76,7 +79,7 @@ _SIGNATURES = {
 
 _NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
               "ddfa_build_csr_workspace_bytes", "ddfa_arena_batch_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
-              "ddfa_act_image_bytes"}
+              "ddfa_act_image_bytes", "ddfa_ggnn_workspace_bytes"}
 
 
 class _Lib:

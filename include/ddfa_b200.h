@@ -218,6 +218,26 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
                       size_t workspace_bytes, int engine, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K3+K4 over all T steps: the whole dgl.nn.GatedGraphConv (ggnn.py:57-60 construction, :95 call) behind one call each.
+ * They sequence the per-step entry points above (same kernels, same order as deepdfa_b200/engine.py) and carve every
+ * intermediate out of ONE workspace of ddfa_ggnn_workspace_bytes(N, D, T, engine, training) bytes, which also carries
+ * the saved activations from ddfa_ggnn_fwd(training = 1) to ddfa_ggnn_bwd (same workspace, untouched in between).
+ *   fwd: x = h_0 [N,D] (the embedding output; must stay valid until the backward) -> h_out = h_T [N,D].
+ *   bwd: dh_T [N,D] -> dx [N,D] = dL/dh_0 (overwritten); dw_msg[D,D], db_msg[D], dw_ih[3D,D], dw_hh[3D,D], db_ih[3D],
+ *        db_hh[3D] accumulated (+=).  w_msg / b_msg = GatedGraphConv.linears[0], the rest = GatedGraphConv.gru.
+ * engine = DDFA_ENGINE_SIMT (any D % 4 == 0) or DDFA_ENGINE_TCGEN05 (D == 128). */
+size_t ddfa_ggnn_workspace_bytes(int32_t num_nodes, int32_t dim, int32_t n_steps, int engine, int training);
+int ddfa_ggnn_fwd(const int32_t *indptr, const int32_t *indices, const float *x, int32_t num_nodes, int32_t dim,
+                  int32_t n_steps, const float *w_msg, const float *b_msg, const float *w_ih, const float *w_hh,
+                  const float *b_ih, const float *b_hh, float *h_out, void *workspace, size_t workspace_bytes,
+                  int training, int engine, void *stream);
+int ddfa_ggnn_bwd(const int32_t *indptr, const int32_t *indptr_t, const int32_t *indices_t, const float *x,
+                  int32_t num_nodes, int32_t dim, int32_t n_steps, const float *w_msg, const float *b_msg,
+                  const float *w_ih, const float *w_hh, const float *dh_T, float *dx, float *dw_msg, float *db_msg,
+                  float *dw_ih, float *dw_hh, float *db_ih, float *db_hh, void *workspace, size_t workspace_bytes,
+                  int engine, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * K5-K7  readout + MLP.  Replaces torch.cat([ggnn_out, feat_embed]) (ggnn.py:98, never
  * materialised), DGL GlobalAttentionPooling(Linear(2D,1)) (ggnn.py:66-68,102) and the
  * output_layer MLP (ggnn.py:70-80,107).

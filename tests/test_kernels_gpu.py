@@ -337,6 +337,52 @@ def test_gru_step_image_entries(graphs, nodes):
                _p(ws_b), wsb_b, 0, st())
 
 
+@pytest.mark.parametrize("D,T", [(128, 3), (128, 8), (128, 18), (32, 4), (128, 1), (128, 0)])
+def test_ggnn_fused_drivers(D, T):
+    """ddfa_ggnn_fwd / ddfa_ggnn_bwd (the whole GatedGraphConv behind one call each) vs fp64 autograd of the oracle's
+    restatement of dgl.nn.GatedGraphConv, both engines; T = 18 takes the per-step weight-gradient path (> 16 slots)."""
+    g = synth.make_batch(9, 50, seed=T + D, variable=True)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    torch.manual_seed(D + T)
+    conv = O.GatedGraphConvRestated(D, D, T).double()
+    with torch.no_grad():
+        conv.linears[0].bias.uniform_(-0.2, 0.2)          # DGL initialises it to zero; exercise the bias path
+    x = (torch.randn(N, D, dtype=torch.float64) * 0.5).requires_grad_(True)
+    h_ref = conv(g, x)
+    dh_T = torch.randn(N, D, dtype=torch.float64)
+    (h_ref * dh_T).sum().backward()
+    par = dict(w_msg=conv.linears[0].weight, b_msg=conv.linears[0].bias, w_ih=conv.gru.weight_ih, w_hh=conv.gru.weight_hh,
+               b_ih=conv.gru.bias_ih, b_hh=conv.gru.bias_hh)
+    pd = {k: dev(v.detach().float()) for k, v in par.items()}
+    xd, dhd = dev(x.detach().float()), dev(dh_T.float())
+    L = lib()
+    for engine in engines_for(D):
+        for training in (1, 0):
+            wsb = L.call("ddfa_ggnn_workspace_bytes", N, D, T, engine, training)
+            assert wsb > 0
+            ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+            h_out = torch.full((N, D), float("nan"), device=DEV)
+            L.call("ddfa_ggnn_fwd", _p(dg.indptr), _p(dg.indices), _p(xd), N, D, T, _p(pd["w_msg"]), _p(pd["b_msg"]), _p(pd["w_ih"]),
+                   _p(pd["w_hh"]), _p(pd["b_ih"]), _p(pd["b_hh"]), _p(h_out), _p(ws), wsb, training, engine, st())
+            tol = (3e-5 if engine == ENGINE_SIMT else 2e-4) * max(1, T)
+            assert (h_out.cpu().double() - h_ref.detach()).abs().max() < tol, (engine, training)
+            if not training:
+                continue
+            dx = torch.full((N, D), float("nan"), device=DEV)
+            gr = {k: torch.zeros_like(v) for k, v in pd.items()}
+            L.call("ddfa_ggnn_bwd", _p(dg.indptr), _p(dg.indptr_t), _p(dg.indices_t), _p(xd), N, D, T, _p(pd["w_msg"]), _p(pd["b_msg"]),
+                   _p(pd["w_ih"]), _p(pd["w_hh"]), _p(dhd), _p(dx), _p(gr["w_msg"]), _p(gr["b_msg"]), _p(gr["w_ih"]), _p(gr["w_hh"]),
+                   _p(gr["b_ih"]), _p(gr["b_hh"]), _p(ws), wsb, engine, st())
+            checks = [(dx, x.grad)] + [(gr[k], par[k].grad if T > 0 else torch.zeros_like(par[k])) for k in par]
+            for got, ref in checks:
+                scale = max(1.0, float(ref.abs().max()))
+                assert (got.cpu().double() - ref).abs().max() < (1e-4 if engine == ENGINE_SIMT else 5e-4) * scale * max(1, T ** 0.5), engine
+    with pytest.raises(DdfaError, match="workspace"):
+        L.call("ddfa_ggnn_fwd", _p(dg.indptr), _p(dg.indices), _p(xd), N, D, max(T, 1), _p(pd["w_msg"]), _p(pd["b_msg"]), _p(pd["w_ih"]),
+               _p(pd["w_hh"]), _p(pd["b_ih"]), _p(pd["b_hh"]), _p(h_out), _p(ws), 16, 1, ENGINE_SIMT, st())
+
+
 @pytest.mark.parametrize("D,L", [(128, 3), (128, 1), (32, 2), (64, 0), (256, 2)])
 def test_readout_mlp_fwd_bwd(D, L):
     sizes = [1, 2, 300, 40, 5, 0, 17]          # includes an EMPTY graph (pooled = 0) and a 1-node graph
