@@ -293,3 +293,52 @@ def test_batched_weight_gradient_matches_per_step(monkeypatch):
         for n, gref in grads["default"].items():
             scale = max(1e-6, float(gref.abs().max()))
             assert float((grads[key][n] - gref).abs().max()) < 2e-4 * scale, (key, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_linevul_style_combined_head(engine):
+    """the encoder_mode output feeding a LineVul-style head (LineVul/linevul/linevul_model.py:6-24:
+    cat(<s> feature, flowgnn embedding) -> dense -> tanh -> out_proj(2), CrossEntropyLoss at :57-60) — loss and the
+    gradients reaching the GGNN parameters match the oracle driving the same head; a tiny HF RoBERTa encoder (random
+    weights, transformers is installed) provides the token features to show the two autograd graphs join."""
+    from transformers import RobertaConfig, RobertaModel
+    torch.manual_seed(0)
+    hidden = 64
+    cfg = RobertaConfig(vocab_size=120, hidden_size=hidden, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                        max_position_embeddings=40, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    roberta = RobertaModel(cfg, add_pooling_layer=False).to(DEV).eval()
+    b = synth.make_batch(6, 30, seed=9, variable=True, vuln_rate=0.3)
+    B = b.batch_size
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, encoder_mode=True).double()
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, encoder_mode=True, engine=engine)
+    m.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+    m.to(DEV)
+    assert m.out_dim == o.out_dim == 256
+    dense = torch.nn.Linear(hidden + m.out_dim, hidden).double()
+    out_proj = torch.nn.Linear(hidden, 2).double()
+    input_ids = torch.randint(3, 120, (B, 24), device=DEV)
+    labels = torch.tensor([0, 1, 0, 0, 1, 1])
+    feats = roberta(input_ids, attention_mask=input_ids.ne(1))[0]            # [B, 24, hidden] (linevul_model.py:63)
+
+    def head(cls_feature, flow, dense_, proj_):
+        x = torch.cat((cls_feature, flow), dim=1)
+        return proj_(torch.tanh(dense_(x)))
+
+    # oracle side (fp64, CPU)
+    cls_ref = feats[:, 0, :].detach().cpu().double()
+    loss_ref = torch.nn.functional.cross_entropy(head(cls_ref, o(b), dense, out_proj), labels)
+    loss_ref.backward()
+    # ours: GPU, fp32, the same head weights
+    dense32, proj32 = torch.nn.Linear(hidden + 256, hidden).to(DEV), torch.nn.Linear(hidden, 2).to(DEV)
+    dense32.load_state_dict({k: v.float() for k, v in dense.state_dict().items()})
+    proj32.load_state_dict({k: v.float() for k, v in out_proj.state_dict().items()})
+    flow = m(b, {})
+    assert flow.shape == (B, 256)
+    loss = torch.nn.functional.cross_entropy(head(feats[:, 0, :], flow, dense32, proj32), labels.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 2e-4
+    tol = 1e-4 if engine == "simt" else 1e-3
+    for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
+        assert (p.grad.cpu().double() - q.grad).abs().max() <= tol * max(1.0, float(q.grad.abs().max())) + 1e-7, name
+    assert roberta.embeddings.word_embeddings.weight.grad is not None       # the transformer side of the joint graph got its gradient
