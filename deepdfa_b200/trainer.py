@@ -60,6 +60,7 @@ class FusedTrainer:
         self.ws = E.Workspace(self.device)
         self._graphs = {}
         self._stream_slots = {}
+        self._copy_stream = None
         self._warm_shapes = set()
 
     # ------------------------------------------------------------------------------------
@@ -80,35 +81,81 @@ class FusedTrainer:
                self.eps, self.weight_decay, torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------------------------
-    def _step_streamed(self, g, global_batch: Optional[int]) -> torch.Tensor:
-        """Host batch + use_cuda_graph: the batch's arrays are copied into device buffers that are STATIC per shape
-        (num_nodes, num_edges, batch_size) and one captured CUDA graph per shape covers the whole step including the device
-        CSR build — a new batch of a known shape costs its H2D copies plus one graph launch.  First visit of a shape runs
-        eagerly (workspace growth), second captures."""
-        m = self.module
+    # ---- host batches through per-shape static buffers + captured graphs -------------------------------------------------
+    def _stream_slot(self, g, global_batch: Optional[int]):
         N, Eg, B = g.num_nodes(), g.num_edges(), g.batch_size
         gb = global_batch if global_batch is not None else B * self.world
         key = (N, Eg, B, gb)
         slot = self._stream_slots.get(key)
-        with torch.cuda.device(self.device):
-            if slot is None:
-                src, dst = g.edges()
-                dev = self.device
-                stat = {"src": torch.empty_like(src, device=dev), "dst": torch.empty_like(dst, device=dev),
-                        "bnn": torch.empty_like(g.batch_num_nodes(), device=dev),
-                        "ndata": {k: torch.empty_like(v, device=dev) for k, v in g.ndata.items()}}
-                slot = {"static": stat, "graph": None, "warm": False, "keep": None}
-                self._stream_slots[key] = slot
-            stat = slot["static"]
+        if slot is None:
             src, dst = g.edges()
-            stat["src"].copy_(src, non_blocking=True)
-            stat["dst"].copy_(dst, non_blocking=True)
-            stat["bnn"].copy_(g.batch_num_nodes(), non_blocking=True)
+            dev = self.device
+
+            def new_set():
+                return {"src": torch.empty_like(src, device=dev), "dst": torch.empty_like(dst, device=dev),
+                        "bnn": torch.empty_like(g.batch_num_nodes(), device=dev),
+                        "ndata": {k: torch.empty_like(v, device=dev) for k, v in g.ndata.items()},
+                        "graph": None, "keep": None, "free": None, "ready": None}
+            # two input-buffer sets: while the graph of one set runs, the next batch is copied into the other (prefetch)
+            slot = {"sets": [new_set(), new_set()], "next": 0, "staged": None, "warm": False, "N": N, "gb": gb}
+            self._stream_slots[key] = slot
+        return slot
+
+    def _stage(self, slot, g, stream):
+        """Copies the host batch ``g`` into the slot's next buffer set on ``stream``; returns the set index."""
+        i = slot["next"]
+        slot["next"] = 1 - i
+        st = slot["sets"][i]
+        with torch.cuda.stream(stream):
+            if st["free"] is not None:
+                stream.wait_event(st["free"])           # the graph that last read this set has finished
+            src, dst = g.edges()
+            st["src"].copy_(src, non_blocking=True)
+            st["dst"].copy_(dst, non_blocking=True)
+            st["bnn"].copy_(g.batch_num_nodes(), non_blocking=True)
             for k, v in g.ndata.items():
-                stat["ndata"][k].copy_(v, non_blocking=True)
+                st["ndata"][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            st["ready"] = ev
+        return i
+
+    def prefetch(self, batch, global_batch: Optional[int] = None) -> None:
+        """Starts the host->device copy of a (pinned) host batch on a side stream so that it overlaps the step that is running;
+        the following ``step(batch)`` with the SAME batch object picks the staged copy up.  No-op without ``use_cuda_graph`` or
+        for device batches."""
+        if not self.use_cuda_graph:
+            return
+        g = as_batched_cfg(batch)
+        if g.device.type != "cpu":
+            return
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            slot = self._stream_slot(g, global_batch)
+            slot["staged"] = (id(batch), self._stage(slot, g, self._copy_stream))
+
+    def _step_streamed(self, batch, g, global_batch: Optional[int]) -> torch.Tensor:
+        """Host batch + use_cuda_graph: the batch's arrays are copied into device buffers that are STATIC per shape
+        (num_nodes, num_edges, batch_size) and one captured CUDA graph per buffer set covers the whole step including the
+        device CSR build — a new batch of a known shape costs its H2D copies (overlappable: ``prefetch``) plus one graph
+        launch.  The first visit of a shape runs eagerly (workspace growth), the next two capture."""
+        m = self.module
+        with torch.cuda.device(self.device):
+            slot = self._stream_slot(g, global_batch)
+            N, gb = slot["N"], slot["gb"]
+            main = torch.cuda.current_stream()
+            staged = slot["staged"]
+            slot["staged"] = None
+            if staged is not None and staged[0] == id(batch):
+                i = staged[1]
+                main.wait_event(slot["sets"][i]["ready"])
+            else:
+                i = self._stage(slot, g, main)
+            st = slot["sets"][i]
 
             def enqueue():
-                gs = BatchedCFG(stat["src"], stat["dst"], stat["bnn"], dict(stat["ndata"]), num_nodes=N)   # no cached device CSR
+                gs = BatchedCFG(st["src"], st["dst"], st["bnn"], dict(st["ndata"]), num_nodes=N)   # no cached device CSR
                 g_, dg, idx = m._prepare(gs)
                 vuln = gs.ndata["_VULN"]
                 if vuln.dtype != torch.int32:
@@ -117,16 +164,19 @@ class FusedTrainer:
                 return (gs, dg, idx, vuln)
 
             if not slot["warm"]:
-                slot["keep"] = enqueue()
+                st["keep"] = enqueue()
                 slot["warm"] = True
             else:
-                if slot["graph"] is None:
+                if st["graph"] is None:
                     torch.cuda.synchronize(self.device)
                     cg = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(cg):
-                        slot["keep"] = enqueue()          # tensors allocated during capture live in the graph's pool
-                    slot["graph"] = cg
-                slot["graph"].replay()
+                        st["keep"] = enqueue()            # tensors allocated during capture live in the graph's pool
+                    st["graph"] = cg
+                st["graph"].replay()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            st["free"] = ev
         return self.loss_slot
 
     def step_ids(self, arena, ids, global_batch: Optional[int] = None) -> torch.Tensor:
@@ -181,7 +231,7 @@ class FusedTrainer:
         if self.use_cuda_graph:
             gb_ = as_batched_cfg(batch)
             if gb_.device.type == "cpu":
-                return self._step_streamed(gb_, global_batch)
+                return self._step_streamed(batch, gb_, global_batch)
         g, dg, idx = m._prepare(batch)
         vuln = g.ndata["_VULN"]
         if vuln.device != self.device or vuln.dtype != torch.int32:

@@ -253,20 +253,24 @@ def test_fused_trainer_cuda_graph_paths_match_eager(engine):
     per-shape input buffers + one graph that includes the device CSR build.  Both must reproduce the eager loss curve."""
     batches = [synth.make_batch(16, 40, seed=70 + i, vuln_rate=0.3) for i in range(3)]        # same shape, different content
     losses = {}
-    for mode in ("eager", "graph_host", "graph_device"):
+    for mode in ("eager", "graph_host", "graph_host_prefetch", "graph_device"):
         torch.manual_seed(1)
         m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 4, 2, concat_all_absdf=True, engine=engine).to(DEV)
         tr = D.FusedTrainer(m, use_cuda_graph=(mode != "eager"))
         bs = [b.to(DEV) for b in batches] if mode == "graph_device" else batches
         cur = []
         for step in range(9):                       # every batch is visited eagerly (warm-up), at capture, and on replay
-            cur.append(float(tr.step(bs[step % 3])))
+            loss_t = tr.step(bs[step % 3])
+            if mode == "graph_host_prefetch":       # H2D of the next batch overlaps this step
+                tr.prefetch(bs[(step + 1) % 3])
+            cur.append(float(loss_t))
         losses[mode] = cur
-        if mode == "graph_host":
-            assert len(tr._stream_slots) == 1 and next(iter(tr._stream_slots.values()))["graph"] is not None
+        if mode in ("graph_host", "graph_host_prefetch"):
+            slot = next(iter(tr._stream_slots.values()))
+            assert len(tr._stream_slots) == 1 and all(st["graph"] is not None for st in slot["sets"])
         if mode == "graph_device":
             assert len(tr._graphs) == 3
-    for mode in ("graph_host", "graph_device"):
+    for mode in ("graph_host", "graph_host_prefetch", "graph_device"):
         for a, b in zip(losses["eager"], losses[mode]):
             assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (mode, losses["eager"], losses[mode])
     assert losses["eager"][0] != losses["eager"][3]      # the parameters did move
