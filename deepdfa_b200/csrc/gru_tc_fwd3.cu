@@ -23,6 +23,8 @@
 //     no cross-warp barrier anywhere in the epilogue; global accesses are 32-byte row segments (full sectors).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ddfa {
@@ -222,6 +224,15 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     pdl_wait();        // everything above (barriers, TMEM, the packed weights) is independent of the previous kernel
 
     const size_t plane = (size_t)N * kD;
+    // image addressing of this thread's (even) column pair: chunk = [variant c & 1][k-block], swizzle by row & 7
+    const int kcol = (gcol & ~1) & 63;
+    const uint32_t img_chunk_off = (uint32_t)(((c & 1) * 2 + (gcol >> 6)) * kChunkBytes);
+    uint32_t img_lane_off[2];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int r7 = g + 4 * jj;
+      img_lane_off[jj] = (uint32_t)(r7 * 128 + ((((kcol >> 3) ^ r7) & 7) << 4) + (kcol & 7) * 2);
+    }
     float *X = reinterpret_cast<float *>(smem + kOffX) + (size_t)(warp - 2) * kXFloats;   // warp-private exchange tile
     const bool tr = (warp == 2 && lane == 0);
     // h and the in-degree of the 8 nodes this thread finishes per tile (two 16-node chunks x nodes g, g+4, g+8, g+12) are
@@ -269,48 +280,59 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has read its part of the accumulator buffer
       if (tr) trace_stamp(tron, k, 9);
+      // Addresses: every output of this thread is (per-tile base) + (compile-time offset): node = node_w + 16 ch + g + 4 j, so
+      // row-major planes move by (16 ch + 4 j) rows, and inside the image the 8-row group index is 4 e + 2 ch + (j >> 1) while
+      // row & 7 = g + 4 (j & 1) selects one of two swizzle offsets computed once per kernel (img_lane_off).
+      float *const ho = h_out + (node_w + g) * kD + gcol;
+      float *const gp0 = gates ? gates + (node_w + g) * kD + gcol : nullptr;
+      uint8_t *const ip = h_out_img ? h_out_img + (size_t)tile * kImageTileBytes + img_chunk_off + (size_t)e * 4096 : nullptr;
+      auto finish_tile = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;      // every node of the tile exists: no bounds predicates
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        // thread (g, c) holds pre-activation g of column c for nodes 0..15 of the chunk -> X[g][node][c]
+        for (int ch = 0; ch < 2; ++ch) {
+          // thread (g, c) holds pre-activation g of column c for nodes 0..15 of the chunk -> X[g][node][c]
 #pragma unroll
-        for (int i = 0; i < 16; ++i) X[g * kXGateLd + i * 8 + c] = ch == 0 ? v0[i] : v1[i];
-        __syncwarp();
+          for (int i = 0; i < 16; ++i) X[g * kXGateLd + i * 8 + c] = ch == 0 ? v0[i] : v1[i];
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = g + 4 * j;                                     // node of the chunk finished by this thread
-          const int64_t node = node_w + ch * 16 + i;
-          const bool valid = node < N;
-          const float dg = deg[ch * 4 + j];
-          const float gin = X[0 * kXGateLd + i * 8 + c] + fmaf(dg, d_gin, b_gin);
-          const float r = fast_sigmoid(X[1 * kXGateLd + i * 8 + c] + fmaf(dg, d_r, b_r));
-          const float z = fast_sigmoid(X[2 * kXGateLd + i * 8 + c] + fmaf(dg, d_z, b_z));
-          const float ghn = X[3 * kXGateLd + i * 8 + c] + b_ghn;
-          const float n = fast_tanh(fmaf(r, ghn, gin));
-          const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
-          if (valid) {
-            h_out[node * kD + gcol] = hnew;
-            if (gates) {
-              float *g0 = gates + node * kD + gcol;
-              g0[0] = r;
-              g0[plane] = z;
-              g0[2 * plane] = n;
-              g0[3 * plane] = ghn;
+          for (int j = 0; j < 4; ++j) {
+            const int i = g + 4 * j;                                     // node of the chunk finished by this thread
+            const bool valid = kFull || (node_w + ch * 16 + i < N);
+            const float dg = deg[ch * 4 + j];
+            const float gin = X[0 * kXGateLd + i * 8 + c] + fmaf(dg, d_gin, b_gin);
+            const float r = fast_sigmoid(X[1 * kXGateLd + i * 8 + c] + fmaf(dg, d_r, b_r));
+            const float z = fast_sigmoid(X[2 * kXGateLd + i * 8 + c] + fmaf(dg, d_z, b_z));
+            const float ghn = X[3 * kXGateLd + i * 8 + c] + b_ghn;
+            const float n = fast_tanh(fmaf(r, ghn, gin));
+            const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
+            constexpr int kRow = 0;   // (placeholder so the offsets below read as one expression)
+            const int row_off = (ch * 16 + 4 * j + kRow) * kD;
+            if (valid) {
+              ho[row_off] = hnew;
+              if (gp0) {
+                gp0[row_off] = r;
+                gp0[plane + row_off] = z;
+                gp0[2 * plane + row_off] = n;
+                gp0[3 * plane + row_off] = ghn;
+              }
+            }
+            if (ip) {
+              // columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
+              const float other = __shfl_xor_sync(0xffffffffu, hnew, 1);
+              const float x0 = (c & 1) ? other : hnew, x1 = (c & 1) ? hnew : other;
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(x0, h0, l0);
+              split_bf16(x1, h1, l1);
+              const uint32_t word = (c & 1) ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
+                                            : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
+              *reinterpret_cast<uint32_t *>(ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1]) = word;
             }
           }
-          if (h_out_img) {
-            // columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
-            const float other = __shfl_xor_sync(0xffffffffu, hnew, 1);
-            const float x0 = (c & 1) ? other : hnew, x1 = (c & 1) ? hnew : other;
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(x0, h0, l0);
-            split_bf16(x1, h1, l1);
-            const uint32_t word = (c & 1) ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
-                                          : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
-            *reinterpret_cast<uint32_t *>(h_out_img + image_offset(node, gcol & ~1, c & 1)) = word;
-          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
+      };
+      if ((int64_t)(tile + 1) * kTileM <= N) finish_tile(std::true_type{});
+      else finish_tile(std::false_type{});
       if (tr) trace_stamp(tron, k, 10);
     }
   }
