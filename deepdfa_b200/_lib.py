@@ -7,6 +7,7 @@ binding raises.  Every call checks the status code and raises ``DdfaError`` carr
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -84,7 +85,7 @@ _NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "d
 
 class _Lib:
     def __init__(self):
-        path = _build.LIB
+        path = Path(os.environ["DDFA_LIB_PATH"]) if os.environ.get("DDFA_LIB_PATH") else _build.LIB   # override: A/B of two builds
         if not path.exists():
             raise DdfaError(
                 f"{path} is missing: build it with `python -m deepdfa_b200.build` (or __graft_entry__.build()). "

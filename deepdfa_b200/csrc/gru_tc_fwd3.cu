@@ -23,8 +23,6 @@
 //     no cross-warp barrier anywhere in the epilogue; global accesses are 32-byte row segments (full sectors).
 #include <stdlib.h>
 
-#include <type_traits>
-
 #include "tc_common.cuh"
 
 namespace ddfa {
@@ -286,8 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       float *const ho = h_out + (node_w + g) * kD + gcol;
       float *const gp0 = gates ? gates + (node_w + g) * kD + gcol : nullptr;
       uint8_t *const ip = h_out_img ? h_out_img + (size_t)tile * kImageTileBytes + img_chunk_off + (size_t)e * 4096 : nullptr;
-      auto finish_tile = [&](auto full_tag) {
-        constexpr bool kFull = decltype(full_tag)::value;      // every node of the tile exists: no bounds predicates
+      // (one code path: a separate predicate-free body for full tiles was faster in isolation, 48 vs 53 us, but pushed the kernel
+      // past the instruction cache — 43 KB of SASS — and lost in the real step, 54.7 vs 53.5 us: profiles/r02j)
+      {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           // thread (g, c) holds pre-activation g of column c for nodes 0..15 of the chunk -> X[g][node][c]
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = g + 4 * j;                                     // node of the chunk finished by this thread
-            const bool valid = kFull || (node_w + ch * 16 + i < N);
+            const bool valid = node_w + ch * 16 + i < N;
             const float dg = deg[ch * 4 + j];
             const float gin = X[0 * kXGateLd + i * 8 + c] + fmaf(dg, d_gin, b_gin);
             const float r = fast_sigmoid(X[1 * kXGateLd + i * 8 + c] + fmaf(dg, d_r, b_r));
@@ -305,8 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             const float ghn = X[3 * kXGateLd + i * 8 + c] + b_ghn;
             const float n = fast_tanh(fmaf(r, ghn, gin));
             const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
-            constexpr int kRow = 0;   // (placeholder so the offsets below read as one expression)
-            const int row_off = (ch * 16 + 4 * j + kRow) * kD;
+            const int row_off = (ch * 16 + 4 * j) * kD;
             if (valid) {
               ho[row_off] = hnew;
               if (gp0) {
@@ -330,9 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
           }
           __syncwarp();
         }
-      };
-      if ((int64_t)(tile + 1) * kTileM <= N) finish_tile(std::true_type{});
-      else finish_tile(std::false_type{});
+      }
       if (tr) trace_stamp(tron, k, 10);
     }
   }
