@@ -21,6 +21,14 @@ bool chain_take_break() {
   return b;
 }
 
+int l2_hints() {
+  static const int mask = [] {
+    const char *e = getenv("DDFA_L2_HINTS");
+    return e ? atoi(e) : 23;     // measured best on whole-step A/Bs (profiles/r02l-m): 1 + 2 + 4 + 16
+  }();
+  return mask;
+}
+
 int pdl_mask() {
   static const int mask = [] {
     const char *e = getenv("DDFA_PDL");

@@ -125,6 +125,45 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
 // L2-only load (ld.global.cg): for kernels of the PDL chain, whose L1 may hold lines from before the predecessor's writes
 __device__ __forceinline__ float4 ldg_cg_f4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint) -----------------------------------------------------------
+// The train step moves ~5.9 GB through a 126 MB L2 per step; what a kernel writes for a consumer many kernels later (the saved
+// gates) should not push out what the next kernel needs, and what dies after the next kernel (ds, dh, dh'z) should stay.
+// kind: 0 = evict_normal, 1 = evict_first, 2 = evict_last.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_f32_hint(float *p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_f4_hint(float *p, const float4 &v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ldg_cg_f4_hint(const float *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_cg_f32_hint(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_u32_hint(void *p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_u2_hint(void *p, const uint2 &v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+// abi.cu: $DDFA_L2_HINTS bit mask, default 23.  1: saved gates written evict_first; 2: saved activations read evict_first in the
+// backward pass; 4: ds / dh / dh'z written evict_last; 8: their last reads evict_first; 16: h' and its image written evict_last;
+// 32 / 64: operand tiles of the weight-gradient / dgrad kernels copied evict_first.  Whole-step A/B (one box, profiles/r02l-m):
+// 4 alone +1.0 %, 7 +1.3 %, 23 +1.9 % over 0; 8, 32, 64 neutral or negative.
+int l2_hints();
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -38,17 +38,18 @@ struct GbRow {
 };
 __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_out, const float *__restrict__ h,
                                         const float *__restrict__ gates, const int32_t *__restrict__ indptr,
-                                        const int32_t *__restrict__ indptr_t, size_t plane, int64_t node, int col, bool ok) {
+                                        const int32_t *__restrict__ indptr_t, size_t plane, int64_t node, int col, bool ok,
+                                        uint64_t pol_saved, uint64_t pol_dh) {
   x.tb = x.te = 0;
   if (ok) {
     if (indptr_t) { x.tb = __ldcg(indptr_t + node); x.te = __ldcg(indptr_t + node + 1); }
     const size_t off = (size_t)node * kD + col;
-    x.d = ldg_cg_f4(dh_out + off);
-    x.hv = ldg_cg_f4(h + off);
-    x.rr = ldg_cg_f4(gates + off);
-    x.zz = ldg_cg_f4(gates + plane + off);
-    x.nn = ldg_cg_f4(gates + 2 * plane + off);
-    x.gh = ldg_cg_f4(gates + 3 * plane + off);
+    x.d = ldg_cg_f4_hint(dh_out + off, pol_dh);
+    x.hv = ldg_cg_f4_hint(h + off, pol_saved);                 // saved activations: last use
+    x.rr = ldg_cg_f4_hint(gates + off, pol_saved);
+    x.zz = ldg_cg_f4_hint(gates + plane + off, pol_saved);
+    x.nn = ldg_cg_f4_hint(gates + 2 * plane + off, pol_saved);
+    x.gh = ldg_cg_f4_hint(gates + 3 * plane + off, pol_saved);
     x.deg = (float)(__ldcg(indptr + node + 1) - __ldcg(indptr + node));
   }
 }
@@ -60,12 +61,13 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
                                                                           int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
                                                                           uint8_t *__restrict__ h_img, float *__restrict__ dhz,
                                                                           float *__restrict__ db_fold,
-                                                                          float *__restrict__ db_ih, float *__restrict__ db_hh) {
+                                                                          float *__restrict__ db_ih, float *__restrict__ db_hh, int hints) {
   __shared__ float red[kGbWarps][7 * kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = lane * 4;
   pdl_launch_dependents();
   pdl_wait();
+  const uint64_t pol_saved = l2_policy((hints & 2) ? 1 : 0), pol_tmp = l2_policy((hints & 4) ? 2 : 0), pol_dh = l2_policy((hints & 8) ? 1 : 0);
   const size_t plane = (size_t)N * kD;
   float4 sum[7];
 #pragma unroll
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr, hv = qr;
     if (ok) {
       hv = x.hv;
-      *reinterpret_cast<float4 *>(dhz + (size_t)node * kD + col) = make_float4(x.d.x * x.zz.x, x.d.y * x.zz.y, x.d.z * x.zz.z, x.d.w * x.zz.w);
+      st_f4_hint(dhz + (size_t)node * kD + col, make_float4(x.d.x * x.zz.x, x.d.y * x.zz.y, x.d.z * x.zz.z, x.d.w * x.zz.w), pol_tmp);
 #define BWDQ(f)                                                      \
   {                                                                  \
     const float dz_ = x.d.f * (x.hv.f - x.nn.f);                     \
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
     const int64_t node2 = node + stride;
     GbRow a, b;
     const bool ok_a = node < N, ok_b = node2 < N;
-    gb_load(a, dh_out, h, gates, indptr, indptr_t, plane, node, col, ok_a);
-    gb_load(b, dh_out, h, gates, indptr, indptr_t, plane, node2, col, ok_b);
+    gb_load(a, dh_out, h, gates, indptr, indptr_t, plane, node, col, ok_a, pol_saved, pol_dh);
+    gb_load(b, dh_out, h, gates, indptr, indptr_t, plane, node2, col, ok_b, pol_saved, pol_dh);
     if (indptr_t) {
       // dh' += sum over the transposed-graph neighbours of ds_in: first up to 4 neighbour ids of both rows, then their
       // rows, all loads of a phase in flight together; longer lists finish in a plain loop (deterministic order)
@@ -204,7 +206,7 @@ __global__ void dgrad3_pack_kernel(const float *__restrict__ w_fold, const float
 __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__restrict__ q_img, size_t img_stride,
                                                              const float *__restrict__ dhz,
                                                              const uint32_t *__restrict__ packed3, int32_t N,
-                                                             float *__restrict__ ds, float *__restrict__ dh) {
+                                                             float *__restrict__ ds, float *__restrict__ dh, int hints) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
     // ===== producer: per tile the three q matrices of this role, one 64 KB copy each =====
     if (elect_one()) {
       pdl_wait();      // the q images come from gate_bwd_image_kernel, the previous kernel of the chain
+      const uint64_t pol_q = l2_policy((hints & 64) ? 1 : 0);
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = num_tiles - 1 - (group + k * num_groups);   // back to front: the q tiles written last are still in L2
@@ -253,8 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
           if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
           if (g == 0) trace_stamp(tron, k, 1);
           mbar_arrive_expect_tx(a_full(stage), kD3StageBytes);
-          bulk_g2s(sbase + stage * kD3StageBytes, q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes, kD3StageBytes,
-                   a_full(stage));
+          bulk_g2s_hint(sbase + stage * kD3StageBytes, q_img + (size_t)m * img_stride + (size_t)tile * kImageTileBytes, kD3StageBytes,
+                        a_full(stage), pol_q);
           if (g == 2) trace_stamp(tron, k, 2);
         }
       }
@@ -327,6 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
     pdl_wait();
 
     float *out = role == 0 ? ds : dh;
+    const uint64_t pol_tmp = l2_policy((hints & 4) ? 2 : 0);       // ds / dh die after the next kernel has read them
+    const uint64_t pol_dhz = l2_policy((hints & 8) ? 1 : 0);       // last read of dh'z
     const bool tr = (warp == 2 && lane == 0);
     for (int k = 0; k < my_tiles; ++k) {
       const int tile = num_tiles - 1 - (group + k * num_groups);
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
         float dv[32];
         if (role == 1) {       // dh = acc + (dh' * z) : fetch the elementwise term (written by gate_bwd) while the MMAs run
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dv[i] = (i < rows_valid) ? __ldcg(dhz + (node0 + i) * kD + col) : 0.f;
+          for (int i = 0; i < 32; ++i) dv[i] = (i < rows_valid) ? ldg_cg_f32_hint(dhz + (node0 + i) * kD + col, pol_dhz) : 0.f;
         }
         mbar_wait(acc_full(half), k & 1);
         tc_fence_after();
@@ -362,10 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const uint8_t *__re
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (i < rows_valid) o[(size_t)i * kD] = v0[i];
+          if (i < rows_valid) st_f32_hint(o + (size_t)i * kD, v0[i], pol_tmp);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (16 + i < rows_valid) o[(size_t)(16 + i) * kD] = v1[i];
+          if (16 + i < rows_valid) st_f32_hint(o + (size_t)(16 + i) * kD, v1[i], pol_tmp);
       }
       if (tr) trace_stamp(tron, k, 10);
     }
@@ -412,7 +417,7 @@ struct WgBatch {
 };
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__restrict__ q_img, size_t img_stride, size_t step_stride,
                                                             const __grid_constant__ WgBatch batch,
-                                                            int32_t N, float *__restrict__ partial, int first) {
+                                                            int32_t N, float *__restrict__ partial, int first, int hints) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -446,6 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
 
   if (warp == 0) {
     if (elect_one()) {
+      const uint64_t pol_wg = l2_policy((hints & 32) ? 1 : 0);     // every operand of the batched launch is read once
       int uses[kWgSlots] = {0, 0, 0};
       for (int i = 0; i < my_tiles; ++i) {
         const int idx = (int)blockIdx.x + i * (int)gridDim.x;
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const uint8_t *__res
             src = q_img + (size_t)t * step_stride + (size_t)pl * img_stride;
           }
           mbar_arrive_expect_tx(full_bar(slot), kWgSlotBytes);
-          bulk_g2s(sbase + slot * kWgSlotBytes, src + (size_t)tile * kImageTileBytes, kWgSlotBytes, full_bar(slot));
+          bulk_g2s_hint(sbase + slot * kWgSlotBytes, src + (size_t)tile * kImageTileBytes, kWgSlotBytes, full_bar(slot), pol_wg);
         }
       }
     }
@@ -654,7 +660,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
   DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h, gates, indptr, ds_in,
-                         ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh));
+                         ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh,
+                         l2_hints()));
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
@@ -663,7 +670,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     int groups = kNumSMs / 2;
     if (groups > tiles) groups = tiles;
     DDFA_CUDA(launch_chain(8, tc2b::dgrad3_kernel, dim3(groups * 2), dim3(tc2b::kThreads), tc2b::kD3SmemAlloc, stream, q_img, img, dhz,
-                           reinterpret_cast<const uint32_t *>(packed), N, ds, dh));
+                           reinterpret_cast<const uint32_t *>(packed), N, ds, dh, l2_hints()));
     DDFA_CHECK_LAUNCH("tc2b::dgrad3_kernel");
   }
   if (wgrad_mode >= 16) return DDFA_OK;       // q images kept; the batched weight-gradient launch follows the last step
@@ -672,7 +679,7 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
   one.s_img[0] = static_cast<const uint8_t *>(s_img);
   one.h_img[0] = h_img;
   one.steps = 1;
-  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 0, one, N, partial, wgrad_mode == 2 ? 0 : 1);
+  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 0, one, N, partial, wgrad_mode == 2 ? 0 : 1, 0);
   DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
   if (wgrad_mode == 0) return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, stream);
   return DDFA_OK;
@@ -705,7 +712,7 @@ int gru_tc2_bwd_wgrad_batched(const void *const *s_imgs, const void *const *h_im
   }
   b.steps = steps;
   DDFA_CUDA(cudaFuncSetAttribute(tc2b::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kWgSmemAlloc));
-  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 4 * img, b, N, partial, 1);
+  tc2b::wgrad_kernel<<<dim3(kWgCtas, 2), tc2b::kThreads, tc2b::kWgSmemAlloc, stream>>>(q_img, img, 4 * img, b, N, partial, 1, l2_hints());
   DDFA_CHECK_LAUNCH("tc2b::wgrad_kernel");
   return gru_tc2_bwd_finish(N, dw_fold, dw_hh, workspace, workspace_bytes, stream);
 }

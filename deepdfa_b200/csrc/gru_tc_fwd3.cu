@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
                                                                const float *__restrict__ h, const int32_t *__restrict__ indptr,
                                                                const uint8_t *__restrict__ packed, int32_t N,
                                                                float *__restrict__ h_out, uint8_t *__restrict__ h_out_img,
-                                                               float *__restrict__ gates) {
+                                                               float *__restrict__ gates, int hints) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();        // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     pdl_wait();        // everything above (barriers, TMEM, the packed weights) is independent of the previous kernel
 
     const size_t plane = (size_t)N * kD;
+    const uint64_t pol_gates = l2_policy((hints & 1) ? 1 : 0);      // the saved gates are next read in the backward pass
+    const uint64_t pol_next = l2_policy((hints & 16) ? 2 : 0);      // h' and its image feed the next two kernels
     // image addressing of this thread's (even) column pair: chunk = [variant c & 1][k-block], swizzle by row & 7
     const int kcol = (gcol & ~1) & 63;
     const uint32_t img_chunk_off = (uint32_t)(((c & 1) * 2 + (gcol >> 6)) * kChunkBytes);
@@ -306,12 +308,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
             const int row_off = (ch * 16 + 4 * j) * kD;
             if (valid) {
-              ho[row_off] = hnew;
+              st_f32_hint(ho + row_off, hnew, pol_next);
               if (gp0) {
-                gp0[row_off] = r;
-                gp0[plane + row_off] = z;
-                gp0[2 * plane + row_off] = n;
-                gp0[3 * plane + row_off] = ghn;
+                st_f32_hint(gp0 + row_off, r, pol_gates);
+                st_f32_hint(gp0 + plane + row_off, z, pol_gates);
+                st_f32_hint(gp0 + 2 * plane + row_off, n, pol_gates);
+                st_f32_hint(gp0 + 3 * plane + row_off, ghn, pol_gates);
               }
             }
             if (ip) {
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
               split_bf16(x1, h1, l1);
               const uint32_t word = (c & 1) ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
                                             : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
-              *reinterpret_cast<uint32_t *>(ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1]) = word;
+              st_u32_hint(ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1], word, pol_next);
             }
           }
           __syncwarp();
@@ -361,7 +363,7 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
   if (groups > tiles) groups = tiles;
   DDFA_CUDA(launch_chain(2, tc3::gru_fwd3_kernel, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc, stream,
                          static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,
-                         static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates));
+                         static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates, l2_hints()));
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
   return DDFA_OK;
 }
