@@ -420,8 +420,8 @@ def run_ours(args):
     tc = args.engine == "tcgen05"
     fwd_line = hbm_line("gru_fwd3_kernel (GRU step forward, tcgen05: weights in TMEM, bf16x3)" if tc else "GRU step forward (simt engine)",
                         9 * P, gru_f_ms, gru_f_n, share["ddfa_gru_step_fwd"],
-                        # dram__bytes_read.sum + dram__bytes_write.sum of the training-mode launch, profiles/r01s_ncu_fwd3_bwd.txt
-                        traffic=(59736576 + 64268800) if tc else None,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of the training-mode launch, profiles/r02o_ncu_tc_kernels.txt
+                        traffic=(59709696 + 43025408) if tc else None,
                         tensor_tflops=3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 if tc else None,
                         tensor_frac=(3 * flops_fwd_step / (gru_f_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if tc else None)
     wg_spans = prof.spans["wgrad_batched"]
