@@ -282,6 +282,67 @@ class FlowGNNGGNNModule(nn.Module):
                 out = out.unsqueeze(0)
             return loss, torch.sigmoid(out), labels.int()
 
+    # ---- profiling / timing records in the reference's schema --------------------------------------
+    def analytic_counts(self, num_nodes: int, batch_size: int):
+        """(flops, macs, params) of one forward pass in the REFERENCE formulation (what its DeepSpeed FlopsProfiler run,
+        base_module.py:76-77,259-272, reports for the module tree): per node and propagation step D*D MACs for
+        GatedGraphConv.linears[0] plus 6*D*D for the GRUCell; the gate Linear(2D, 1) per node; the MLP head per graph.
+        Embedding lookups and elementwise work are not counted; flops = 2 * macs."""
+        D, T = self._D, self.hparams.n_steps
+        macs = num_nodes * T * 7 * D * D + num_nodes * 2 * D
+        if not self.hparams.encoder_mode:
+            dims = [2 * D] * self._num_layers + [1] if self._num_layers > 0 else []
+            macs += batch_size * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        params = sum(p.numel() for p in self.parameters())
+        return 2 * macs, macs, params
+
+    @staticmethod
+    def _count_str(x: float) -> str:
+        """'<number> <unit>' with the units scripts/report_profiling.py parses (G / M / K)."""
+        for unit, scale in (("G", 1e9), ("M", 1e6), ("K", 1e3)):
+            if x >= scale:
+                return f"{x / scale:.2f} {unit}"
+        return f"{x:.2f} K" if x == 0 else f"{x / 1e3:.4f} K"
+
+    def test_step(self, batch_data, batch_idx=0):
+        """base_module.py:238-321 without the torchmetrics bookkeeping: returns (loss, sigmoid(out), int labels).  With
+        ``time=True`` (``--model.time True``, scripts/run_profiling.sh) every step after the third appends
+        ``{"step", "batch_size", "runtime"}`` (CUDA-event milliseconds around ``forward``) to ``timedata.jsonl``; with
+        ``profile=True`` it appends ``{"step", "flops", "params", "macs", "batch_size"}`` to ``profiledata.jsonl`` — the files
+        ``scripts/report_profiling.py`` reads.  The counts are analytic (``analytic_counts``), not instrumented."""
+        import json
+        import os
+        batch, extrafeats = batch_data
+        do_profile = bool(self.hparams.profile) and batch_idx > 2
+        do_time = bool(self.hparams.time) and batch_idx > 2
+        with torch.no_grad():
+            labels = self.get_label(batch)
+            if do_time:
+                start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                start.record()
+            out = self.forward(batch, extrafeats)
+            if do_time:
+                end.record()
+            record, filename = None, None
+            if do_profile:
+                g = as_batched_cfg(batch)
+                flops, macs, params = self.analytic_counts(g.num_nodes(), g.batch_size)
+                record = {"step": batch_idx, "flops": self._count_str(flops), "params": self._count_str(params),
+                          "macs": self._count_str(macs), "batch_size": int(labels.numel())}
+                filename = "profiledata.jsonl"
+            elif do_time:
+                torch.cuda.synchronize()
+                record = {"step": batch_idx, "batch_size": int(labels.numel()), "runtime": start.elapsed_time(end)}
+                filename = "timedata.jsonl"
+            if filename is not None:
+                with open(os.path.join(getattr(self, "profile_output_dir", "."), filename), "a") as f:
+                    f.write(json.dumps(record))
+                    f.write("\n")
+            loss, labels = self.loss_and_labels(batch, out)
+            if out.dim() == 0:
+                out = out.unsqueeze(0)
+            return loss, torch.sigmoid(out), labels.int()
+
     def configure_optimizers(self, lr=1e-3, weight_decay=1e-2):
         """config_default.yaml:43-47 (torch.optim.Adam, coupled L2).  The fused B200 optimizer is
         ``deepdfa_b200.trainer.FusedTrainer``; this returns the stock optimizer for drop-in scripts."""

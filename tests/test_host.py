@@ -134,3 +134,17 @@ def test_param_list_order_matches_parampack():
     assert pk.w_msg is m.ggnn.linears[0].weight and pk.w_hh is m.ggnn.gru.weight_hh and pk.b_gate is m.pooling.gate_nn.bias
     assert pk.mlp_w[2] is m.output_layer[4].weight and pk.mlp_b[0] is m.output_layer[0].bias
     assert [t.shape for t in pk.flat_list()] == [p.shape for p in m.param_list()]
+
+
+def test_analytic_counts_and_count_strings():
+    """the MAC model behind profiledata.jsonl and the '<number> <unit>' strings report_profiling.py parses."""
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 8, 2, concat_all_absdf=True)
+    flops, macs, params = m.analytic_counts(38400, 256)
+    Dw = 128
+    assert macs == 38400 * 8 * 7 * Dw * Dw + 38400 * 2 * Dw + 256 * (2 * Dw * 2 * Dw + 2 * Dw)
+    assert flops == 2 * macs and params == sum(p.numel() for p in m.parameters()) == 375938 - (2 * Dw * 2 * Dw + 2 * Dw)  # L = 2 head
+    for x, want in ((70.46e9, "70.46 G"), (3.5e6, "3.50 M"), (1234.0, "1.23 K")):
+        s = m._count_str(x)
+        assert s == want and len(s.split(" ")) == 2 and s.split(" ")[1] in ("G", "M", "K")
+    enc = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, encoder_mode=True)
+    assert enc.analytic_counts(100, 4)[1] == 100 * 5 * 7 * Dw * Dw + 100 * 2 * Dw

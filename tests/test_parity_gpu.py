@@ -346,3 +346,28 @@ def test_linevul_style_combined_head(engine):
     for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
         assert (p.grad.cpu().double() - q.grad).abs().max() <= tol * max(1.0, float(q.grad.abs().max())) + 1e-7, name
     assert roberta.embeddings.word_embeddings.weight.grad is not None       # the transformer side of the joint graph got its gradient
+
+
+@pytest.mark.gpu
+def test_test_step_writes_reference_profiling_records(tmp_path):
+    """test_step with time / profile emits timedata.jsonl / profiledata.jsonl rows in the schema
+    scripts/report_profiling.py reads (base_module.py:238-291), only for steps after the third."""
+    import json
+    b = synth.make_batch(12, 40, seed=4, vuln_rate=0.3).to(DEV)
+    for flag, fname, keys in (("time", "timedata.jsonl", {"step", "batch_size", "runtime"}),
+                              ("profile", "profiledata.jsonl", {"step", "flops", "params", "macs", "batch_size"})):
+        m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 4, 2, concat_all_absdf=True, **{flag: True}).to(DEV)
+        m.profile_output_dir = str(tmp_path)
+        outs = [m.test_step((b, {}), i) for i in range(6)]
+        rows = [json.loads(l) for l in open(tmp_path / fname)]
+        assert [r["step"] for r in rows] == [3, 4, 5] and all(set(r) == keys and r["batch_size"] == 12 for r in rows)
+        if flag == "time":
+            assert all(0.0 < r["runtime"] < 1e3 for r in rows)
+        else:
+            flops, macs, params = m.analytic_counts(b.num_nodes(), 12)
+            for r in rows:      # the parsing rule of report_profiling.py
+                count, unit = r["flops"].split(" ")
+                assert abs(float(count) * {"G": 1e9, "M": 1e6, "K": 1e3}[unit] - flops) <= 0.005 * {"G": 1e9, "M": 1e6, "K": 1e3}[unit]
+        loss, prob, labels = outs[-1]
+        ref_loss, ref_prob, ref_labels = m.validation_step((b, {}), 0)
+        assert torch.equal(prob, ref_prob) and torch.equal(labels, ref_labels) and float(loss) == float(ref_loss)
