@@ -28,23 +28,26 @@ __global__ void csr_count_kernel(const IdxT *__restrict__ src, const IdxT *__res
 }
 
 // One CTA scans one array in place: a[1..n] (counts) -> inclusive prefix sums; a[0] stays 0.
-// blockIdx.x selects which of the two arrays.  1024 threads x 4 items per pass with a carry.
+// blockIdx.x selects which of the two arrays.  1024 threads x 16 items per pass (all 16 loads in flight) with a carry:
+// 38 401 counts = 3 passes (4 items per pass took 10 passes of three barriers and a memory round trip each, ~20 us).
 __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t *a0, int32_t *a1, int32_t n) {
   int32_t *a = blockIdx.x == 0 ? a0 : a1;
   if (a == nullptr) return;
   a += 1;
+  constexpr int kItems = 16;
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int32_t base = 0; base < n; base += 4096) {
-    int32_t i0 = base + tid * 4;
-    int32_t v[4];
+  for (int32_t base = 0; base < n; base += 1024 * kItems) {
+    const int32_t i0 = base + tid * kItems;
+    int32_t v[kItems];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (i0 + j < n) ? a[i0 + j] : 0;
-    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
-    int32_t x = v[3];
+    for (int j = 0; j < kItems; ++j) v[j] = (i0 + j < n) ? a[i0 + j] : 0;
+#pragma unroll
+    for (int j = 1; j < kItems; ++j) v[j] += v[j - 1];
+    int32_t x = v[kItems - 1];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -62,10 +65,10 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t *a0, int32_t *a1
       warp_tot[lane] = t;
     }
     __syncthreads();
-    int32_t carry = carry_s;
-    int32_t excl = x - v[3] + (wid > 0 ? warp_tot[wid - 1] : 0) + carry;
+    const int32_t carry = carry_s;
+    const int32_t excl = x - v[kItems - 1] + (wid > 0 ? warp_tot[wid - 1] : 0) + carry;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < kItems; ++j)
       if (i0 + j < n) a[i0 + j] = v[j] + excl;
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_tot[31];
