@@ -26,7 +26,8 @@ _ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat 
 
 class FusedTrainer:
     def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False):
+                 weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False, max_graph_shapes: int = 8,
+                 max_resident_graphs: int = 64):
         if module.device.type != "cuda":
             raise _lib.DdfaError("FusedTrainer needs the module on a CUDA device (no CPU fallback)")
         self.module = module
@@ -35,6 +36,10 @@ class FusedTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_cuda_graph = use_cuda_graph
+        # a captured graph bakes in the batch SHAPE (and, for resident batches, the batch object): cap how many are kept so a
+        # stream of ever-new shapes (un-bucketed real data) degrades to eager launches instead of growing without bound
+        self.max_graph_shapes = max_graph_shapes
+        self.max_resident_graphs = max_resident_graphs
         plist = module.param_list()
         offs, total = [], 0
         for p in plist:
@@ -88,6 +93,8 @@ class FusedTrainer:
         key = (N, Eg, B, gb)
         slot = self._stream_slots.get(key)
         if slot is None:
+            if len(self._stream_slots) >= self.max_graph_shapes:
+                return None
             src, dst = g.edges()
             dev = self.device
 
@@ -133,7 +140,8 @@ class FusedTrainer:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
             slot = self._stream_slot(g, global_batch)
-            slot["staged"] = (id(batch), self._stage(slot, g, self._copy_stream))
+            if slot is not None:
+                slot["staged"] = (id(batch), self._stage(slot, g, self._copy_stream))
 
     def _step_streamed(self, batch, g, global_batch: Optional[int]) -> torch.Tensor:
         """Host batch + use_cuda_graph: the batch's arrays are copied into device buffers that are STATIC per shape
@@ -143,6 +151,8 @@ class FusedTrainer:
         m = self.module
         with torch.cuda.device(self.device):
             slot = self._stream_slot(g, global_batch)
+            if slot is None:          # more shapes than max_graph_shapes: same kernels, launched eagerly
+                return self._step_eager(batch, global_batch)
             N, gb = slot["N"], slot["gb"]
             main = torch.cuda.current_stream()
             staged = slot["staged"]
@@ -199,8 +209,10 @@ class FusedTrainer:
         slot = self._stream_slots.get(key)
         with torch.cuda.device(self.device):
             if slot is None:
+                if len(self._stream_slots) >= self.max_graph_shapes:
+                    return self._step_eager(arena.batch(ids), global_batch)
                 slot = {"out": arena.alloc_outputs(B, N, Eg), "stage": torch.empty(B, dtype=torch.int32).pin_memory(),
-                        "graph": None, "warm": False, "keep": None}
+                        "graph": None, "warm": False, "keep": None, "arena": arena}     # the arena stays alive with its graph
                 self._stream_slots[key] = slot
             slot["stage"].copy_(torch.from_numpy(ids_np.astype(np.int32)))
             slot["out"]["ids"].copy_(slot["stage"], non_blocking=True)
@@ -232,6 +244,11 @@ class FusedTrainer:
             gb_ = as_batched_cfg(batch)
             if gb_.device.type == "cpu":
                 return self._step_streamed(batch, gb_, global_batch)
+        return self._step_eager(batch, global_batch)
+
+    def _step_eager(self, batch, global_batch: Optional[int] = None) -> torch.Tensor:
+        """Device-resident batch objects (one captured graph per object when ``use_cuda_graph``), or plain eager launches."""
+        m = self.module
         g, dg, idx = m._prepare(batch)
         vuln = g.ndata["_VULN"]
         if vuln.device != self.device or vuln.dtype != torch.int32:
@@ -245,7 +262,9 @@ class FusedTrainer:
             global_batch = dg.batch_size * self.world
         with torch.cuda.device(self.device):
             shape_key = (dg.num_nodes, dg.num_edges, dg.batch_size)
-            if not self.use_cuda_graph or shape_key not in self._warm_shapes:
+            capturable = self.use_cuda_graph and as_batched_cfg(batch).device.type == "cuda" and \
+                (id(g) in self._graphs or len(self._graphs) < self.max_resident_graphs)
+            if not capturable or shape_key not in self._warm_shapes:
                 # eager step; also the warm-up (workspace growth, lazy CUDA module init) before any capture
                 self._enqueue(g, dg, idx, vuln, global_batch)
                 self._warm_shapes.add(shape_key)

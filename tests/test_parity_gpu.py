@@ -371,3 +371,21 @@ def test_test_step_writes_reference_profiling_records(tmp_path):
         loss, prob, labels = outs[-1]
         ref_loss, ref_prob, ref_labels = m.validation_step((b, {}), 0)
         assert torch.equal(prob, ref_prob) and torch.equal(labels, ref_labels) and float(loss) == float(ref_loss)
+
+
+@pytest.mark.gpu
+def test_graph_caps_degrade_to_eager():
+    """A stream of ever-new batch shapes must not accumulate captured graphs: beyond max_graph_shapes the same kernels run
+    eagerly and the results stay those of the eager trainer."""
+    batches = [synth.make_batch(8, 20 + 3 * i, seed=90 + i, vuln_rate=0.3) for i in range(5)]     # 5 different shapes
+    order = [0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 0, 1]
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(2)
+        m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 3, 2, concat_all_absdf=True, engine="tcgen05").to(DEV)
+        tr = D.FusedTrainer(m, use_cuda_graph=(mode == "graph"), max_graph_shapes=2)
+        losses[mode] = [float(tr.step(batches[i])) for i in order]
+        if mode == "graph":
+            assert len(tr._stream_slots) == 2
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a))
