@@ -77,7 +77,6 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uin
                "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -180,61 +179,6 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl
   split4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
   ph = make_uint4(h0.x, h0.y, h1.x, h1.y);
   pl = make_uint4(l0.x, l0.y, l1.x, l1.y);
-}
-
-// ---- coalesced epilogue I/O -------------------------------------------------------------------------------------
-// tcgen05.ld hands an accumulator tile to the epilogue as "thread = row": each lane owns 16 consecutive fp32 columns of
-// its row.  Writing that to a row-major [N,128] matrix directly makes every 16-byte store its own memory transaction
-// (r01i ncu: 32 sectors per request, LSU-throttled).  Instead two warps that hold the two 16-column halves of the same
-// 32 rows (same TMEM lane quarter) share a padded shared-memory plane [32 rows][36 floats]: both write their half
-// (conflict-free: 8 consecutive rows per quarter-warp, row stride 36 = 4 * odd), meet at a 64-thread named barrier, and
-// each then moves 16 of the rows with lane = (row, 16-byte piece) so one instruction covers 4 full 128-byte rows.
-constexpr int kStageLd = 36;                       // floats per staged row (32 + pad)
-constexpr int kStagePlaneFloats = 32 * kStageLd;   // 1152 floats = 4608 B
-
-__device__ __forceinline__ void pair_sync(int bar_id) { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
-
-// this thread's 16 values -> columns [16*half, 16*half+16) of row `lane`
-__device__ __forceinline__ void stage_write16(float *plane, int lane, int half, const float (&v)[16]) {
-  float *p = plane + lane * kStageLd + half * 16;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4 *>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void stage_read16(const float *plane, int lane, int half, float (&v)[16]) {
-  const float *p = plane + lane * kStageLd + half * 16;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = *reinterpret_cast<const float4 *>(p + 4 * i);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-// rows [16*half, 16*half+16) of the plane -> global; gbase points at (first row of the 32-row block, first of the 32 columns),
-// ld = row stride in floats, rows_valid = number of rows of the block that exist (row < rows_valid is stored)
-__device__ __forceinline__ void stage_store_rows(const float *plane, float *gbase, int ld, int lane, int half, int rows_valid) {
-  const int piece = lane & 7;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = half * 16 + j * 4 + (lane >> 3);
-    if (row < rows_valid)
-      *reinterpret_cast<float4 *>(gbase + (size_t)row * ld + piece * 4) = *reinterpret_cast<const float4 *>(plane + row * kStageLd + piece * 4);
-  }
-}
-// global rows -> registers (issue early), then registers -> plane (rows past rows_valid read as zero)
-__device__ __forceinline__ void stage_fetch_rows(const float *gbase, int ld, int lane, int half, int rows_valid, float4 (&r)[4]) {
-  const int piece = lane & 7;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = half * 16 + j * 4 + (lane >> 3);
-    r[j] = (row < rows_valid) ? ldg_nc_f4(gbase + (size_t)row * ld + piece * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-__device__ __forceinline__ void stage_put_rows(float *plane, int lane, int half, const float4 (&r)[4]) {
-  const int piece = lane & 7;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = half * 16 + j * 4 + (lane >> 3);
-    *reinterpret_cast<float4 *>(plane + row * kStageLd + piece * 4) = r[j];
-  }
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
