@@ -13,6 +13,14 @@ PARITY STATUS: **partially pinned**.
     is executed here by the *real* torch modules — that part is the reference's own
     dependency running in this container, and ``tests/test_oracle.py`` additionally pins the
     explicit-formula restatement (``gru_cell_formula``) against ``torch.nn.GRUCell``.
+  * The reference's OWN code for this path — ``FlowGNNGGNNModule.__init__ / forward`` (ggnn.py:23-109) and
+    ``BaseModule.__init__ / get_label / training_step`` (base_module.py:27-95, 171-199) — has been EXECUTED in the build
+    container with stand-ins for its bookkeeping imports (Lightning, torchmetrics, deepspeed, nni) and with the two DGL
+    operators bound to the restatements below (``tests/golden/make_reference_ctrlflow_golden.py``); its outputs, labels,
+    training loss, gradients and state_dict are committed (``tests/golden/reference_ctrlflow_golden.pt``) and
+    ``tests/test_oracle.py::test_oracle_matches_reference_control_flow`` pins this oracle against them.  So parameter
+    construction and naming, embedding order, concatenations, pooling / MLP placement, ``squeeze``, ``encoder_mode``, the
+    graph-label rule and the loss are pinned to the reference's executing code.
   * The two **DGL** ops are restated from the pinned upstream version (``dgl<1.1.3``,
     ``environment.yml:10``; ``dgl-cu113==0.9.0`` in ``LineVul/requirements.txt``), whose
     source is NOT vendored in ``/root/reference`` and is not installed:

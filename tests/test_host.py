@@ -148,3 +148,17 @@ def test_analytic_counts_and_count_strings():
         assert s == want and len(s.split(" ")) == 2 and s.split(" ")[1] in ("G", "M", "K")
     enc = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, encoder_mode=True)
     assert enc.analytic_counts(100, 4)[1] == 100 * 5 * 7 * Dw * Dw + 100 * 2 * Dw
+
+
+def test_module_state_dict_matches_the_reference_classes():
+    """Key names and shapes of FlowGNNGGNNModule.state_dict() vs the state_dict the REAL reference classes produced
+    (tests/golden/reference_ctrlflow_golden.pt, written by make_reference_ctrlflow_golden.py), incl. loss_fn.pos_weight."""
+    import os
+    data = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_ctrlflow_golden.pt"), weights_only=False)
+    for case in data["cases"]:
+        m = D.FlowGNNGGNNModule(**case["ctor"])
+        ours, ref = m.state_dict(), case["state_dict"]
+        assert sorted(ours.keys()) == sorted(ref.keys()), case["name"]
+        for k in ref:
+            assert ours[k].shape == ref[k].shape, (case["name"], k)
+        m.load_state_dict(ref)                      # a reference checkpoint loads as is

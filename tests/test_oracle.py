@@ -190,3 +190,40 @@ def test_against_real_dgl_if_available():
     pool = O.GlobalAttentionPoolingRestated(torch.nn.Linear(16, 1))
     pool.load_state_dict(pool_ref.state_dict())
     assert torch.allclose(pool_ref(dg, feat), pool(g, feat), atol=1e-6)
+
+
+def test_oracle_matches_reference_control_flow():
+    """The fixture was produced by the reference's OWN ggnn.py / base_module.py code (tests/golden/make_reference_ctrlflow_golden.py:
+    real FlowGNNGGNNModule + BaseModule with stand-ins for the bookkeeping imports; the two DGL operators bound to the oracle's
+    restatements).  It pins the oracle's — and therefore the module's — restatement of that code: parameter names and shapes,
+    embedding order, concatenations, pooling / MLP placement, squeeze, encoder_mode, graph labels, BCE(pos_weight), gradients."""
+    import os
+    from deepdfa_b200.batched_graph import BatchedCFG
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_ctrlflow_golden.pt")
+    data = torch.load(path, weights_only=False)
+    assert len(data["cases"]) == 4
+    for case in data["cases"]:
+        gd = case["graph"]
+        g = BatchedCFG(gd["src"], gd["dst"], gd["batch_num_nodes"], gd["ndata"])
+        o = O.OracleFlowGNNGGNN(**case["ctor"])
+        # same parameter / buffer names (the reference lists loss_fn.pos_weight first: BaseModule.__init__ runs first; order is
+        # irrelevant to load_state_dict)
+        assert sorted(o.state_dict().keys()) == sorted(case["state_dict"].keys()), case["name"]
+        for k, v in o.state_dict().items():
+            assert v.shape == case["state_dict"][k].shape, (case["name"], k)
+        o.load_state_dict(case["state_dict"])
+        o.eval()
+        with torch.no_grad():
+            out = o(g)
+        assert out.shape == case["out"].shape and torch.allclose(out, case["out"], atol=1e-6, rtol=1e-5), case["name"]
+        assert torch.equal(o.get_label(g), case["label"]), case["name"]
+        if "train_loss" in case:
+            o.train()
+            o.zero_grad()
+            loss, _ = o.training_loss(g)
+            loss.backward()
+            assert torch.allclose(loss, case["train_loss"], atol=1e-6, rtol=1e-5), case["name"]
+            grads = {k: p.grad for k, p in o.named_parameters() if p.grad is not None}
+            assert set(grads) == set(case["grads"]), case["name"]
+            for k, gref in case["grads"].items():
+                assert torch.allclose(grads[k], gref, atol=1e-6, rtol=1e-4), (case["name"], k)

@@ -389,3 +389,34 @@ def test_graph_caps_degrade_to_eager():
             assert len(tr._stream_slots) == 2
     for a, b in zip(losses["eager"], losses["graph"]):
         assert abs(a - b) < 1e-5 * max(1.0, abs(a))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["simt"])
+def test_module_matches_reference_control_flow_goldens(engine):
+    """The CUDA module against outputs of the reference's own ggnn.py / base_module.py code (fixture written by
+    tests/golden/make_reference_ctrlflow_golden.py; small widths, so the SIMT engine): logits / pooled embedding, graph labels,
+    training loss and parameter gradients."""
+    import os
+    from deepdfa_b200.batched_graph import BatchedCFG
+    data = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_ctrlflow_golden.pt"), weights_only=False)
+    for case in data["cases"]:
+        gd = case["graph"]
+        g = BatchedCFG(gd["src"], gd["dst"], gd["batch_num_nodes"], gd["ndata"])
+        m = D.FlowGNNGGNNModule(**case["ctor"], engine=engine)
+        m.load_state_dict(case["state_dict"])
+        m.to(DEV)
+        with torch.no_grad():
+            out = m(g, {})
+        assert out.shape == case["out"].shape, case["name"]
+        assert (out.cpu() - case["out"]).abs().max() < 1e-4, case["name"]
+        assert torch.equal(m.get_label(g).cpu(), case["label"]), case["name"]
+        if "train_loss" in case:
+            m.zero_grad(set_to_none=True)
+            loss = m.training_step((g, {}), 0)
+            loss.backward()
+            assert abs(float(loss) - float(case["train_loss"])) < 1e-4, case["name"]
+            for k, p in m.named_parameters():
+                if k in case["grads"]:
+                    ref = case["grads"][k]
+                    assert (p.grad.cpu() - ref).abs().max() < 2e-4 * max(1.0, float(ref.abs().max())), (case["name"], k)
