@@ -127,6 +127,9 @@ def main():
                                           encoder_mode=True), graphs=dict(sizes=[12, 7, 33], seed=13, vuln_rate=0.2, input_dim=64)),
         dict(name="one_graph_squeeze", ctor=dict(feat=feat, input_dim=64, hidden_dim=8, n_steps=2, num_output_layers=1, concat_all_absdf=True),
              graphs=dict(sizes=[21], seed=14, vuln_rate=0.4, input_dim=64)),
+        # hidden width 128 (what the tcgen05 engine runs): forward only, to keep the fixture small
+        dict(name="concat_D128_T8_L1_fwd", ctor=dict(feat=feat, input_dim=64, hidden_dim=32, n_steps=8, num_output_layers=1, concat_all_absdf=True),
+             graphs=dict(sizes=[150, 3, 77, 140, 1, 129], seed=15, vuln_rate=0.3, input_dim=64), forward_only=True),
     ]
     for i, spec in enumerate(specs):
         torch.manual_seed(100 + i)
@@ -144,7 +147,7 @@ def main():
             case["label"] = ref.get_label(g).clone()
         # (a one-graph batch cannot take the reference's training step: `.squeeze()` makes the logit 0-d and BCEWithLogitsLoss
         #  rejects it against the [1] label — reference behaviour, base_module.py:183)
-        if not spec["ctor"].get("encoder_mode") and g.batch_size > 1:
+        if not spec["ctor"].get("encoder_mode") and g.batch_size > 1 and not spec.get("forward_only"):
             ref.train()
             ref.zero_grad()
             loss = ref.training_step((g, {}), 0)

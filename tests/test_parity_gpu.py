@@ -392,7 +392,7 @@ def test_graph_caps_degrade_to_eager():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", ["simt"])
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
 def test_module_matches_reference_control_flow_goldens(engine):
     """The CUDA module against outputs of the reference's own ggnn.py / base_module.py code (fixture written by
     tests/golden/make_reference_ctrlflow_golden.py; small widths, so the SIMT engine): logits / pooled embedding, graph labels,
@@ -403,13 +403,16 @@ def test_module_matches_reference_control_flow_goldens(engine):
     for case in data["cases"]:
         gd = case["graph"]
         g = BatchedCFG(gd["src"], gd["dst"], gd["batch_num_nodes"], gd["ndata"])
+        if engine == "tcgen05" and case["ctor"]["hidden_dim"] * (4 if case["ctor"].get("concat_all_absdf") else 1) != 128:
+            continue                                                      # the tensor-core engine is the width-128 one
         m = D.FlowGNNGGNNModule(**case["ctor"], engine=engine)
         m.load_state_dict(case["state_dict"])
         m.to(DEV)
         with torch.no_grad():
             out = m(g, {})
         assert out.shape == case["out"].shape, case["name"]
-        assert (out.cpu() - case["out"]).abs().max() < 1e-4, case["name"]
+        assert (out.cpu() - case["out"]).abs().max() < (1e-4 if engine == "simt" else 1e-3), case["name"]   # north-star bound 1e-3
+        assert torch.equal((out.cpu() > 0), (case["out"] > 0)), case["name"]                                # identical decisions
         assert torch.equal(m.get_label(g).cpu(), case["label"]), case["name"]
         if "train_loss" in case:
             m.zero_grad(set_to_none=True)
