@@ -17,7 +17,10 @@ What the reference does, and where:
   as many non-vulnerable ones, sampled without replacement from a persistent ``RandomState``).
 
 This module restates exactly that with pandas (the ``.bin`` container itself is DGL's and is not read: it holds nothing that
-``edges.csv`` does not).  The dataset is not shipped with the reference, so the tests build small files in the same schema.
+``edges.csv`` does not).  The dataset is not shipped with the reference, so the tests build small files in the same schema —
+and the reference's OWN ``get_nodes_df`` / ``get_graphs`` / ``get_epoch_indices`` were run on those files in the build container
+(``tests/golden/make_reference_io_golden.py``); ``tests/test_bigvul_io.py::test_reader_matches_reference_loaders`` holds the
+reader to their output.  Only the three DGL calls of ``dbize_graphs.py`` stay a restatement.
 """
 from __future__ import annotations
 

@@ -7,39 +7,7 @@ import torch
 import deepdfa_b200 as D
 from deepdfa_b200 import bigvul_io as IO
 
-FEAT = "_ABS_DATAFLOW_datatype_all_limitall_1000_limitsubkeys_1000"
-TAIL = "_all_limitall_1000_limitsubkeys_1000"
-
-
-def _write_dataset(root, seed=0, n_graphs=7):
-    """Files as dbize.py:104-105 / dbize_absdf.py write them: an unnamed index column first, rows grouped by graph."""
-    rng = np.random.default_rng(seed)
-    folder = root / "bigvul"
-    folder.mkdir(parents=True)
-    node_rows, edge_rows, truth = [], [], {}
-    for gid in rng.permutation(np.arange(100, 100 + 3 * n_graphs, 3))[:n_graphs]:        # non-contiguous, unsorted graph ids
-        n = int(rng.integers(2, 12))
-        node_ids = rng.permutation(np.arange(1000, 1000 + 4 * n, 4))[:n]                 # Joern node ids: arbitrary
-        # CFG-like edges in dgl ids; make sure the highest id appears (dgl.graph infers N = max id + 1)
-        src = rng.integers(0, n, size=2 * n); dst = rng.integers(0, n, size=2 * n)
-        src[0], dst[0] = n - 1, 0
-        vul = rng.random(n) < 0.3
-        feats = {k: rng.integers(0, 1002, n) for k in D.batched_graph.ABS_DATAFLOW_SUBKEYS}
-        feats["main"] = feats["datatype"]        # FEAT is the datatype file itself (config_default.yaml: feat = ..._datatype_all_...)
-        for i in range(n):
-            node_rows.append(dict(graph_id=gid, node_id=int(node_ids[i]), dgl_id=i, vuln=int(vul[i]), code=f"x = {i};", _label="CALL"))
-        for s_, d_ in zip(src, dst):
-            edge_rows.append(dict(graph_id=gid, innode=int(s_), outnode=int(d_)))
-        truth[int(gid)] = dict(n=n, src=src, dst=dst, vul=vul.astype(np.int32), feats=feats, node_ids=node_ids)
-    nodes = pd.DataFrame(node_rows); edges = pd.DataFrame(edge_rows)
-    nodes.to_csv(folder / "nodes.csv"); edges.to_csv(folder / "edges.csv")
-    def feat_file(stem, key):
-        rows = [dict(graph_id=g, node_id=int(t["node_ids"][i]), **{stem: int(t["feats"][key][i])}) for g, t in truth.items() for i in range(t["n"])]
-        df = pd.DataFrame(rows).sample(frac=1.0, random_state=1)      # feature files need not be in node order: it is a merge
-        df.to_csv(folder / f"nodes_feat_{stem}_fixed.csv")
-    for sub in D.batched_graph.ABS_DATAFLOW_SUBKEYS:
-        feat_file(f"_ABS_DATAFLOW_{sub}{TAIL}", sub)
-    return truth
+from bigvul_fixture import FEAT, write_dataset as _write_dataset
 
 
 def test_reader_reproduces_dbize_graphs_and_graphmogrifier(tmp_path):
@@ -95,3 +63,32 @@ def test_epoch_indices_follow_dclass(undersample, oversample):
     if undersample == "v1.0" and oversample is None:
         idx = IO.epoch_indices(df, undersample, None, np.random.RandomState(1))
         assert (df.loc[idx].vul == 1).sum() == (df.vul == 1).sum() == (df.loc[idx].vul == 0).sum()
+
+
+def test_reader_matches_reference_loaders(tmp_path):
+    """tests/golden/reference_io_golden.pt holds what the reference's OWN graphmogrifier.get_nodes_df / get_graphs and
+    BigVulDataset.get_epoch_indices produced on these files (make_reference_io_golden.py); the reader must reproduce it."""
+    import os
+    golden = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_io_golden.pt"), weights_only=False)
+    _write_dataset(tmp_path, seed=0, n_graphs=7)
+    nodes = IO.read_nodes(tmp_path, "bigvul", FEAT, concat_all_absdf=True)
+    assert list(nodes.columns) == golden["nodes_columns"]
+    for col, ref in golden["nodes_records"].items():
+        assert nodes[col].tolist() == ref, col
+    graphs = IO.load_graphs(tmp_path, "bigvul", FEAT, concat_all_absdf=True)
+    assert list(graphs) == golden["graph_ids"]                      # groupby order = ascending graph id
+    for gid in golden["graph_ids"]:
+        assert graphs[gid].num_nodes() == golden["num_nodes"][gid]
+        assert sorted(graphs[gid].ndata) == sorted(golden["ndata"][gid])
+        for name, ref in golden["ndata"][gid].items():
+            got = graphs[gid].ndata[name]
+            assert got.dtype == ref.dtype and torch.equal(got, ref), (gid, name)
+    rng0 = np.random.default_rng(3)
+    df = pd.DataFrame({"id": np.arange(500) * 7, "vul": (rng0.random(500) < 0.12).astype(int)})
+    for key, ref_epochs in golden["epoch_indices"].items():
+        us, os_ = key.split("|")
+        us = None if us == "None" else (us if us.startswith("v") else float(us))
+        os_ = None if os_ == "None" else float(os_)
+        rng = np.random.RandomState(0)
+        for ref in ref_epochs:
+            assert IO.epoch_indices(df, us, os_, rng).tolist() == ref, key
