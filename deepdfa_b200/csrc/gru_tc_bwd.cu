@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
 // =================================================================================================
 // (2) dgrad, weight-in-TMEM orientation ("dgrad3")
 // =================================================================================================
-// The in-kernel timeline of dgrad_kernel (profiles/r01l_trace_dgrad.log) shows it is bound by the operand feed: 96 KB of
+// The in-kernel timeline of its predecessor (weight slices in shared memory; profiles/r01l_trace_dgrad.log) showed the operand feed as the bound: 96 KB of
 // shared memory hold the weight slice, only 2 x 32 KB are left for activations, and with ~1 us per copy in flight that
 // is ~35 GB/s per SM while every CTA has to pull 256 KB per tile (each q tile is read by four slice CTAs).
 // Here the GEMM is transposed:  D^T[col, node] = W^T[col, K] * Q[node, K]^T
