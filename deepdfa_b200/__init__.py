@@ -13,7 +13,8 @@ from .batched_graph import BatchedCFG, add_self_loop, as_batched_cfg, batch, col
 from .module import FlowGNNGGNNModule, allfeats  # noqa: F401
 from .trainer import FusedTrainer  # noqa: F401
 from .arena import ArenaBatch, GraphArena  # noqa: F401
+from ._lib import DdfaError  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = ["FlowGNNGGNNModule", "FusedTrainer", "GraphArena", "ArenaBatch", "BatchedCFG", "batch", "unbatch", "graph", "add_self_loop",
-           "collate", "as_batched_cfg", "synth", "allfeats"]
+           "collate", "as_batched_cfg", "synth", "allfeats", "DdfaError"]

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "ddfa_device_supported": (_int, []),
     "ddfa_launch_count": (C.c_longlong, []),
     "ddfa_engine_available": (_int, [_int]),
+    "ddfa_tuning_set": (_int, [_int, _int]),
+    "ddfa_tuning_get": (_int, [_int]),
     "ddfa_debug_set": (_int, [_int, _int]),
     "ddfa_debug_read": (_int, [_int, _vp, _sz]),
     "ddfa_build_csr_workspace_bytes": (_sz, [_i64, _i32]),
@@ -74,11 +76,14 @@ _SIGNATURES = {
     "ddfa_mlp_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ddfa_readout_bwd": (_int, [_vp] * 5 + [_i32, _i32] + [_vp] * 8 + [_vp]),
     "ddfa_graph_label_bce": (_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "ddfa_graph_label_bce_valid": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "ddfa_adam_flat": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "ddfa_sgemm": (_int, [_int, _int, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _i32, _f32, _vp, _i32, _i32, _vp]),
 }
 
-_NO_STATUS = {"ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
+TUNE_L2_HINTS, TUNE_PDL_MASK, TUNE_GATHER_VARIANT = 0, 1, 2
+
+_NO_STATUS = {"ddfa_tuning_get", "ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
               "ddfa_build_csr_workspace_bytes", "ddfa_arena_batch_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
               "ddfa_act_image_bytes", "ddfa_ggnn_workspace_bytes"}
 
@@ -106,6 +111,10 @@ class _Lib:
         abi = self._dll.ddfa_abi_version()
         if abi != 1:
             raise DdfaError(f"ABI version mismatch: library {abi}, binding 1")
+        # A/B scripts select launch configurations through the environment of the PYTHON layer; the library itself reads none
+        for env, key in (("DDFA_L2_HINTS", TUNE_L2_HINTS), ("DDFA_PDL", TUNE_PDL_MASK), ("DDFA_GATHER_VARIANT", TUNE_GATHER_VARIANT)):
+            if os.environ.get(env) is not None:
+                self._dll.ddfa_tuning_set(key, int(os.environ[env]))
 
     def last_error(self) -> str:
         msg = self._dll.ddfa_last_error()

@@ -174,9 +174,19 @@ def as_batched_cfg(g) -> BatchedCFG:
     if isinstance(g, BatchedCFG):
         return g
     if all(hasattr(g, a) for a in ("edges", "batch_num_nodes", "ndata")):
-        src, dst = g.edges()
+        # memoised on the source object: a step calls this 2-3 times (forward, loss/labels) and the wrapper carries the device
+        # CSR cache — a fresh wrapper per call would rebuild the CSR each time
+        cached = getattr(g, "_ddfa_b200_cfg", None)
         nd = {k: g.ndata[k] for k in g.ndata.keys()}
+        if cached is not None and cached.ndata.keys() == nd.keys() and \
+                all(cached.ndata[k].data_ptr() == v.data_ptr() and cached.ndata[k].shape == v.shape for k, v in nd.items()):
+            return cached      # same node data storage: the graph object was not re-populated since
+        src, dst = g.edges()
         out = BatchedCFG(src, dst, g.batch_num_nodes(), nd)
+        try:
+            g._ddfa_b200_cfg = out
+        except Exception:      # objects that refuse new attributes: no memoisation
+            pass
         return out
     raise TypeError(f"expected a BatchedCFG or DGLGraph-like object, got {type(g)!r}")
 

@@ -21,21 +21,16 @@ bool chain_take_break() {
   return b;
 }
 
-int l2_hints() {
-  static const int mask = [] {
-    const char *e = getenv("DDFA_L2_HINTS");
-    return e ? atoi(e) : 23;     // measured best on whole-step A/Bs (profiles/r02l-m): 1 + 2 + 4 + 16
-  }();
-  return mask;
-}
-
-int pdl_mask() {
-  static const int mask = [] {
-    const char *e = getenv("DDFA_PDL");
-    return e ? atoi(e) : 15;
-  }();
-  return mask;
-}
+// Tuning knobs (ddfa_tuning_set / ddfa_tuning_get): compiled-in defaults, no environment reads inside the library; the A/B
+// scripts set them through the C ABI.  They select between equivalent launch configurations of the same kernels.
+static std::atomic<int> g_tuning[DDFA_TUNE__COUNT] = {
+    {23},   // DDFA_TUNE_L2_HINTS: measured best on whole-step A/Bs (profiles/r02l-m): 1 + 2 + 4 + 16
+    {15},   // DDFA_TUNE_PDL_MASK: all four chain kernels
+    {9},    // DDFA_TUNE_GATHER_VARIANT: r01b sweep — 2 rows/pass, 4 loads in flight, 128-thread CTAs
+};
+int l2_hints() { return g_tuning[DDFA_TUNE_L2_HINTS].load(std::memory_order_relaxed); }
+int pdl_mask() { return g_tuning[DDFA_TUNE_PDL_MASK].load(std::memory_order_relaxed); }
+int gather_variant() { return g_tuning[DDFA_TUNE_GATHER_VARIANT].load(std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -55,6 +50,16 @@ int ddfa_engine_available(int engine) {
   if (engine == DDFA_ENGINE_SIMT) return 1;
   if (engine == DDFA_ENGINE_TCGEN05) return 1;
   return 0;
+}
+
+int ddfa_tuning_set(int key, int value) {
+  DDFA_REQUIRE(key >= 0 && key < DDFA_TUNE__COUNT, "ddfa_tuning_set: unknown key %d", key);
+  ddfa::g_tuning[key].store(value, std::memory_order_relaxed);
+  return DDFA_OK;
+}
+int ddfa_tuning_get(int key) {
+  if (key < 0 || key >= DDFA_TUNE__COUNT) return -1;
+  return ddfa::g_tuning[key].load(std::memory_order_relaxed);
 }
 
 int ddfa_debug_set(int key, int value) {

@@ -58,7 +58,8 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 // Both instructions are no-ops in a normal launch.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-int pdl_mask();       // abi.cu: $DDFA_PDL — unset: all chain kernels; "0": none; else a bit mask (1 gather_image, 2 gru_fwd3, 4 gate_bwd, 8 dgrad3)
+int pdl_mask();       // abi.cu: DDFA_TUNE_PDL_MASK — bit mask of the kernels launched programmatically (1 gather_image, 2 gru_fwd3, 4 gate_bwd, 8 dgrad3)
+int gather_variant(); // abi.cu: DDFA_TUNE_GATHER_VARIANT
 void chain_break();   // abi.cu: the next launch_chain() on this thread is a normal (fully serialised) launch
 bool chain_take_break();
 
@@ -85,7 +86,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // sgemm.cu — SIMT fp32 GEMM, C = alpha*op(A)op(B) + beta*C (row-major)
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
           float beta, float *C, int ldc, int split_k, cudaStream_t stream);
-// gru_tc_fwd.cu — tcgen05 engine, forward (D == 128; weight-stationary, activation images)
+// gru_tc_fwd3.cu — tcgen05 engine, forward (D == 128): activation images
 size_t act_image_bytes(int64_t n);
 int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream);
 // gru_tc_fwd3.cu — forward, weights-in-TMEM orientation
@@ -158,7 +159,7 @@ __device__ __forceinline__ void st_u32_hint(void *p, uint32_t v, uint64_t pol) {
 __device__ __forceinline__ void st_u2_hint(void *p, const uint2 &v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
-// abi.cu: $DDFA_L2_HINTS bit mask, default 23.  1: saved gates written evict_first; 2: saved activations read evict_first in the
+// abi.cu: DDFA_TUNE_L2_HINTS bit mask, default 23.  1: saved gates written evict_first; 2: saved activations read evict_first in the
 // backward pass; 4: ds / dh / dh'z written evict_last; 8: their last reads evict_first; 16: h' and its image written evict_last;
 // 32 / 64: operand tiles of the weight-gradient / dgrad kernels copied evict_first.  Whole-step A/B (one box, profiles/r02l-m):
 // 4 alone +1.0 %, 7 +1.3 %, 23 +1.9 % over 0; 8, 32, 64 neutral or negative.

@@ -242,14 +242,7 @@ static int launch_d128_variant(int variant, const int32_t *indptr, const int32_t
   }
 }
 
-static int default_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("DDFA_GATHER_VARIANT");
-    v = e ? atoi(e) : 9;  // r01b sweep on B200: variant 9 (2 rows/pass, 4 loads in flight, 40 regs, 128-thread CTAs) is fastest
-  }
-  return v;
-}
+static int default_variant() { return gather_variant(); }
 
 static int check_gather_args(const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, int32_t D, float *out) {
   DDFA_REQUIRE(N >= 0 && D > 0 && D % 4 == 0 && D <= 1024, "ddfa_gather_sum: unsupported shape N=%d D=%d (need D%%4==0, D<=1024)", N, D);

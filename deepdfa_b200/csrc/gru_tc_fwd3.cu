@@ -6,7 +6,7 @@
 //     gi = s W'^T + deg * b' + b_ih ,  gh = h Whh^T + b_hh ,  r,z = sigmoid(gi + gh) ,  n = tanh(gi_n + r * gh_n) ,
 //     h' = n + z (h - n)
 //
-// Why v3.  The v2 kernel (gru_tc_fwd.cu) keeps a 96 KB weight slice in shared memory, which leaves two 32 KB operand
+// Why v3.  The v2 kernel (removed; history in DESIGN.md §3) kept a 96 KB weight slice in shared memory, which leaves two 32 KB operand
 // stages; its timeline (profiles/r01l_trace_fwd.log) shows ~1 us per copy in flight, i.e. a feed of ~35 GB/s per SM, and
 // copy_bench2 (profiles/r01m_copy_bench2.log) shows a B200 SM needs >= 3 x 64 KB in flight to pull > 100 GB/s.
 // Here the GEMM is transposed,  D^T[gate column, node] = W[gate column, K] * X[node, K]^T :
@@ -366,6 +366,58 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
                          static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates, l2_hints()));
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
   return DDFA_OK;
+}
+
+// ---- fp32 [N,128] -> activation image (zero tail rows): h_0 enters the image pipeline here ------------------------------
+namespace tc3 {
+__global__ void __launch_bounds__(256) to_image_kernel(const float *__restrict__ x, int32_t N, uint8_t *__restrict__ image) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread = 8 consecutive columns of a row
+  const int64_t rows = ((int64_t)N + kTileM - 1) / kTileM * kTileM;
+  if (t >= rows * 16) return;
+  const int64_t node = t >> 4;
+  const int col = (int)(t & 15) * 8;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (node < N) {
+    const float4 a = ldg_nc_f4(x + node * kD + col), b = ldg_nc_f4(x + node * kD + col + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  uint4 ph, pl;
+  split8(v, ph, pl);
+  *reinterpret_cast<uint4 *>(image + image_offset(node, col, 0)) = ph;
+  *reinterpret_cast<uint4 *>(image + image_offset(node, col, 1)) = pl;
+}
+}  // namespace tc3
+
+size_t act_image_bytes(int64_t n) { return tcc::image_bytes(n); }
+
+int act_to_image(const float *x, int32_t N, void *image, cudaStream_t stream) {
+  const int64_t rows = ((int64_t)N + tcc::kTileM - 1) / tcc::kTileM * tcc::kTileM;
+  const int64_t total = rows * 16;
+  if (total == 0) return DDFA_OK;
+  tc3::to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, N, static_cast<uint8_t *>(image));
+  DDFA_CHECK_LAUNCH("to_image_kernel");
+  return DDFA_OK;
+}
+
+// workspace-checked entry points used by gru_step.cu (the forward workspace is exactly the packed weights)
+size_t gru_tc2_workspace_bytes() { return gru_tc3_packed_bytes(); }
+
+int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
+                    void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < gru_tc2_workspace_bytes()) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_workspace_bytes());
+    return DDFA_ERR_WORKSPACE;
+  }
+  return gru_tc3_prepare(w_fold, b_fold, b_ih, w_hh, b_hh, workspace, stream);
+}
+
+int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
+                     void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < gru_tc2_workspace_bytes()) {
+    set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_workspace_bytes());
+    return DDFA_ERR_WORKSPACE;
+  }
+  return gru_tc3_step_fwd(s_img, h_img, h, indptr, N, h_out, h_out_img, save_gates, workspace, stream);
 }
 
 int gru_tc3_trace_enable(int on) {

@@ -12,8 +12,8 @@ namespace ddfa {
 
 // warp per graph: segment max of vuln, then the loss term of that graph
 __global__ void __launch_bounds__(256) graph_label_bce_kernel(const float *__restrict__ logits, const int32_t *__restrict__ vuln,
-                                                              const int32_t *__restrict__ graph_ptr, int32_t B, float pos_weight,
-                                                              float loss_scale, float grad_scale, float *__restrict__ labels,
+                                                              const int32_t *__restrict__ graph_ptr, int32_t B, int32_t B_valid,
+                                                              float pos_weight, float loss_scale, float grad_scale, float *__restrict__ labels,
                                                               float *__restrict__ loss_out, float *__restrict__ dlogits) {
   __shared__ float s_loss[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) graph_label_bce_kernel(const float *__res
     const float y = (float)mx;
     if (lane == 0) {
       if (labels) labels[b] = y;
-      if (logits) {
+      if (dlogits && b >= B_valid) dlogits[b] = 0.f;      // padding graphs (shape bucketing): no loss term, no gradient
+      if (logits && b < B_valid) {
         const float x = logits[b];
         // torch: (1-y)*x + (1+(pw-1)*y) * (log1p(exp(-|x|)) + max(-x,0))
         const float lw = 1.f + (pos_weight - 1.f) * y;
@@ -83,19 +84,25 @@ __global__ void adam_step_inc_kernel(int32_t *step_count) { *step_count += 1; }
 
 extern "C" {
 
-int ddfa_graph_label_bce(const float *logits, const int32_t *vuln, const int32_t *graph_ptr, int32_t B, float pos_weight,
-                         float loss_scale, float grad_scale, float *labels, float *loss_out, float *dlogits, void *stream_) {
+int ddfa_graph_label_bce_valid(const float *logits, const int32_t *vuln, const int32_t *graph_ptr, int32_t B, int32_t B_valid,
+                               float pos_weight, float loss_scale, float grad_scale, float *labels, float *loss_out, float *dlogits,
+                               void *stream_) {
   using namespace ddfa;
-  DDFA_REQUIRE(B >= 0, "ddfa_graph_label_bce: negative batch");
+  DDFA_REQUIRE(B >= 0 && B_valid >= 0 && B_valid <= B, "ddfa_graph_label_bce: need 0 <= num_valid (%d) <= num_graphs (%d)", B_valid, B);
   if (B == 0) return DDFA_OK;
   DDFA_REQUIRE(vuln && graph_ptr, "ddfa_graph_label_bce: NULL pointer");
   DDFA_REQUIRE(logits || (!loss_out && !dlogits), "ddfa_graph_label_bce: loss requested without logits");
   cudaStream_t stream = as_stream(stream_);
   if (loss_out) DDFA_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), stream));
-  graph_label_bce_kernel<<<(B + 7) / 8, 256, 0, stream>>>(logits, vuln, graph_ptr, B, pos_weight, loss_scale, grad_scale, labels,
+  graph_label_bce_kernel<<<(B + 7) / 8, 256, 0, stream>>>(logits, vuln, graph_ptr, B, B_valid, pos_weight, loss_scale, grad_scale, labels,
                                                          loss_out, dlogits);
   DDFA_CHECK_LAUNCH("graph_label_bce_kernel");
   return DDFA_OK;
+}
+
+int ddfa_graph_label_bce(const float *logits, const int32_t *vuln, const int32_t *graph_ptr, int32_t B, float pos_weight,
+                         float loss_scale, float grad_scale, float *labels, float *loss_out, float *dlogits, void *stream_) {
+  return ddfa_graph_label_bce_valid(logits, vuln, graph_ptr, B, B, pos_weight, loss_scale, grad_scale, labels, loss_out, dlogits, stream_);
 }
 
 int ddfa_adam_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int32_t *step_count, int64_t numel,

@@ -28,6 +28,12 @@ def _p(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+# Execution options of the backward pass (A/B switches for scripts and tests; both settings of each run the CUDA kernels):
+#   fuse_gather_bwd: the transposed edge gather of step t+1's ds rides in step t's gate_bwd launch (tcgen05 engine)
+#   batched_wgrad:   ONE weight-gradient launch over all T steps instead of a deferred accumulation per step
+OPTIONS = {"fuse_gather_bwd": os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0",
+           "batched_wgrad": os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0"}
+
 # Optional timing hook (bench.py): an object with begin(name) / end(name) that records CUDA events
 # on the current stream around selected C-ABI calls.  None (default) costs nothing.
 profile_hook = None
@@ -166,33 +172,46 @@ class Saved:
 
 
 class Workspace:
-    """Grow-only named device buffers (used by the fused trainer to avoid per-step allocation)."""
+    """Grow-only named device buffers (used by the fused trainer to avoid per-step allocation).
+
+    A captured CUDA graph bakes in the raw pointers of the buffers it was captured with.  When a larger batch shape makes a
+    buffer grow, the old block is therefore RETIRED, not freed: it stays alive (``_retired``) for as long as the workspace
+    does, so a graph captured earlier keeps replaying over memory that is still its own (a step produces every intermediate
+    it reads, so the retired block needs no content).  Growth is geometric (x1.25) to bound the number of retired blocks;
+    ``generation`` counts reallocations (tests)."""
 
     def __init__(self, device):
         self.device = device
         self._bufs = {}
+        self._retired = []
+        self.generation = 0
+
+    def _get(self, name, shape, dtype, zeroed):
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            grow = max(numel, 1)
+            if buf is not None:
+                self._retired.append(buf)
+                self.generation += 1
+                if buf.dtype == dtype:
+                    grow = max(grow, int(buf.numel() * 1.25))
+            # images rely on never containing non-finite garbage in their padding rows -> zero-filled on (re)allocation
+            buf = (torch.zeros if zeroed else torch.empty)(grow, dtype=dtype, device=self.device)
+            self._bufs[name] = buf
+        return buf[:numel].view(*shape)
 
     def get(self, name, shape, dtype=torch.float32):
-        numel = 1
-        for s in shape:
-            numel *= int(s)
-        buf = self._bufs.get(name)
-        if buf is None or buf.numel() < numel or buf.dtype != dtype:
-            buf = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
-            self._bufs[name] = buf
-        return buf[:numel].view(*shape)
+        return self._get(name, shape, dtype, False)
 
     def get_zeroed(self, name, shape, dtype=torch.float32):
-        """Like get(), but the backing store is zero-filled when it is (re)allocated — activation images rely
-        on never containing non-finite garbage in their padding rows."""
-        numel = 1
-        for s in shape:
-            numel *= int(s)
-        buf = self._bufs.get(name)
-        if buf is None or buf.numel() < numel or buf.dtype != dtype:
-            buf = torch.zeros(max(numel, 1), dtype=dtype, device=self.device)
-            self._bufs[name] = buf
-        return buf[:numel].view(*shape)
+        """Like get(), but the backing store is zero-filled when it is (re)allocated."""
+        return self._get(name, shape, dtype, True)
+
+    def retired_bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._retired)
 
 
 class _FreshAlloc:
@@ -340,10 +359,9 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     ds = alloc.get("ds", (N, D))
     ds_prev = None                     # tcgen05 engine: ds of the step after t, folded into step t's call (dh' = dh + A^T ds)
     ds_alt = alloc.get("ds_b", (N, D)) if engine == ENGINE_TCGEN05 else None
-    fuse_gather = os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0"   # A/B switch for scripts; both paths are the CUDA kernels
+    fuse_gather = OPTIONS["fuse_gather_bwd"]
     # tcgen05: keep the q images of every step and run the weight-gradient GEMM of the whole pass as ONE launch at the end
-    batched_wgrad = (engine == ENGINE_TCGEN05 and bool(saved.h_img) and 0 < T <= 16
-                     and os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0")       # env: A/B switch for scripts
+    batched_wgrad = engine == ENGINE_TCGEN05 and bool(saved.h_img) and 0 < T <= 16 and OPTIONS["batched_wgrad"]
     ws_bytes = L.call("ddfa_gru_step_bwd_workspace_bytes_steps", N, D, engine, T if batched_wgrad else 1)
     ws = alloc.get("gru_ws_bwd", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
@@ -379,8 +397,9 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
 
 
 def graph_label_bce(dg: DeviceGraph, vuln: torch.Tensor, logits: Optional[torch.Tensor], pos_weight: float,
-                    loss_scale: float, grad_scale: float, want_grad: bool, alloc=None, loss_out=None):
-    """Labels (segment max of _VULN) + BCE-with-logits sum (+ dlogits). Returns (labels, loss[1], dlogits)."""
+                    loss_scale: float, grad_scale: float, want_grad: bool, alloc=None, loss_out=None, num_valid: Optional[int] = None):
+    """Labels (segment max of _VULN) + BCE-with-logits sum (+ dlogits). Returns (labels, loss[1], dlogits).
+    ``num_valid``: graphs [num_valid, B) are bucket padding (no loss term, zero gradient)."""
     L = _lib.lib()
     alloc = alloc or _FreshAlloc(dg.device)
     B = dg.batch_size
@@ -391,6 +410,6 @@ def graph_label_bce(dg: DeviceGraph, vuln: torch.Tensor, logits: Optional[torch.
     dlogits = alloc.get("dlogits", (B,)) if (want_grad and logits is not None) else None
     if vuln.dtype != torch.int32:
         vuln = vuln.to(torch.int32)
-    L.call("ddfa_graph_label_bce", _p(logits), _p(vuln.contiguous()), _p(dg.graph_ptr), B, float(pos_weight),
-           float(loss_scale), float(grad_scale), _p(labels), _p(loss), _p(dlogits), _stream_ptr())
+    L.call("ddfa_graph_label_bce_valid", _p(logits), _p(vuln.contiguous()), _p(dg.graph_ptr), B, B if num_valid is None else int(num_valid),
+           float(pos_weight), float(loss_scale), float(grad_scale), _p(labels), _p(loss), _p(dlogits), _stream_ptr())
     return labels, loss, dlogits

@@ -82,9 +82,10 @@ class _GGNNFunction(torch.autograd.Function):
     """Whole hot path as one autograd node: forward and backward are hand-written kernels."""
 
     @staticmethod
-    def forward(ctx, dg, idx, n_steps, engine, num_tables, num_layers, oob, *flat):
+    def forward(ctx, dg, idx, n_steps, engine, num_tables, num_layers, oob, need_grad, *flat):
+        # need_grad is decided by the caller: ctx.needs_input_grad is True for Parameters even under torch.no_grad(), which
+        # would run validation / test / inference in the training-mode forward (every per-step buffer kept)
         params = E.ParamPack.from_flat_list([t.detach() for t in flat], num_tables, num_layers)
-        need_grad = any(ctx.needs_input_grad[7:])
         pooled, logits, saved = E.forward(params, dg, idx, n_steps, training=need_grad, engine=engine, oob_counter=oob)
         ctx.state = (params, dg, saved, engine, num_layers)
         return logits if num_layers > 0 else pooled
@@ -99,7 +100,7 @@ class _GGNNFunction(torch.autograd.Function):
         else:
             E.backward(params, dg, saved, grads, dpooled=dout, engine=engine)
         ctx.state = None
-        return (None,) * 7 + tuple(grads.flat_list())
+        return (None,) * 8 + tuple(grads.flat_list())
 
 
 class _BCEFunction(torch.autograd.Function):
@@ -191,8 +192,14 @@ class FlowGNNGGNNModule(nn.Module):
         if engine not in _ENGINES:
             raise ValueError(f"engine must be one of {sorted(_ENGINES)}, got {engine!r}")
         self.engine = engine
-        self.validate_inputs = os.environ.get("DDFA_B200_VALIDATE", "0") == "1"
+        # Input validation (the reference raises on an out-of-range embedding index; DGL rejects edge ids >= num_nodes):
+        #   "deferred" (default)     device-side counters, read without a host sync -> IndexError at the NEXT call / check_inputs()
+        #   "sync" ($DDFA_B200_VALIDATE=1)   checked before forward returns (one device sync per call)
+        #   "off"  ($DDFA_B200_VALIDATE=0)   indices are clamped / bad edges dropped silently
+        self.validate_inputs = {"1": "sync", "0": "off"}.get(os.environ.get("DDFA_B200_VALIDATE", ""), "deferred")
         self._oob = None
+        self._oob_host = None
+        self._oob_pending = None
 
     # ---- parameter plumbing -----------------------------------------------------------------
     def _tables(self):
@@ -231,20 +238,63 @@ class FlowGNNGGNNModule(nn.Module):
         """ggnn.py:82-109.  Returns logits [B] (0-d for a single graph, like ``.squeeze()``) or, in
         encoder_mode, the pooled embedding [B, out_dim]."""
         g, dg, idx = self._prepare(graph)
-        if self.validate_inputs and self._oob is None:
-            self._oob = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._raise_deferred_input_errors()
+        if self.validate_inputs != "off" and self._oob is None:
+            with torch.cuda.device(self.device):
+                self._oob = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._oob_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         flat = self.param_list()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in flat)
         with torch.cuda.device(self.device):
             out = _GGNNFunction.apply(dg, idx, self.hparams.n_steps, _ENGINES[self.engine], len(self._tables()),
-                                      self._num_layers, self._oob, *flat)
-        if self.validate_inputs:
-            bad = int(self._oob.item())
-            if bad:
-                self._oob.zero_()
-                raise IndexError(f"{bad} node feature indices outside [0, {self.input_dim})")
+                                      self._num_layers, self._oob, need_grad, *flat)
+            if self.validate_inputs == "sync":
+                self._check_inputs_now(dg)
+            elif self.validate_inputs == "deferred":
+                # no host sync on the hot path: the counters travel to pinned host memory behind the kernels and are looked at
+                # by the NEXT call (or by check_inputs()), which raises for this batch one step late
+                self._oob_host.copy_(self._oob, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._oob_pending = (ev, dg)
         if self.hparams.encoder_mode:
             return out
         return out.squeeze()
+
+    # ---- input validation ------------------------------------------------------------------
+    def _check_inputs_now(self, dg):
+        bad = int(self._oob.item())
+        dropped = int(dg._csr_ws[:4].view(torch.int32).item()) if getattr(dg, "_csr_ws", None) is not None else 0
+        if bad:
+            self._oob.zero_()
+            raise IndexError(f"{bad} node feature indices outside [0, {self.input_dim})")
+        if dropped:
+            raise IndexError(f"{dropped} edges with an endpoint outside [0, num_nodes) were dropped by ddfa_build_csr")
+
+    def _raise_deferred_input_errors(self, wait: bool = False):
+        pend = self._oob_pending
+        if pend is None:
+            return
+        ev, dg = pend
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._oob_pending = None
+        bad = int(self._oob_host[0])
+        if bad:
+            self._oob.zero_()
+            self._oob_host.zero_()
+            raise IndexError(f"{bad} node feature indices outside [0, {self.input_dim}) in an earlier batch")
+        if getattr(dg, "_csr_ws", None) is not None:
+            dropped = int(dg._csr_ws[:4].view(torch.int32).item())      # the event has completed: this read does not wait
+            if dropped:
+                raise IndexError(f"{dropped} edges with an endpoint outside [0, num_nodes) were dropped by ddfa_build_csr in an earlier batch")
+
+    def check_inputs(self):
+        """Waits for the last forward's validation counters and raises IndexError if that batch had out-of-range node
+        feature indices or edge endpoints (validate_inputs == "deferred")."""
+        self._raise_deferred_input_errors(wait=True)
 
     def get_label(self, batch):
         """base_module.py:83-95 (graph style): per-graph max of ndata['_VULN'] as float — a fused

@@ -96,6 +96,26 @@ def make_batch(num_graphs: int = 256, nodes_per_graph: int = 150, edges_per_node
                       ndata, torch.from_numpy(bne.astype(np.int64)))
 
 
+def make_learnable_batch(num_graphs: int, nodes_per_graph: int, seed: int, variable: bool = True, vuln_rate: float = 0.4) -> BatchedCFG:
+    """A batch whose graph label can be learned from the node features (``make_batch`` draws labels independently of the
+    features, which is right for throughput and parity but leaves nothing to learn): the vulnerable node of a vulnerable graph
+    carries api token 7 and operator token 11; 8 % of the clean graphs carry api token 7 on one node as a distractor.  Used by
+    the train-both-arms / F1 comparisons (BASELINE configs[2], configs[4])."""
+    g = make_batch(num_graphs, nodes_per_graph, seed=seed, variable=variable, vuln_rate=vuln_rate)
+    rng = np.random.default_rng(seed)
+    vuln = g.ndata["_VULN"].numpy()
+    api, op = g.ndata["_ABS_DATAFLOW_api"].numpy(), g.ndata["_ABS_DATAFLOW_operator"].numpy()
+    hot = np.nonzero(vuln)[0]
+    api[hot] = 7
+    op[hot] = 11
+    offs = np.concatenate([[0], np.cumsum(g.batch_num_nodes().numpy())])
+    labels = np.maximum.reduceat(vuln, offs[:-1])
+    for b in np.nonzero(labels == 0)[0]:
+        if rng.random() < 0.08:
+            api[offs[b] + rng.integers(0, offs[b + 1] - offs[b])] = 7
+    return g
+
+
 def make_edge_cases(input_dim: int = 1002, seed: int = 7) -> BatchedCFG:
     """Tiny ragged batch covering the reference-relevant edge cases:
     a 1-node graph, a 2-node graph, a 300-node graph, a node with zero in-degree

@@ -27,14 +27,22 @@ _ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat 
 class FusedTrainer:
     def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False, max_graph_shapes: int = 8,
-                 max_resident_graphs: int = 64):
+                 max_resident_graphs: int = 64, distributed: bool = True, bucket_nodes: int = 0, bucket_edges: int = 0,
+                 bucket_min_pad_nodes: int = 64):
+        """``distributed=False`` makes this a single-rank trainer even inside an initialised process group (no all-reduce).
+        ``bucket_nodes`` / ``bucket_edges`` > 0 switch on shape bucketing for HOST batches under ``use_cuda_graph``: every batch
+        is padded with ONE dummy graph of isolated nodes up to the next multiple of ``bucket_nodes`` nodes (at least
+        ``bucket_min_pad_nodes`` of them, which also carry the padding edges as self loops) and ``bucket_edges`` edges, so that a
+        shuffled stream of ever-new ``(N, E)`` (the reference reshuffles every epoch, datamodule.py:123-129) replays a handful of
+        captured graphs.  The dummy graph has zero loss weight (``ddfa_graph_label_bce_valid``): no gradient comes from it."""
         if module.device.type != "cuda":
             raise _lib.DdfaError("FusedTrainer needs the module on a CUDA device (no CPU fallback)")
         self.module = module
         self.device = module.device
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
+        self.bucket_nodes, self.bucket_edges, self.bucket_min_pad_nodes = int(bucket_nodes), int(bucket_edges), int(bucket_min_pad_nodes)
         self.use_cuda_graph = use_cuda_graph
         # a captured graph bakes in the batch SHAPE (and, for resident batches, the batch object): cap how many are kept so a
         # stream of ever-new shapes (un-bucketed real data) degrades to eager launches instead of growing without bound
@@ -69,14 +77,24 @@ class FusedTrainer:
         self._warm_shapes = set()
 
     # ------------------------------------------------------------------------------------
-    def _enqueue(self, g, dg, idx, vuln, global_batch: int):
+    def _global_batch(self, global_batch: Optional[int], local_graphs: int) -> int:
+        """The divisor of the mean BCE (base_module.py:74,183).  Ranks generally hold different numbers of graphs
+        (batched_graph.split_batch balances by nodes), so with more than one rank the caller must say what the global batch is."""
+        if global_batch is not None:
+            return int(global_batch)
+        if self.world > 1:
+            raise _lib.DdfaError("FusedTrainer.step: global_batch is required when world_size > 1 (shards hold different numbers of graphs; "
+                                 "the loss is the mean over the GLOBAL batch)")
+        return int(local_graphs)
+
+    def _enqueue(self, g, dg, idx, vuln, global_batch: int, num_valid: Optional[int] = None):
         m = self.module
         eng = _ENGINES[m.engine]
         pw = 1.0 if m.hparams.positive_weight is None else float(m.hparams.positive_weight)
         self.flat_g.zero_()
         _, logits, saved = E.forward(self.params, dg, idx, m.hparams.n_steps, training=True, engine=eng, alloc=self.ws)
         _, _, dlogits = E.graph_label_bce(dg, vuln, logits, pw, 1.0 / global_batch, 1.0 / global_batch, True,
-                                          alloc=self.ws, loss_out=self.loss_slot)
+                                          alloc=self.ws, loss_out=self.loss_slot, num_valid=num_valid)
         E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws)
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
@@ -87,29 +105,48 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------------------------
     # ---- host batches through per-shape static buffers + captured graphs -------------------------------------------------
+    def _bucket_shape(self, N: int, Eg: int):
+        """Padded (nodes, edges) of a batch under shape bucketing, or None when bucketing is off."""
+        if self.bucket_nodes <= 0:
+            return None
+        bn, be = self.bucket_nodes, max(self.bucket_edges, 1)
+        Nb = (N + max(self.bucket_min_pad_nodes, 1) + bn - 1) // bn * bn
+        Eb = (Eg + be - 1) // be * be
+        return Nb, Eb
+
+    def num_bucket_shapes(self) -> int:
+        return sum(1 for k in self._stream_slots if k[0] == "bucket")
+
     def _stream_slot(self, g, global_batch: Optional[int]):
         N, Eg, B = g.num_nodes(), g.num_edges(), g.batch_size
-        gb = global_batch if global_batch is not None else B * self.world
-        key = (N, Eg, B, gb)
+        gb = self._global_batch(global_batch, B)
+        bucket = self._bucket_shape(N, Eg)
+        key = ("bucket", bucket[0], bucket[1], B, gb) if bucket else ("exact", N, Eg, B, gb)
         slot = self._stream_slots.get(key)
         if slot is None:
             if len(self._stream_slots) >= self.max_graph_shapes:
                 return None
             src, dst = g.edges()
             dev = self.device
+            Ns, Es, Bs = (bucket[0], bucket[1], B + 1) if bucket else (N, Eg, B)
 
             def new_set():
-                return {"src": torch.empty_like(src, device=dev), "dst": torch.empty_like(dst, device=dev),
-                        "bnn": torch.empty_like(g.batch_num_nodes(), device=dev),
-                        "ndata": {k: torch.empty_like(v, device=dev) for k, v in g.ndata.items()},
-                        "graph": None, "keep": None, "free": None, "ready": None}
+                st = {"src": torch.empty(Es, dtype=src.dtype, device=dev), "dst": torch.empty(Es, dtype=dst.dtype, device=dev),
+                      "bnn": torch.empty(Bs, dtype=torch.int64, device=dev),
+                      "ndata": {k: torch.zeros((Ns,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in g.ndata.items()},
+                      "graph": None, "keep": None, "free": None, "ready": None}
+                return st
             # two input-buffer sets: while the graph of one set runs, the next batch is copied into the other (prefetch)
-            slot = {"sets": [new_set(), new_set()], "next": 0, "staged": None, "warm": False, "N": N, "gb": gb}
+            slot = {"sets": [new_set(), new_set()], "next": 0, "staged": None, "warm": False, "N": Ns, "gb": gb,
+                    "valid": B if bucket else None,
+                    "iota": torch.arange(Es, dtype=src.dtype, device=dev) if bucket else None}
             self._stream_slots[key] = slot
         return slot
 
     def _stage(self, slot, g, stream):
-        """Copies the host batch ``g`` into the slot's next buffer set on ``stream``; returns the set index."""
+        """Copies the host batch ``g`` into the slot's next buffer set on ``stream``; returns the set index.  Under bucketing
+        the tails are (re)written too: padding nodes get feature index 0 / _VULN 0, the padding edges become self loops spread
+        round-robin over the padding nodes, and the dummy graph's node count goes into the last ``batch_num_nodes`` entry."""
         i = slot["next"]
         slot["next"] = 1 - i
         st = slot["sets"][i]
@@ -117,11 +154,22 @@ class FusedTrainer:
             if st["free"] is not None:
                 stream.wait_event(st["free"])           # the graph that last read this set has finished
             src, dst = g.edges()
-            st["src"].copy_(src, non_blocking=True)
-            st["dst"].copy_(dst, non_blocking=True)
-            st["bnn"].copy_(g.batch_num_nodes(), non_blocking=True)
+            N, Eg, B = g.num_nodes(), g.num_edges(), g.batch_size
+            st["src"][:Eg].copy_(src, non_blocking=True)
+            st["dst"][:Eg].copy_(dst, non_blocking=True)
+            st["bnn"][:B].copy_(g.batch_num_nodes(), non_blocking=True)
             for k, v in g.ndata.items():
-                st["ndata"][k].copy_(v, non_blocking=True)
+                st["ndata"][k][:N].copy_(v, non_blocking=True)
+            if slot["valid"] is not None:
+                Nb, Eb = slot["N"], st["src"].shape[0]
+                pad_nodes = Nb - N
+                st["bnn"][B:].fill_(pad_nodes)
+                for k in st["ndata"]:
+                    st["ndata"][k][N:].zero_()
+                if Eb > Eg:
+                    torch.remainder(slot["iota"][: Eb - Eg], pad_nodes, out=st["src"][Eg:])
+                    st["src"][Eg:].add_(N)
+                    st["dst"][Eg:].copy_(st["src"][Eg:])
             ev = torch.cuda.Event()
             ev.record(stream)
             st["ready"] = ev
@@ -145,9 +193,10 @@ class FusedTrainer:
 
     def _step_streamed(self, batch, g, global_batch: Optional[int]) -> torch.Tensor:
         """Host batch + use_cuda_graph: the batch's arrays are copied into device buffers that are STATIC per shape
-        (num_nodes, num_edges, batch_size) and one captured CUDA graph per buffer set covers the whole step including the
-        device CSR build — a new batch of a known shape costs its H2D copies (overlappable: ``prefetch``) plus one graph
-        launch.  The first visit of a shape runs eagerly (workspace growth), the next two capture."""
+        (num_nodes, num_edges, batch_size — or per BUCKET shape with ``bucket_nodes`` / ``bucket_edges``) and one captured
+        CUDA graph per buffer set covers the whole step including the device CSR build — a new batch of a known shape costs
+        its H2D copies (overlappable: ``prefetch``) plus one graph launch.  The first visit of a shape runs eagerly
+        (workspace growth), the next two capture."""
         m = self.module
         with torch.cuda.device(self.device):
             slot = self._stream_slot(g, global_batch)
@@ -170,7 +219,7 @@ class FusedTrainer:
                 vuln = gs.ndata["_VULN"]
                 if vuln.dtype != torch.int32:
                     vuln = vuln.to(torch.int32)
-                self._enqueue(g_, dg, idx, vuln.contiguous(), gb)
+                self._enqueue(g_, dg, idx, vuln.contiguous(), gb, num_valid=slot["valid"])
                 return (gs, dg, idx, vuln)
 
             if not slot["warm"]:
@@ -204,18 +253,31 @@ class FusedTrainer:
         B = int(ids_np.shape[0])
         N = int(arena.nodes_per_graph[ids_np].sum())
         Eg = int(arena.edges_per_graph[ids_np].sum())
-        gb = global_batch if global_batch is not None else B * self.world
+        gb = self._global_batch(global_batch, B)
         key = ("arena", id(arena), N, Eg, B, gb)
         slot = self._stream_slots.get(key)
         with torch.cuda.device(self.device):
             if slot is None:
                 if len(self._stream_slots) >= self.max_graph_shapes:
                     return self._step_eager(arena.batch(ids), global_batch)
-                slot = {"out": arena.alloc_outputs(B, N, Eg), "stage": torch.empty(B, dtype=torch.int32).pin_memory(),
+                # a ring of pinned id stages: the host may run several steps ahead of the device (that is what the captured
+                # graph is for), so a stage is rewritten only after the H2D copy that last read it has completed
+                slot = {"out": arena.alloc_outputs(B, N, Eg), "stages": [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(4)],
+                        "stage_done": [None] * 4, "turn": 0, "steps": 0,
                         "graph": None, "warm": False, "keep": None, "arena": arena}     # the arena stays alive with its graph
                 self._stream_slots[key] = slot
-            slot["stage"].copy_(torch.from_numpy(ids_np.astype(np.int32)))
-            slot["out"]["ids"].copy_(slot["stage"], non_blocking=True)
+            k = slot["turn"]
+            slot["turn"] = (k + 1) % len(slot["stages"])
+            if slot["stage_done"][k] is not None:
+                slot["stage_done"][k].synchronize()
+            slot["stages"][k].copy_(torch.from_numpy(ids_np.astype(np.int32)))
+            slot["out"]["ids"].copy_(slot["stages"][k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            slot["stage_done"][k] = ev
+            slot["steps"] += 1
+            if slot["keep"] is not None and slot["steps"] % 256 == 0:
+                slot["keep"][0].check()      # the assembler's device error counter (bad id / totals mismatch): one sync every 256 steps
 
             def enqueue():
                 g = arena._assemble(slot["out"]["ids"], B, N, Eg, slot["out"])
@@ -258,8 +320,7 @@ class FusedTrainer:
                 cached = vuln.to(self.device, non_blocking=True).to(torch.int32).contiguous()
                 g._cache[key] = cached
             vuln = cached
-        if global_batch is None:
-            global_batch = dg.batch_size * self.world
+        global_batch = self._global_batch(global_batch, dg.batch_size)
         with torch.cuda.device(self.device):
             shape_key = (dg.num_nodes, dg.num_edges, dg.batch_size)
             capturable = self.use_cuda_graph and as_batched_cfg(batch).device.type == "cuda" and \
@@ -280,3 +341,31 @@ class FusedTrainer:
                     self._graphs[id(g)] = entry
                 entry[0].replay()
         return self.loss_slot
+
+    # ------------------------------------------------------------------------------------
+    @staticmethod
+    def dp_self_check(engine: str, device, rank: int, world: int, steps: int = 5, graphs_per_rank: int = 24, nodes: int = 60) -> dict:
+        """On-hardware data-parallel parity (SURVEY.md §8(e) "Determinism"): ``steps`` optimisation steps of a global batch
+        sharded over the ``world`` ranks (node-balanced shards of different sizes, NCCL all-reduce) against the same steps of
+        the UNSHARDED batch on this rank alone, same seeds.  fp32 summation order is the only difference.  Collective: every
+        rank must call it.  Returns the loss curves and the largest parameter difference after the last step."""
+        from . import synth
+        from .batched_graph import split_batch
+        feat = "_ABS_DATAFLOW_api_all_limitall_1000_limitsubkeys_1000"
+
+        def make(distributed):
+            torch.manual_seed(4321)
+            m = FlowGNNGGNNModule(feat, 1002, 32, 8, 2, concat_all_absdf=True, positive_weight=4.0, engine=engine).to(device)
+            return m, FusedTrainer(m, distributed=distributed)
+        m_dp, tr_dp = make(True)
+        m_1, tr_1 = make(False)
+        l_dp, l_1 = [], []
+        for i in range(steps):
+            b = synth.make_batch(graphs_per_rank * world, nodes, seed=900 + i, variable=True, vuln_rate=0.3)
+            shard = split_batch(b, world)[rank]
+            l_dp.append(float(tr_dp.step(shard.to(device), global_batch=b.batch_size)))
+            l_1.append(float(tr_1.step(b.to(device), global_batch=b.batch_size)))
+        dparam = max(float((p.data - q.data).abs().max()) for p, q in zip(m_dp.param_list(), m_1.param_list()))
+        return {"steps": steps, "world": world, "global_batch": graphs_per_rank * world, "loss_sharded": l_dp, "loss_single_rank": l_1,
+                "max_abs_loss_diff": max(abs(a - b) for a, b in zip(l_dp, l_1)), "max_abs_param_diff": dparam,
+                "shard_sizes_differ": True}

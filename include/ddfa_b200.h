@@ -48,6 +48,16 @@ const char *ddfa_last_error(void);
 int ddfa_device_supported(void);
 /* 1 if the given DDFA_ENGINE_* is compiled into this library, else 0 */
 int ddfa_engine_available(int engine);
+/* Tuning knobs: process-wide selectors between equivalent launch configurations of the same kernels (defaults compiled in;
+ * the library reads no environment variables).  ddfa_tuning_get returns -1 for an unknown key. */
+enum {
+  DDFA_TUNE_L2_HINTS = 0,       /* bit mask of L2 eviction-priority hints, default 23 (csrc/common.cuh) */
+  DDFA_TUNE_PDL_MASK = 1,       /* bit mask of kernels launched with programmatic stream serialization, default 15 */
+  DDFA_TUNE_GATHER_VARIANT = 2, /* launch shape of the D = 128 edge gather (ddfa_gather_sum_variant ids), default 9 */
+  DDFA_TUNE__COUNT = 3
+};
+int ddfa_tuning_set(int key, int value);
+int ddfa_tuning_get(int key);
 /* development aid: in-kernel pipeline timeline of the tcgen05 kernels (SM-clock stamps per CTA / tile / event).
  * ddfa_debug_set(2, v): v = 0 off, 1 = forward + dgrad kernels, 2 = forward + wgrad kernels;
  * ddfa_debug_read(2 | 3, host, bytes): stamps of the backward (2) or forward (3) kernel's last launch. */
@@ -277,6 +287,12 @@ int ddfa_readout_bwd(const float *dpooled, const float *pooled, const float *h_f
 int ddfa_graph_label_bce(const float *logits, const int32_t *vuln, const int32_t *graph_ptr,
                          int32_t num_graphs, float pos_weight, float loss_scale, float grad_scale,
                          float *labels, float *loss_out, float *dlogits, void *stream);
+/* Same, for a batch padded to a bucket shape (FusedTrainer: one CUDA graph per bucket shape on a shuffled stream, the reference
+ * reshuffles every epoch, datamodule.py:123-129): graphs [num_valid, num_graphs) are padding — they get a label but contribute
+ * no loss term and dlogits = 0, so nothing of them reaches any gradient. */
+int ddfa_graph_label_bce_valid(const float *logits, const int32_t *vuln, const int32_t *graph_ptr,
+                               int32_t num_graphs, int32_t num_valid, float pos_weight, float loss_scale,
+                               float grad_scale, float *labels, float *loss_out, float *dlogits, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * K10  torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2 (DDFA/configs/

@@ -127,9 +127,13 @@ def main():
                                           encoder_mode=True), graphs=dict(sizes=[12, 7, 33], seed=13, vuln_rate=0.2, input_dim=64)),
         dict(name="one_graph_squeeze", ctor=dict(feat=feat, input_dim=64, hidden_dim=8, n_steps=2, num_output_layers=1, concat_all_absdf=True),
              graphs=dict(sizes=[21], seed=14, vuln_rate=0.4, input_dim=64)),
-        # hidden width 128 (what the tcgen05 engine runs): forward only, to keep the fixture small
+        # hidden width 128 (what the tcgen05 engine runs): forward only
         dict(name="concat_D128_T8_L1_fwd", ctor=dict(feat=feat, input_dim=64, hidden_dim=32, n_steps=8, num_output_layers=1, concat_all_absdf=True),
              graphs=dict(sizes=[150, 3, 77, 140, 1, 129], seed=15, vuln_rate=0.3, input_dim=64), forward_only=True),
+        # hidden width 128 WITH the reference's training step: loss + parameter gradients for the tcgen05 backward kernels
+        dict(name="concat_D128_T8_L2_pw_train", ctor=dict(feat=feat, input_dim=64, hidden_dim=32, n_steps=8, num_output_layers=2,
+                                                         concat_all_absdf=True, positive_weight=3.0),
+             graphs=dict(sizes=[150, 3, 77, 140, 1, 129, 260, 31], seed=16, vuln_rate=0.4, input_dim=64)),
     ]
     for i, spec in enumerate(specs):
         torch.manual_seed(100 + i)

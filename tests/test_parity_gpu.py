@@ -111,6 +111,48 @@ def test_encoder_mode_backward_through_pooled(golden):
         assert (p.grad.cpu().double() - q.grad).abs().max() <= 1e-4 * max(1.0, float(q.grad.abs().max())) + 1e-7, name
 
 
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_adam_steps_width128_both_paths_against_oracle(engine):
+    """Three Adam steps at hidden width 128 on both engines, through (a) the reference-style loop (module.training_step +
+    loss.backward() + stock torch.optim.Adam) and (b) FusedTrainer (flat buffers + ddfa_adam_flat): losses and the parameters
+    after the third step follow the fp32 oracle trained the same way."""
+    g = synth.make_batch(12, 50, seed=21, variable=True, vuln_rate=0.4)
+    torch.manual_seed(5)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 6, 2, concat_all_absdf=True, positive_weight=2.5)
+    state0 = copy.deepcopy(o.state_dict())
+    opt = O.make_optimizer(o)
+    ref_losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss_ref, _ = o.training_loss(g)
+        loss_ref.backward()
+        opt.step()
+        ref_losses.append(float(loss_ref))
+    for path in ("module_api", "fused_trainer"):
+        m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 6, 2, concat_all_absdf=True, positive_weight=2.5, engine=engine)
+        m.load_state_dict(state0)
+        m.to(DEV)
+        gd = g.to(DEV)
+        losses = []
+        if path == "module_api":
+            mopt = m.configure_optimizers()
+            for _ in range(3):
+                mopt.zero_grad()
+                loss = m.training_step((gd, {}), 0)
+                loss.backward()
+                mopt.step()
+                losses.append(float(loss))
+        else:
+            tr = D.FusedTrainer(m)
+            losses = [float(tr.step(gd)) for _ in range(3)]
+        assert losses == pytest.approx(ref_losses, abs=5e-5), (path, engine)
+        worst = max(float((m.state_dict()[k].cpu() - v).abs().max()) for k, v in o.state_dict().items())
+        print(f"adam x3 {path} {engine}: max |dparam| vs oracle {worst:.2e}")
+        # Adam's first steps move every touched parameter by ~lr = 1e-3 whatever the gradient's size, so a sign flip of a
+        # near-zero gradient component shows as 2e-3; bound well below that
+        assert worst < (2e-5 if engine == "simt" else 2e-4), (path, engine, worst)
+
+
 def test_tiny_adam_steps_autograd_path_and_fused_trainer(golden):
     case = next(c for c in golden["cases"] if c["name"] == "tiny_T3_L2")
     g = graph_of(case).to(DEV)
@@ -158,23 +200,54 @@ def test_full_size_c0_against_live_oracle(engine, T, L):
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("variable", [False, True])
+def test_c1_logits_against_live_fp64_oracle(engine, variable):
+    """BASELINE configs[2] shape: 1024 CFGs (fixed 150 nodes, and lognormal sizes 2..2000) — logits of both engines against the
+    fp64 CPU oracle at trained-scale weights, identical decisions."""
+    g = synth.make_batch(1024, 150, seed=11, variable=variable)
+    torch.manual_seed(0)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 8, 2, concat_all_absdf=True)
+    for p in o.parameters():
+        p.data.mul_(2.0)
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 8, 2, concat_all_absdf=True, engine=engine)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV)
+    o = o.double()
+    with torch.no_grad():
+        ref = o(g)
+        out = m(g, {})
+    err = assert_logits_close(out, ref)
+    print(f"C1 variable={variable} engine={engine}: N={g.num_nodes()} max|dlogit| vs fp64 = {err:.2e}, |logit| max {float(ref.abs().max()):.2f}")
+    assert torch.equal(m.get_label(g).cpu(), o.get_label(g).float())
+
+
+# per-parameter gradient bound, relative to the largest entry of that parameter's reference gradient.  The fp32 oracle itself is
+# ~1e-6 from fp64 on these; the tcgen05 engine multiplies with bf16x3 split operands (2^-16 per product) and uses ex2.approx
+# gate math, which is what the measured worst case (printed, and recorded in DESIGN.md §4) reflects.
+GRAD_TOL = {"simt": 2e-4, "tcgen05": 4e-3}
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
 def test_full_size_gradients_against_live_oracle(engine):
     g = synth.make_batch(64, 150, seed=5, variable=True, vuln_rate=0.3)
     torch.manual_seed(1)
-    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, positive_weight=4.0)
+    o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, positive_weight=4.0).double()
     loss_ref, _ = o.training_loss(g)
     loss_ref.backward()
     m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 8, 3, concat_all_absdf=True, positive_weight=4.0, engine=engine)
-    m.load_state_dict(o.state_dict())
+    m.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
     m.to(DEV)
     loss = m.training_step((g.to(DEV), {}), 0)
     loss.backward()
     assert abs(float(loss) - float(loss_ref)) < 1e-4
+    worst = {}
     for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
         ref = q.grad
         scale = max(float(ref.abs().max()), 1e-6)
-        rel = float((p.grad.cpu() - ref).abs().max()) / scale
-        assert rel < (2e-3 if engine == "simt" else 2e-2), (name, rel)
+        worst[name] = float((p.grad.cpu().double() - ref).abs().max()) / scale
+    print(f"gradient worst case per parameter vs fp64 oracle, engine={engine}: " + ", ".join(f"{k}={v:.1e}" for k, v in worst.items()))
+    bad = {k: v for k, v in worst.items() if v >= GRAD_TOL[engine]}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
@@ -214,19 +287,36 @@ def test_single_graph_squeeze_and_duck_typed_dgl_graph():
 
 def test_index_validation_raises():
     m = D.FlowGNNGGNNModule(FEAT, 60, 8, 2, 1, concat_all_absdf=True).to(DEV)
-    m.validate_inputs = True
     g = synth.make_batch(sizes=[6, 3], input_dim=60, seed=1)
+    good = synth.make_batch(sizes=[6, 3], input_dim=60, seed=2)
     g.ndata["_ABS_DATAFLOW_api"][2] = 60
+    assert m.validate_inputs == "deferred"          # default: no host sync on the hot path, the error surfaces one call later
+    m(g, {})
+    with pytest.raises(IndexError):
+        m.check_inputs()
+    m(g, {})
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        m(good, {})
+    m(good, {})
+    m.check_inputs()                                # a clean batch raises nothing
+    m.validate_inputs = "sync"                      # $DDFA_B200_VALIDATE=1: checked before forward returns
     with pytest.raises(IndexError):
         m(g, {})
+    bad_edge = synth.make_batch(sizes=[6, 3], input_dim=60, seed=3)
+    src, dst = bad_edge.edges()
+    src[1] = 9                                      # endpoint outside [0, 9)
+    with pytest.raises(IndexError):
+        m(bad_edge, {})
 
 
-def test_fused_trainer_tracks_oracle_training():
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_fused_trainer_tracks_oracle_training(engine):
     """Config-3 style check at reduced size: 10 optimisation steps on a stream of batches; the loss
-    curve and the final decisions follow the oracle trained on the identical stream."""
+    curve and the final decisions follow the oracle trained on the identical stream (both engines, width 128)."""
     torch.manual_seed(0)
     o = O.OracleFlowGNNGGNN(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, positive_weight=8.0)
-    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, positive_weight=8.0, engine="simt")
+    m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, positive_weight=8.0, engine=engine)
     m.load_state_dict(copy.deepcopy(o.state_dict()))
     m.to(DEV)
     tr = D.FusedTrainer(m)
@@ -283,11 +373,9 @@ def test_batched_weight_gradient_matches_per_step(monkeypatch):
     torch.manual_seed(3)
     b = synth.make_batch(24, 60, seed=5, variable=True, vuln_rate=0.3)
     grads = {}
-    for key, env in (("default", {}), ("per_step_wgrad", {"DDFA_BATCHED_WGRAD": "0"}), ("unfused_gather", {"DDFA_FUSE_GATHER_BWD": "0"})):
-        for k in ("DDFA_BATCHED_WGRAD", "DDFA_FUSE_GATHER_BWD"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
+    from deepdfa_b200 import engine as E
+    for key, opts in (("default", {}), ("per_step_wgrad", {"batched_wgrad": False}), ("unfused_gather", {"fuse_gather_bwd": False})):
+        monkeypatch.setattr(E, "OPTIONS", dict({"fuse_gather_bwd": True, "batched_wgrad": True}, **opts))
         torch.manual_seed(11)
         m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 6, 2, concat_all_absdf=True, engine="tcgen05").to(DEV)
         loss = m.training_step((b, {}), 0)
@@ -400,6 +488,7 @@ def test_module_matches_reference_control_flow_goldens(engine):
     import os
     from deepdfa_b200.batched_graph import BatchedCFG
     data = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_ctrlflow_golden.pt"), weights_only=False)
+    checked_grads = 0
     for case in data["cases"]:
         gd = case["graph"]
         g = BatchedCFG(gd["src"], gd["dst"], gd["batch_num_nodes"], gd["ndata"])
@@ -422,4 +511,7 @@ def test_module_matches_reference_control_flow_goldens(engine):
             for k, p in m.named_parameters():
                 if k in case["grads"]:
                     ref = case["grads"][k]
-                    assert (p.grad.cpu() - ref).abs().max() < 2e-4 * max(1.0, float(ref.abs().max())), (case["name"], k)
+                    tol = 2e-4 if engine == "simt" else 2e-3
+                    assert (p.grad.cpu() - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), (case["name"], k)
+            checked_grads += 1
+    assert checked_grads >= 1, "no reference-code gradient case ran for this engine"
