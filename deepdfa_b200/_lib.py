@@ -62,6 +62,10 @@ _SIGNATURES = {
     "ddfa_act_to_image": (_int, [_vp, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum_image": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ddfa_gru_step_fwd_image": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddfa_gather_sum_image_src": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "ddfa_gru_gates_packed_bytes": (_sz, [_i32, _i32]),
+    "ddfa_gru_step_fwd_image_v2": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ddfa_gru_step_bwd_image_v2": (_int, [_vp] * 9 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd_image": (_int, [_vp] * 9 + [_i32, _i32] + [_vp] * 7 + [_vp, _sz, _int, _vp]),
     "ddfa_gru_step_bwd_finish": (_int, [_i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ddfa_gru_step_bwd_workspace_bytes": (_sz, [_i32, _i32, _int]),
@@ -83,7 +87,7 @@ _SIGNATURES = {
 
 TUNE_L2_HINTS, TUNE_PDL_MASK, TUNE_GATHER_VARIANT = 0, 1, 2
 
-_NO_STATUS = {"ddfa_tuning_get", "ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
+_NO_STATUS = {"ddfa_gru_gates_packed_bytes", "ddfa_tuning_get", "ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
               "ddfa_build_csr_workspace_bytes", "ddfa_arena_batch_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
               "ddfa_act_image_bytes", "ddfa_ggnn_workspace_bytes"}
 

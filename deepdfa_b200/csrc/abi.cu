@@ -77,6 +77,12 @@ int ddfa_debug_read(int key, void *host_out, size_t bytes) {
   switch (key) {   // [148 CTAs][12 tiles][12 events] int64 SM-clock stamps
     case 2: return ddfa::gru_tc2b_trace_read(host_out, bytes);    // dgrad3_kernel / wgrad_kernel
     case 3: return ddfa::gru_tc3_trace_read(host_out, bytes);     // gru_fwd3_kernel
+    case 4: {                                                     // int32: bounded-wait failures of the TMA-staged gather variants
+      DDFA_REQUIRE(bytes >= sizeof(int), "ddfa_debug_read: key 4 needs 4 bytes");
+      const int v = ddfa::gather_tma_errors();
+      memcpy(host_out, &v, sizeof(int));
+      return DDFA_OK;
+    }
     default: ddfa::set_error("ddfa_debug_read: unknown key %d", key); return DDFA_ERR_INVALID_ARG;
   }
 }

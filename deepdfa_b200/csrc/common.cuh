@@ -94,7 +94,7 @@ size_t gru_tc3_packed_bytes();
 int gru_tc3_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh, void *packed,
                     cudaStream_t stream);
 int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
-                     void *h_out_img, float *save_gates, const void *packed, cudaStream_t stream);
+                     void *h_out_img, float *save_gates, void *save_gates_packed, const void *packed, cudaStream_t stream);
 int gru_tc3_trace_enable(int on);   // pipeline timeline of gru_fwd3_kernel (development aid)
 int gru_tc3_trace_read(void *host, size_t bytes);
 int gru_tc2b_trace_enable(int on);  // pipeline timeline of dgrad3_kernel (value 1) / wgrad_kernel (value 2) — development aid
@@ -103,17 +103,23 @@ size_t gru_tc2_workspace_bytes();
 int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih, const float *w_hh, const float *b_hh,
                     void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
-                     void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                     void *h_out_img, float *save_gates, void *save_gates_packed, const void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
 // gru_tc_bwd.cu — tcgen05 engine, backward (gate backward -> q images, dgrad, wgrad)
 size_t gru_tc2_bwd_workspace_bytes(int32_t N, int32_t slots);
 void *gru_tc2_bwd_s_image_scratch(void *workspace, int32_t N);   // one image inside the workspace for the fp32-s entry point
 int gru_tc2_prepare_bwd(const float *w_fold, const float *w_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *indptr_t, const int32_t *indices_t, const float *h,
-                     const void *h_img_in, const void *s_img, const float *gates, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+                     const void *h_img_in, const void *s_img, const float *gates, const void *gates_packed, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
                      float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream);
 int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int gru_tc2_bwd_wgrad_batched(const void *const *s_imgs, const void *const *h_imgs, int32_t steps, int32_t N, float *dw_fold,
                               float *dw_hh, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// gather_tma.cu — TMA-staged variants (10: per-row bulk copies, 11: tensor-map gather4) of the D == 128 edge gather
+int launch_gather_tma(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N, float *out, int accumulate,
+                      cudaStream_t stream);
+int gather_tma_errors();   // bounded-wait failures since load (0 in a healthy run)
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
   float4 v;

@@ -221,6 +221,102 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
   }
 }
 
+// ---- D = 128, input AND output as activation images ------------------------------------------------------------------------
+// The same gather for the steps whose h_t exists only as its image (tcgen05 engine, t >= 1: the forward GRU kernel no longer
+// writes an fp32 copy of h').  A node's image row is four 128-byte pieces [hi | lo] x [cols 0-63 | 64-127]; lane l fetches one
+// 16-byte unit (8 bf16) of piece l / 8, un-swizzling by row & 7, accumulates hi and lo parts separately in fp32 and the two
+// halves of the warp are combined at the end: s = sum hi + sum lo (every term exact in fp32).  Same mapping as above otherwise.
+__global__ void __launch_bounds__(128) gather_sum_image_src_kernel(const int32_t *__restrict__ indptr,
+                                                                   const int32_t *__restrict__ indices,
+                                                                   const uint8_t *__restrict__ h_img, int32_t N,
+                                                                   uint8_t *__restrict__ out_img) {
+  constexpr int RW = 2, PASSES = 2, ROWS = RW * PASSES, UNROLL = 4;
+  const int lane = threadIdx.x & 31;
+  const int piece = lane >> 3, unit = lane & 7;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t v0 = warp_global * ROWS;
+  const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (v0 >= Npad) return;
+  const int nrows = (int)min((int64_t)ROWS, Npad - v0);
+  int32_t myptr = 0;
+  if (lane <= nrows) myptr = __ldcg(indptr + min(v0 + lane, (int64_t)N));
+  const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
+  const int32_t total = __shfl_sync(0xffffffffu, myptr, nrows) - beg0;
+  const int32_t pre = (lane < total) ? __ldcg(indices + beg0 + lane) : 0;
+#pragma unroll 1
+  for (int p = 0; p < PASSES; ++p) {
+    const int r0 = p * RW;
+    if (r0 >= nrows) break;
+    int32_t rend[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) rend[r] = __shfl_sync(0xffffffffu, myptr, min(r0 + r + 1, nrows)) - beg0;
+    const int32_t pbeg = __shfl_sync(0xffffffffu, myptr, r0) - beg0;
+    const int32_t pend = rend[RW - 1];
+    float acc[RW][8];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+    for (int32_t b = pbeg; b < pend; b += UNROLL) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const int32_t pos = min(b + j, pend - 1);
+        int32_t u = __shfl_sync(0xffffffffu, pre, pos & 31);
+        if (pos >= 32) u = __ldcg(indices + beg0 + pos);
+        const int row = u & 127;
+        const uint8_t *src = h_img + (size_t)(u >> 7) * 65536 + (size_t)piece * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4);
+        v[j] = (b + j < pend) ? __ldcg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const int32_t pos = b + j;
+        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const bool mine = (pos < rend[r]) && (r == 0 ? true : pos >= rend[r - 1]);
+          if (mine) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[r][2 * i] += __uint_as_float(w[i] << 16);
+              acc[r][2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (r0 + r < nrows) {            // warp-uniform
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = acc[r][i] + __shfl_down_sync(0xffffffffu, acc[r][i], 16);    // lanes 0-15: hi sums + lo sums
+        if (lane < 16) {
+          const int64_t node = v0 + r0 + r;
+          const int row = (int)(node & 127);
+          uint4 ph, pl;
+          // split8 lives in tc_common.cuh; restated here on packed words to keep gather.cu free of the tensor-core header
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+            hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4 *>(dst + (size_t)piece * 16384) = ph;          // piece = 0 | 1 here: hi chunk of cols 0-63 | 64-127
+          *reinterpret_cast<uint4 *>(dst + (size_t)(2 + piece) * 16384) = pl;
+        }
+      }
+    }
+  }
+}
+
 // Tuning variants for the D=128 case (selected by ddfa_gather_sum_variant / $DDFA_GATHER_VARIANT):
 //   id : RW UNROLL PASSES NIDX THREADS
 static int launch_d128_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h, int32_t N,
@@ -236,8 +332,11 @@ static int launch_d128_variant(int variant, const int32_t *indptr, const int32_t
     case 7: return launch_gather<32, 1, 1, 4, 8, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
     case 8: return launch_gather<32, 1, 4, 4, 2, 1, 256>(indptr, indices, h, N, 128, out, accumulate, stream);
     case 9: return launch_gather<32, 1, 2, 4, 2, 1, 128>(indptr, indices, h, N, 128, out, accumulate, stream);
+    case 10:      // gather_tma.cu: neighbour rows staged in shared memory by per-row TMA bulk copies
+    case 11:      // gather_tma.cu: ... by tensor-map tile::gather4 copies (four rows per instruction)
+      return launch_gather_tma(variant, indptr, indices, h, N, out, accumulate, stream);
     default:
-      set_error("ddfa_gather_sum_variant: unknown variant %d (0..9)", variant);
+      set_error("ddfa_gather_sum_variant: unknown variant %d (0..11)", variant);
       return DDFA_ERR_INVALID_ARG;
   }
 }
@@ -285,6 +384,22 @@ int ddfa_gather_sum_image(const int32_t *indptr, const int32_t *indices, const f
   DDFA_CUDA(launch_chain(1, gather_sum_image_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices, h, N,
                          static_cast<uint8_t *>(out_image), out_f32));
   DDFA_CHECK_LAUNCH("gather_sum_image_kernel");
+  return DDFA_OK;
+}
+
+int ddfa_gather_sum_image_src(const int32_t *indptr, const int32_t *indices, const void *h_image, int32_t N, int32_t D,
+                              void *out_image, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gather_sum_image_src: activation images exist for D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(indptr && indices && h_image && out_image && aligned16(h_image) && aligned16(out_image) && h_image != out_image,
+               "ddfa_gather_sum_image_src: NULL, unaligned or aliased pointer");
+  const int64_t rows = ((int64_t)N + 127) / 128 * 128;
+  const int64_t warps = (rows + 3) / 4;
+  const int64_t blocks = (warps * 32 + 127) / 128;
+  DDFA_CUDA(launch_chain(1, gather_sum_image_src_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices,
+                         static_cast<const uint8_t *>(h_image), N, static_cast<uint8_t *>(out_image)));
+  DDFA_CHECK_LAUNCH("gather_sum_image_src_kernel");
   return DDFA_OK;
 }
 

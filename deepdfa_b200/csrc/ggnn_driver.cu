@@ -12,7 +12,7 @@ namespace {
 struct GgnnLayout {
   // offsets into the workspace (bytes); 0-sized regions are unused for the given mode
   size_t w_fold, b_fold, dw_fold, db_fold, gru_ws, h, h_img, s, gates, bwd_ws, ds, dh, total;
-  size_t gru_ws_bytes, bwd_ws_bytes, plane, img;
+  size_t gru_ws_bytes, bwd_ws_bytes, plane, img, gate_step;
   int n_h, n_img, n_s;
 };
 
@@ -31,12 +31,13 @@ GgnnLayout make_layout(int32_t N, int32_t D, int32_t T, int engine, int training
   L.db_fold = take((size_t)3 * D * 4);
   L.gru_ws_bytes = ddfa_gru_step_workspace_bytes(tc ? 0 : N, D, engine);
   L.gru_ws = take(L.gru_ws_bytes < 16 ? 16 : L.gru_ws_bytes);
+  // tcgen05: h_1 .. h_{T-1} exist only as activation images (no fp32 planes); the saved gates are packed fp16 (2 planes' worth)
   if (training) {
-    L.n_h = T > 1 ? T - 1 : 0;                   // h_1 .. h_{T-1} (h_0 = x and h_T = h_out belong to the caller)
+    L.n_h = (!tc && T > 1) ? T - 1 : 0;          // simt: h_1 .. h_{T-1} (h_0 = x and h_T = h_out belong to the caller)
     L.n_img = tc ? T : 0;                        // images of h_0 .. h_{T-1}
     L.n_s = T;                                   // s_0 .. s_{T-1}: images (tcgen05) or fp32 planes (simt)
   } else {
-    L.n_h = T > 1 ? 2 : 0;                       // ping-pong
+    L.n_h = (!tc && T > 1) ? 2 : 0;              // ping-pong
     L.n_img = tc ? 2 : 0;
     L.n_s = 1;
   }
@@ -44,7 +45,8 @@ GgnnLayout make_layout(int32_t N, int32_t D, int32_t T, int engine, int training
   L.h_img = take((size_t)L.n_img * L.img);
   L.s = take((size_t)L.n_s * (tc ? L.img : L.plane));
   if (training) {
-    L.gates = take((size_t)T * 4 * L.plane);
+    L.gate_step = tc ? align256(ddfa_gru_gates_packed_bytes(N, D)) : 4 * L.plane;
+    L.gates = take((size_t)T * L.gate_step);
     L.bwd_ws_bytes = ddfa_gru_step_bwd_workspace_bytes_steps(N, D, engine, tc && T <= DDFA_WGRAD_MAX_STEPS ? T : 1);
     L.bwd_ws = take(L.bwd_ws_bytes < 16 ? 16 : L.bwd_ws_bytes);
     L.ds = take(2 * L.plane);
@@ -107,13 +109,16 @@ int ddfa_ggnn_fwd(const int32_t *indptr, const int32_t *indices, const float *x,
   if (tc) GGNN_TRY(ddfa_act_to_image(x, N, D, img_buf(0), stream));
   const float *h_cur = x;
   for (int t = 0; t < T; ++t) {
-    float *h_next = (t == T - 1) ? h_out : h_buf(t + 1);
-    float *g_t = training ? f32_at(workspace, L.gates + (size_t)t * 4 * L.plane) : nullptr;
+    float *g_t = training ? f32_at(workspace, L.gates + (size_t)t * L.gate_step) : nullptr;
     if (tc) {
-      GGNN_TRY(ddfa_gather_sum_image(indptr, indices, h_cur, N, D, s_buf(t), nullptr, stream));
-      GGNN_TRY(ddfa_gru_step_fwd_image(s_buf(t), img_buf(t), h_cur, indptr, N, D, h_next, t + 1 < T ? img_buf(t + 1) : nullptr, g_t, gws,
-                                       L.gru_ws_bytes, stream));
-    } else {
+      if (t == 0) GGNN_TRY(ddfa_gather_sum_image(indptr, indices, x, N, D, s_buf(t), nullptr, stream));
+      else GGNN_TRY(ddfa_gather_sum_image_src(indptr, indices, img_buf(t), N, D, s_buf(t), stream));
+      GGNN_TRY(ddfa_gru_step_fwd_image_v2(s_buf(t), img_buf(t), t == 0 ? x : nullptr, indptr, N, D, t == T - 1 ? h_out : nullptr,
+                                          t + 1 < T ? img_buf(t + 1) : nullptr, g_t, gws, L.gru_ws_bytes, stream));
+      continue;
+    }
+    float *h_next = (t == T - 1) ? h_out : h_buf(t + 1);
+    {
       float *s_t = reinterpret_cast<float *>(s_buf(t));
       GGNN_TRY(ddfa_gather_sum(indptr, indices, h_cur, N, D, s_t, 0, stream));
       GGNN_TRY(ddfa_gru_step_fwd(s_t, h_cur, indptr, w_fold, b_fold, b_ih, w_hh, b_hh, N, D, h_next, g_t, gws, L.gru_ws_bytes, engine, stream));
@@ -154,7 +159,7 @@ int ddfa_ggnn_bwd(const int32_t *indptr, const int32_t *indptr_t, const int32_t 
   DDFA_CUDA(cudaMemsetAsync(dw_fold, 0, (size_t)3 * D * D * 4, cs));
   DDFA_CUDA(cudaMemsetAsync(db_fold, 0, (size_t)3 * D * 4, cs));
   GGNN_TRY(ddfa_gru_step_prepare_bwd(w_fold, w_hh, D, engine, bws, L.bwd_ws_bytes, stream));
-  auto h_at = [&](int t) -> const float * { return t == 0 ? x : f32_at(workspace, L.h + (size_t)(t - 1) * L.plane); };
+  auto h_at = [&](int t) -> const float * { return t == 0 ? x : (tc ? nullptr : f32_at(workspace, L.h + (size_t)(t - 1) * L.plane)); };
   auto img_at = [&](int t) { return u8_at(workspace, L.h_img + (size_t)t * L.img); };
   auto s_at = [&](int t) { return u8_at(workspace, L.s + (size_t)t * (tc ? L.img : L.plane)); };
   float *ds_buf[2] = {f32_at(workspace, L.ds), f32_at(workspace, L.ds + L.plane)};
@@ -164,12 +169,12 @@ int ddfa_ggnn_bwd(const int32_t *indptr, const int32_t *indptr_t, const int32_t 
   for (int t = T - 1; t >= 0; --t) {
     float *ds_t = ds_buf[t & 1];
     float *dh_t = (t == 0) ? dx : dh_buf[t & 1];          // the last step writes dL/dh_0 straight into dx
-    const float *g_t = f32_at(workspace, L.gates + (size_t)t * 4 * L.plane);
+    const float *g_t = f32_at(workspace, L.gates + (size_t)t * L.gate_step);
     if (tc) {
       // incoming gradient = dh_in + A^T ds_prev: the transposed gather of the previous call's ds rides inside the call
-      GGNN_TRY(ddfa_gru_step_bwd_image(dh_in, ds_prev, indptr_t, indices_t, h_at(t), img_at(t), s_at(t), g_t, indptr, N, D, ds_t, dh_t, dw_fold,
-                                       db_fold, db_ih, dw_hh, db_hh, bws, L.bwd_ws_bytes,
-                                       batched ? DDFA_WGRAD_KEEP(t) : (t == T - 1 ? 1 : 2), stream));
+      GGNN_TRY(ddfa_gru_step_bwd_image_v2(dh_in, ds_prev, indptr_t, indices_t, h_at(t), img_at(t), s_at(t), g_t, indptr, N, D, ds_t, dh_t,
+                                          dw_fold, db_fold, db_ih, dw_hh, db_hh, bws, L.bwd_ws_bytes,
+                                          batched ? DDFA_WGRAD_KEEP(t) : (t == T - 1 ? 1 : 2), stream));
       ds_prev = ds_t;
     } else {
       GGNN_TRY(ddfa_gru_step_bwd(dh_in, h_at(t), reinterpret_cast<const float *>(s_at(t)), g_t, indptr, w_fold, w_hh, N, D, ds_t, dh_t, dw_fold,

@@ -227,7 +227,21 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
   DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_fwd_image: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
   if (N == 0) return DDFA_OK;
   DDFA_REQUIRE(s_image && h_image && h && indptr && h_out, "ddfa_gru_step_fwd_image: NULL pointer");
-  return gru_tc2_step_fwd(s_image, h_image, h, indptr, N, h_out, h_out_image, save_gates, workspace, workspace_bytes,
+  return gru_tc2_step_fwd(s_image, h_image, h, indptr, N, h_out, h_out_image, save_gates, nullptr, workspace, workspace_bytes,
+                          as_stream(stream_));
+}
+
+size_t ddfa_gru_gates_packed_bytes(int32_t N, int32_t D) { return (N < 0 || D <= 0) ? 0 : (size_t)N * (size_t)D * 8; }
+
+int ddfa_gru_step_fwd_image_v2(const void *s_image, const void *h_image, const float *h, const int32_t *indptr, int32_t N, int32_t D,
+                               float *h_out, void *h_out_image, void *save_gates_packed, const void *workspace, size_t workspace_bytes,
+                               void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_fwd_image_v2: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(s_image && h_image && indptr, "ddfa_gru_step_fwd_image_v2: NULL pointer");
+  DDFA_REQUIRE(h_out || h_out_image, "ddfa_gru_step_fwd_image_v2: neither h_out nor h_out_image given");
+  return gru_tc2_step_fwd(s_image, h_image, h, indptr, N, h_out, h_out_image, nullptr, save_gates_packed, workspace, workspace_bytes,
                           as_stream(stream_));
 }
 
@@ -275,7 +289,7 @@ int ddfa_gru_step_fwd(const float *s, const float *h, const int32_t *indptr, con
     if (rc) return rc;
     rc = act_to_image(h, N, h_img, stream);
     if (rc) return rc;
-    return gru_tc2_step_fwd(s_img, h_img, h, indptr, N, h_out, nullptr, save_gates, workspace, workspace_bytes, stream);
+    return gru_tc2_step_fwd(s_img, h_img, h, indptr, N, h_out, nullptr, save_gates, nullptr, workspace, workspace_bytes, stream);
   }
   float *gi = static_cast<float *>(workspace);
   float *gh = gi + (size_t)N * 3 * D;
@@ -324,8 +338,27 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int
   DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image: dh must not alias dh_out");
   DDFA_REQUIRE(ds_prev == nullptr || (indptr_t && indices_t), "ddfa_gru_step_bwd_image: ds_prev given without the transposed CSR");
   DDFA_REQUIRE(ds_prev == nullptr || ds_prev != ds, "ddfa_gru_step_bwd_image: ds must not alias ds_prev");
-  return gru_tc2_step_bwd(dh_out, ds_prev, indptr_t, indices_t, h, h_image, s_image, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
+  return gru_tc2_step_bwd(dh_out, ds_prev, indptr_t, indices_t, h, h_image, s_image, gates, nullptr, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh, workspace,
                           workspace_bytes, wgrad_mode, as_stream(stream_));
+}
+
+int ddfa_gru_step_bwd_image_v2(const float *dh_out, const float *ds_prev, const int32_t *indptr_t, const int32_t *indices_t,
+                               const float *h, const void *h_image, const void *s_image, const void *gates_packed,
+                               const int32_t *indptr, int32_t N, int32_t D, float *ds, float *dh, float *dw_fold, float *db_fold,
+                               float *db_ih, float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode,
+                               void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(N >= 0 && D == 128, "ddfa_gru_step_bwd_image_v2: the tcgen05 engine supports D == 128 only (N=%d D=%d)", N, D);
+  DDFA_REQUIRE((wgrad_mode >= 0 && wgrad_mode <= 2) || (wgrad_mode >= 16 && wgrad_mode < 32),
+               "ddfa_gru_step_bwd_image_v2: wgrad_mode must be 0, 1, 2 or DDFA_WGRAD_KEEP(slot < 16) (got %d)", wgrad_mode);
+  if (N == 0) return DDFA_OK;
+  DDFA_REQUIRE(dh_out && h_image && s_image && gates_packed && indptr && ds && dh && dw_fold && db_fold && db_ih && dw_hh && db_hh,
+               "ddfa_gru_step_bwd_image_v2: NULL pointer");
+  DDFA_REQUIRE(dh != dh_out, "ddfa_gru_step_bwd_image_v2: dh must not alias dh_out");
+  DDFA_REQUIRE(ds_prev == nullptr || (indptr_t && indices_t), "ddfa_gru_step_bwd_image_v2: ds_prev given without the transposed CSR");
+  DDFA_REQUIRE(ds_prev == nullptr || ds_prev != ds, "ddfa_gru_step_bwd_image_v2: ds must not alias ds_prev");
+  return gru_tc2_step_bwd(dh_out, ds_prev, indptr_t, indices_t, h, h_image, s_image, nullptr, gates_packed, indptr, N, ds, dh, dw_fold, db_fold,
+                          db_ih, dw_hh, db_hh, workspace, workspace_bytes, wgrad_mode, as_stream(stream_));
 }
 
 int ddfa_gru_step_bwd_finish(int32_t N, int32_t D, float *dw_fold, float *dw_hh, void *workspace, size_t workspace_bytes,
@@ -368,7 +401,7 @@ int ddfa_gru_step_bwd(const float *dh_out, const float *h, const float *s, const
     void *s_img = gru_tc2_bwd_s_image_scratch(workspace, N);
     rc = act_to_image(s, N, s_img, stream);
     if (rc) return rc;
-    return gru_tc2_step_bwd(dh_out, nullptr, nullptr, nullptr, h, /*h_img_in=*/nullptr, s_img, gates, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,
+    return gru_tc2_step_bwd(dh_out, nullptr, nullptr, nullptr, h, /*h_img_in=*/nullptr, s_img, gates, nullptr, indptr, N, ds, dh, dw_fold, db_fold, db_ih, dw_hh, db_hh,
                             workspace, workspace_bytes, /*wgrad_mode=*/0, stream);
   }
   float *dgi = static_cast<float *>(workspace);

@@ -15,6 +15,8 @@
 //         its [384 x 128] fp32 partial sum in TMEM over all its tiles and folds it into a private global partial at the
 //         end; wgrad_reduce_kernel sums the partials once per backward pass.
 // Precision: bf16x3 everywhere (hi*hi + hi*lo + lo*hi), fp32 accumulate.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace ddfa {
@@ -36,8 +38,16 @@ struct GbRow {
   float deg;
   int tb, te;      // this row's neighbour range in the transposed CSR (fused gather)
 };
+__device__ __forceinline__ float4 bf16x4_to_f4(const uint2 &p) {
+  return make_float4(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xffff0000u), __uint_as_float(p.y << 16), __uint_as_float(p.y & 0xffff0000u));
+}
+// Two forms of the saved forward state:
+//   fp32:   h = [N,128] plane, gates = four [N,128] planes (r, z, n, gh_n)                       (ddfa_gru_step_bwd_image)
+//   packed: h = the activation image the forward GEMM read (hi + lo), gates_packed = [N,128] x {half2(r,z), half2(n,gh_n)}
+//           — 64 instead of 96 bytes per lane-row                                               (ddfa_gru_step_bwd_image_v2)
 __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_out, const float *__restrict__ h,
-                                        const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                        const uint8_t *__restrict__ h_img_src, const float *__restrict__ gates,
+                                        const uint4 *__restrict__ gates_packed, const int32_t *__restrict__ indptr,
                                         const int32_t *__restrict__ indptr_t, size_t plane, int64_t node, int col, bool ok,
                                         uint64_t pol_saved, uint64_t pol_dh) {
   x.tb = x.te = 0;
@@ -45,17 +55,44 @@ __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_o
     if (indptr_t) { x.tb = __ldcg(indptr_t + node); x.te = __ldcg(indptr_t + node + 1); }
     const size_t off = (size_t)node * kD + col;
     x.d = ldg_cg_f4_hint(dh_out + off, pol_dh);
-    x.hv = ldg_cg_f4_hint(h + off, pol_saved);                 // saved activations: last use
-    x.rr = ldg_cg_f4_hint(gates + off, pol_saved);
-    x.zz = ldg_cg_f4_hint(gates + plane + off, pol_saved);
-    x.nn = ldg_cg_f4_hint(gates + 2 * plane + off, pol_saved);
-    x.gh = ldg_cg_f4_hint(gates + 3 * plane + off, pol_saved);
+    uint2 hh = make_uint2(0u, 0u), hl = hh;
+    uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+    if (h) x.hv = ldg_cg_f4_hint(h + off, pol_saved);                 // saved activations: last use
+    else {
+      hh = __ldcg(reinterpret_cast<const uint2 *>(h_img_src + image_offset(node, col, 0)));
+      hl = __ldcg(reinterpret_cast<const uint2 *>(h_img_src + image_offset(node, col, 1)));
+    }
+    if (gates) {
+      x.rr = ldg_cg_f4_hint(gates + off, pol_saved);
+      x.zz = ldg_cg_f4_hint(gates + plane + off, pol_saved);
+      x.nn = ldg_cg_f4_hint(gates + 2 * plane + off, pol_saved);
+      x.gh = ldg_cg_f4_hint(gates + 3 * plane + off, pol_saved);
+    } else {
+      g0 = __ldcg(gates_packed + (off >> 1));          // columns col, col+1: {rz, ng, rz, ng}
+      g1 = __ldcg(gates_packed + (off >> 1) + 1);      // columns col+2, col+3
+    }
     x.deg = (float)(__ldcg(indptr + node + 1) - __ldcg(indptr + node));
+    if (!h) {
+      const float4 a = bf16x4_to_f4(hh), b = bf16x4_to_f4(hl);
+      x.hv = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    if (!gates) {
+      const float2 rz0 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.x)), ng0 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.y));
+      const float2 rz1 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.z)), ng1 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.w));
+      const float2 rz2 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.x)), ng2 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.y));
+      const float2 rz3 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.z)), ng3 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.w));
+      x.rr = make_float4(rz0.x, rz1.x, rz2.x, rz3.x);
+      x.zz = make_float4(rz0.y, rz1.y, rz2.y, rz3.y);
+      x.nn = make_float4(ng0.x, ng1.x, ng2.x, ng3.x);
+      x.gh = make_float4(ng0.y, ng1.y, ng2.y, ng3.y);
+    }
   }
 }
 
 __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
-                                                                          const float *__restrict__ gates, const int32_t *__restrict__ indptr,
+                                                                          const uint8_t *__restrict__ h_img_src,
+                                                                          const float *__restrict__ gates, const uint4 *__restrict__ gates_packed,
+                                                                          const int32_t *__restrict__ indptr,
                                                                           const float *__restrict__ ds_in, const int32_t *__restrict__ indptr_t,
                                                                           const int32_t *__restrict__ indices_t,
                                                                           int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
@@ -110,8 +147,8 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
     const int64_t node2 = node + stride;
     GbRow a, b;
     const bool ok_a = node < N, ok_b = node2 < N;
-    gb_load(a, dh_out, h, gates, indptr, indptr_t, plane, node, col, ok_a, pol_saved, pol_dh);
-    gb_load(b, dh_out, h, gates, indptr, indptr_t, plane, node2, col, ok_b, pol_saved, pol_dh);
+    gb_load(a, dh_out, h, h_img_src, gates, gates_packed, indptr, indptr_t, plane, node, col, ok_a, pol_saved, pol_dh);
+    gb_load(b, dh_out, h, h_img_src, gates, gates_packed, indptr, indptr_t, plane, node2, col, ok_b, pol_saved, pol_dh);
     if (indptr_t) {
       // dh' += sum over the transposed-graph neighbours of ds_in: first up to 4 neighbour ids of both rows, then their
       // rows, all loads of a phase in flight together; longer lists finish in a plain loop (deterministic order)
@@ -639,8 +676,12 @@ int gru_tc2_bwd_finish(int32_t N, float *dw_fold, float *dw_hh, void *workspace,
 // h_img_in: the activation image of h (kept from the forward pass) or NULL (then it is rebuilt inside the workspace).
 // ds_in / indptr_t / indices_t: NULL, or the incoming gradient is dh_out + A^T ds_in (A^T as a CSR over the transposed graph)
 int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *indptr_t, const int32_t *indices_t, const float *h,
-                     const void *h_img_in, const void *s_img, const float *gates, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
+                     const void *h_img_in, const void *s_img, const float *gates, const void *gates_packed, const int32_t *indptr, int32_t N, float *ds, float *dh, float *dw_fold, float *db_fold, float *db_ih,
                      float *dw_hh, float *db_hh, void *workspace, size_t workspace_bytes, int wgrad_mode, cudaStream_t stream) {
+  if (h == nullptr && h_img_in == nullptr) {
+    set_error("tcgen05 engine (bwd): neither the fp32 h nor its activation image given");
+    return DDFA_ERR_INVALID_ARG;
+  }
   const int q_slot = wgrad_mode >= 16 ? wgrad_mode - 16 : 0;
   if (workspace == nullptr || workspace_bytes < gru_tc2_bwd_workspace_bytes(N, q_slot + 1)) {
     set_error("tcgen05 engine (bwd): workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_bwd_workspace_bytes(N, q_slot + 1));
@@ -659,7 +700,8 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     const int64_t want = (rows + tc2b::kGbWarps - 1) / tc2b::kGbWarps;
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
-  DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h, gates, indptr, ds_in,
+  DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h,
+                         static_cast<const uint8_t *>(h_img_in), gates, static_cast<const uint4 *>(gates_packed), indptr, ds_in,
                          ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh,
                          l2_hints()));
   DDFA_CHECK_LAUNCH("tc2b::gate_bwd_image_kernel");

@@ -21,6 +21,7 @@
 //     32-node quarter of the tile) each read 16 nodes per tcgen05.ld, swap them through a warp-private, conflict-free
 //     shared-memory tile (thread (gate, c) -> thread (node mod 4, c)), and finish nodes {g, g+4, g+8, g+12} x column c:
 //     no cross-warp barrier anywhere in the epilogue; global accesses are 32-byte row segments (full sectors).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -95,11 +96,14 @@ __global__ void pack_kernel(const float *__restrict__ w_fold, const float *__res
   }
 }
 
+// HIMG: the z*h term reads h from the activation image (h == nullptr) instead of an fp32 plane.
+// GATES: 0 = nothing saved (inference), 1 = four fp32 planes (`gates`), 2 = packed fp16 (`gates_packed`).
+template <bool HIMG, int GATES>
 __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
                                                                const float *__restrict__ h, const int32_t *__restrict__ indptr,
                                                                const uint8_t *__restrict__ packed, int32_t N,
                                                                float *__restrict__ h_out, uint8_t *__restrict__ h_out_img,
-                                                               float *__restrict__ gates, int hints) {
+                                                               float *__restrict__ gates, uint2 *__restrict__ gates_packed, int hints) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();        // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -239,15 +243,25 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     // fetched one tile ahead, so their latency hides behind the current tile's work
     // All loads are L2 loads (PDL rules, common.cuh).  The in-degrees of the warp's 32 nodes come in as two coalesced loads
     // (lane = node) and are handed to the threads that need them by shuffles at use time.
+    // h itself: fp32 plane when the caller has one (h_0 = the embeddings), else reconstructed from the activation image the
+    // MMA reads (h = hi + lo, 2^-17 relative): the even lane of a column pair fetches the pair's hi word, the odd lane its lo
+    // word — the same 4-byte pieces, at the same offsets, as the image stores below — and they swap at use time.
     float hp_n[8];
     int ip0_n = 0, ip1_n = 0;    // raw indptr entries of node nw + lane: the subtraction waits until the values are used
     auto prefetch = [&](int kk) {
       const int64_t nw = (int64_t)(group + kk * num_groups) * kTileM + e * 32;
+      if constexpr (!HIMG) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t node = nw + (i >> 2) * 16 + g + 4 * (i & 3);
-        const bool ok = kk < my_tiles && node < N;
-        hp_n[i] = ok ? __ldcg(h + node * kD + gcol) : 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int64_t node = nw + (i >> 2) * 16 + g + 4 * (i & 3);
+          const bool ok = kk < my_tiles && node < N;
+          hp_n[i] = ok ? __ldcg(h + node * kD + gcol) : 0.f;
+        }
+      } else {
+        const uint8_t *src = h_img + (size_t)(group + kk * num_groups) * kImageTileBytes + img_chunk_off + (size_t)e * 4096;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)      // i = 4 ch + j  ->  8-row group 2 ch + (j >> 1), row & 7 = g + 4 (j & 1); rows past N are zero in the image
+          hp_n[i] = kk < my_tiles ? __uint_as_float(__ldcg(reinterpret_cast<const uint32_t *>(src + ((i >> 2) * 2 + ((i & 3) >> 1)) * 1024 + img_lane_off[i & 1]))) : 0.f;
       }
       const bool okl = kk < my_tiles && nw + lane < N;
       ip0_n = okl ? __ldcg(indptr + nw + lane) : 0;
@@ -262,6 +276,15 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       float hp[8], deg[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) hp[i] = hp_n[i];
+      if constexpr (HIMG) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t mine = __float_as_uint(hp[i]), other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          const uint32_t w_hi = (c & 1) ? other : mine, w_lo = (c & 1) ? mine : other;      // (col pair) hi word, lo word
+          hp[i] = (c & 1) ? __uint_as_float(w_hi & 0xffff0000u) + __uint_as_float(w_lo & 0xffff0000u)
+                          : __uint_as_float(w_hi << 16) + __uint_as_float(w_lo << 16);
+        }
+      }
       {
         const float dl = (float)(ip1_n - ip0_n);           // in-degree of node node_w + lane
 #pragma unroll
@@ -283,8 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       // Addresses: every output of this thread is (per-tile base) + (compile-time offset): node = node_w + 16 ch + g + 4 j, so
       // row-major planes move by (16 ch + 4 j) rows, and inside the image the 8-row group index is 4 e + 2 ch + (j >> 1) while
       // row & 7 = g + 4 (j & 1) selects one of two swizzle offsets computed once per kernel (img_lane_off).
-      float *const ho = h_out + (node_w + g) * kD + gcol;
-      float *const gp0 = gates ? gates + (node_w + g) * kD + gcol : nullptr;
+      float *const ho = h_out ? h_out + (node_w + g) * kD + gcol : nullptr;
+      float *const gp0 = GATES == 1 ? gates + (node_w + g) * kD + gcol : nullptr;
+      uint2 *const gpk = GATES == 2 ? gates_packed + (node_w + g) * kD + gcol : nullptr;
       uint8_t *const ip = h_out_img ? h_out_img + (size_t)tile * kImageTileBytes + img_chunk_off + (size_t)e * 4096 : nullptr;
       // (one code path: a separate predicate-free body for full tiles was faster in isolation, 48 vs 53 us, but pushed the kernel
       // past the instruction cache — 43 KB of SASS — and lost in the real step, 54.7 vs 53.5 us: profiles/r02j)
@@ -308,8 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
             const int row_off = (ch * 16 + 4 * j) * kD;
             if (valid) {
-              st_f32_hint(ho + row_off, hnew, pol_next);
-              if (gp0) {
+              if (ho) st_f32_hint(ho + row_off, hnew, pol_next);
+              if constexpr (GATES == 2) {     // the four saved gate values of an element as ONE 8-byte store: half2(r, z), half2(n, gh_n)
+                const __half2 rz = __floats2half2_rn(r, z), ng = __floats2half2_rn(n, ghn);
+                st_u2_hint(gpk + row_off, make_uint2(*reinterpret_cast<const uint32_t *>(&rz), *reinterpret_cast<const uint32_t *>(&ng)), pol_gates);
+              }
+              if constexpr (GATES == 1) {
                 st_f32_hint(gp0 + row_off, r, pol_gates);
                 st_f32_hint(gp0 + plane + row_off, z, pol_gates);
                 st_f32_hint(gp0 + 2 * plane + row_off, n, pol_gates);
@@ -356,14 +384,35 @@ int gru_tc3_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
 }
 
 int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
-                     void *h_out_img, float *save_gates, const void *packed, cudaStream_t stream) {
+                     void *h_out_img, float *save_gates, void *save_gates_packed, const void *packed, cudaStream_t stream) {
   const int tiles = (N + tcc::kTileM - 1) / tcc::kTileM;
-  DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc));
   int groups = kNumSMs / tc3::kSlices;
   if (groups > tiles) groups = tiles;
-  DDFA_CUDA(launch_chain(2, tc3::gru_fwd3_kernel, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc, stream,
-                         static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,
-                         static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates, l2_hints()));
+  if (save_gates && save_gates_packed) {
+    set_error("tcgen05 engine (fwd): both gate formats requested");
+    return DDFA_ERR_INVALID_ARG;
+  }
+  if ((h == nullptr && save_gates) ) {
+    set_error("tcgen05 engine (fwd): fp32 gate planes go with the fp32 h operand (legacy form)");
+    return DDFA_ERR_INVALID_ARG;
+  }
+#define DDFA_FWD3_LAUNCH(HIMG, GATES)                                                                                                  \
+  do {                                                                                                                                 \
+    DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel<HIMG, GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc)); \
+    DDFA_CUDA(launch_chain(2, tc3::gru_fwd3_kernel<HIMG, GATES>, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc,  \
+                           stream, static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,               \
+                           static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates,              \
+                           static_cast<uint2 *>(save_gates_packed), l2_hints()));                                                      \
+  } while (0)
+  if (h) {
+    if (save_gates) DDFA_FWD3_LAUNCH(false, 1);
+    else if (save_gates_packed) DDFA_FWD3_LAUNCH(false, 2);
+    else DDFA_FWD3_LAUNCH(false, 0);
+  } else {
+    if (save_gates_packed) DDFA_FWD3_LAUNCH(true, 2);
+    else DDFA_FWD3_LAUNCH(true, 0);
+  }
+#undef DDFA_FWD3_LAUNCH
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
   return DDFA_OK;
 }
@@ -412,12 +461,13 @@ int gru_tc2_prepare(const float *w_fold, const float *b_fold, const float *b_ih,
 }
 
 int gru_tc2_step_fwd(const void *s_img, const void *h_img, const float *h, const int32_t *indptr, int32_t N, float *h_out,
-                     void *h_out_img, float *save_gates, const void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     void *h_out_img, float *save_gates, void *save_gates_packed, const void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < gru_tc2_workspace_bytes()) {
     set_error("tcgen05 engine: workspace too small (%zu < %zu)", workspace_bytes, gru_tc2_workspace_bytes());
     return DDFA_ERR_WORKSPACE;
   }
-  return gru_tc3_step_fwd(s_img, h_img, h, indptr, N, h_out, h_out_img, save_gates, workspace, stream);
+  return gru_tc3_step_fwd(s_img, h_img, h, indptr, N, h_out, h_out_img, save_gates, save_gates_packed, workspace, stream);
 }
 
 int gru_tc3_trace_enable(int on) {

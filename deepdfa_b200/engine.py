@@ -31,8 +31,11 @@ def _p(t: Optional[torch.Tensor]) -> int:
 # Execution options of the backward pass (A/B switches for scripts and tests; both settings of each run the CUDA kernels):
 #   fuse_gather_bwd: the transposed edge gather of step t+1's ds rides in step t's gate_bwd launch (tcgen05 engine)
 #   batched_wgrad:   ONE weight-gradient launch over all T steps instead of a deferred accumulation per step
+#   packed_state:    tcgen05 engine: h_t kept only as its activation image and the saved gates as packed fp16 (round-2 form, the
+#                    default); False = the round-1 form (fp32 copy of every h_t, four fp32 gate planes) for whole-step A/Bs
 OPTIONS = {"fuse_gather_bwd": os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0",
-           "batched_wgrad": os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0"}
+           "batched_wgrad": os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0",
+           "packed_state": os.environ.get("DDFA_PACKED_STATE", "1") != "0"}
 
 # Optional timing hook (bench.py): an object with begin(name) / end(name) that records CUDA events
 # on the current stream around selected C-ABI calls.  None (default) costs nothing.
@@ -157,9 +160,9 @@ class Saved:
     T: int
     D: int
     x: torch.Tensor
-    h: List[torch.Tensor]            # h[0..T]
-    s: List[torch.Tensor]            # s[0..T-1]
-    gates: List[torch.Tensor]        # [4,N,D] per step
+    h: List[Optional[torch.Tensor]]  # h[0..T] fp32; tcgen05 engine: only h[0] = x and h[T], the others live as images (None here)
+    s: List[torch.Tensor]            # s[0..T-1] (tcgen05: activation images)
+    gates: List[torch.Tensor]        # per step: [4,N,D] fp32 planes (simt) or packed {half2(r,z), half2(n,gh_n)} bytes (tcgen05)
     w_fold: torch.Tensor
     b_fold: torch.Tensor
     pooled: torch.Tensor
@@ -273,33 +276,63 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
            _p(ws), ws_bytes, st)
     hs, ss, gs = [x], [], []
     h_cur = x
-    if use_images:
+    if use_images and not OPTIONS["packed_state"]:
+        # round-1 form (A/B only): fp32 copy of every h_t next to its image, four fp32 gate planes per step
         img_bytes = L.call("ddfa_act_image_bytes", N)
-        # training keeps the image of every h_t (the weight-gradient GEMM reads it); inference ping-pongs two
         n_img = T if training else 2
         h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(max(n_img, 1))]
         L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
-    for t in range(T):
-        if training:
-            # with images, s_t is kept only as its image (same bytes as fp32); the backward GEMMs read it directly
-            s_t = alloc.get_zeroed(f"s_img{t}", (img_bytes,), torch.uint8) if use_images else alloc.get(f"s{t}", (N, D))
-            h_next = alloc.get(f"h{t + 1}", (N, D))
-            g_t = alloc.get(f"gates{t}", (4, N, D))
-        else:
-            s_t = alloc.get_zeroed("s_img", (img_bytes,), torch.uint8) if use_images else alloc.get("s", (N, D))
-            h_next = alloc.get(f"hpp{t % 2}", (N, D))
-            g_t = None
-        if use_images:
+        for t in range(T):
+            s_t = alloc.get_zeroed(f"s_img{t}" if training else "s_img", (img_bytes,), torch.uint8)
+            h_next = alloc.get(f"h{t + 1}" if training else f"hpp{t % 2}", (N, D))
+            g_t = alloc.get(f"gates{t}", (4, N, D)) if training else None
             _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), None, st, tag="gather_fwd")
             _call("ddfa_gru_step_fwd_image", _p(s_t), _p(h_imgs[t % n_img]), _p(h_cur), _p(dg.indptr), N, D, _p(h_next),
                   _p(h_imgs[(t + 1) % n_img]) if t + 1 < T else None, _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
-        else:
+            if training:
+                hs.append(h_next); ss.append(s_t); gs.append(g_t)
+            h_cur = h_next
+    elif use_images:
+        # tcgen05 engine: between steps h_t exists ONLY as its activation image (the GEMM operand; h = hi + lo to 2^-17) — the
+        # gather, the z*h term and the backward pass read that; fp32 copies exist of h_0 = x and of h_T (for the readout).  The
+        # four saved gate values of an element travel as one 8-byte {half2(r,z), half2(n,gh_n)} word.
+        img_bytes = L.call("ddfa_act_image_bytes", N)
+        gate_bytes = L.call("ddfa_gru_gates_packed_bytes", N, D)
+        n_img = T if training else 2          # training keeps the image of every h_t (the weight-gradient GEMM reads it)
+        h_imgs = [alloc.get_zeroed(f"h_img{i}", (img_bytes,), torch.uint8) for i in range(max(n_img, 1))]
+        L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
+        for t in range(T):
+            last = t == T - 1
+            s_t = alloc.get_zeroed(f"s_img{t}" if training else "s_img", (img_bytes,), torch.uint8)
+            g_t = alloc.get(f"gates_pk{t}", (gate_bytes,), torch.uint8) if training else None
+            h_in_img = h_imgs[t % n_img]
+            if t == 0:
+                _call("ddfa_gather_sum_image", _p(dg.indptr), _p(dg.indices), _p(x), N, D, _p(s_t), None, st, tag="gather_fwd")
+            else:
+                _call("ddfa_gather_sum_image_src", _p(dg.indptr), _p(dg.indices), _p(h_in_img), N, D, _p(s_t), st, tag="gather_fwd")
+            h_next = alloc.get("h_final", (N, D)) if last else None
+            _call("ddfa_gru_step_fwd_image_v2", _p(s_t), _p(h_in_img), _p(x) if t == 0 else None, _p(dg.indptr), N, D, _p(h_next),
+                  None if last else _p(h_imgs[(t + 1) % n_img]), _p(g_t), _p(ws), ws_bytes, st, tag="ddfa_gru_step_fwd")
+            if training:
+                hs.append(h_next); ss.append(s_t); gs.append(g_t)
+            if last:
+                h_cur = h_next
+    else:
+        for t in range(T):
+            if training:
+                s_t = alloc.get(f"s{t}", (N, D))
+                h_next = alloc.get(f"h{t + 1}", (N, D))
+                g_t = alloc.get(f"gates{t}", (4, N, D))
+            else:
+                s_t = alloc.get("s", (N, D))
+                h_next = alloc.get(f"hpp{t % 2}", (N, D))
+                g_t = None
             _call("ddfa_gather_sum", _p(dg.indptr), _p(dg.indices), _p(h_cur), N, D, _p(s_t), 0, st, tag="gather_fwd")
             _call("ddfa_gru_step_fwd", _p(s_t), _p(h_cur), _p(dg.indptr), _p(w_fold), _p(b_fold), _p(params.b_ih),
                   _p(params.w_hh), _p(params.b_hh), N, D, _p(h_next), _p(g_t), _p(ws), ws_bytes, engine, st)
-        if training:
-            hs.append(h_next); ss.append(s_t); gs.append(g_t)
-        h_cur = h_next
+            if training:
+                hs.append(h_next); ss.append(s_t); gs.append(g_t)
+            h_cur = h_next
 
     pooled = alloc.get("pooled", (B, 2 * D))
     logits = alloc.get("logits", (B,)) if nl > 0 else None
@@ -319,8 +352,11 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
 
 
 def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack, *, dlogits: Optional[torch.Tensor] = None,
-             dpooled: Optional[torch.Tensor] = None, engine: int = ENGINE_SIMT, alloc=None):
-    """Accumulates (+=) parameter gradients into ``grads``.  Exactly one of dlogits / dpooled is given."""
+             dpooled: Optional[torch.Tensor] = None, engine: int = ENGINE_SIMT, alloc=None, on_small_grads_ready=None):
+    """Accumulates (+=) parameter gradients into ``grads``.  Exactly one of dlogits / dpooled is given.
+    ``on_small_grads_ready``: called once every gradient EXCEPT those of ggnn.linears[0] and the GRU weight matrices (w_msg,
+    b_msg, w_ih, w_hh) is final — with the tcgen05 engine that is before the batched weight-gradient launch, so a data-parallel
+    trainer can start reducing them while that launch runs."""
     L = _lib.lib()
     dev = dg.device
     alloc = alloc or _FreshAlloc(dev)
@@ -367,8 +403,9 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
     L.call("ddfa_gru_step_prepare_bwd", _p(saved.w_fold), _p(params.w_hh), D, engine, _p(ws), ws_bytes, st)
     for t in range(T - 1, -1, -1):
         if engine == ENGINE_TCGEN05:     # saved.s[t] is the activation image of s_t
-            _call("ddfa_gru_step_bwd_image", _p(dh), _p(ds_prev), _p(dg.indptr_t), _p(dg.indices_t), _p(saved.h[t]),
-                  _p(saved.h_img[t]) if saved.h_img else None, _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
+            _call("ddfa_gru_step_bwd_image_v2" if saved.gates[t].dtype == torch.uint8 else "ddfa_gru_step_bwd_image",
+                  _p(dh), _p(ds_prev), _p(dg.indptr_t), _p(dg.indices_t), _p(saved.h[t]),
+                  _p(saved.h_img[t]), _p(saved.s[t]), _p(saved.gates[t]), _p(dg.indptr), N, D,
                   _p(ds), _p(dh_alt), _p(dw_fold), _p(db_fold), _p(grads.b_ih), _p(grads.w_hh), _p(grads.b_hh), _p(ws), ws_bytes,
                   (16 + t) if batched_wgrad else (1 if t == T - 1 else 2), st, tag="ddfa_gru_step_bwd")   # deferred weight gradient
             if fuse_gather:
@@ -382,9 +419,13 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
         # dh_t += A^T ds   (gather over the transposed graph)
         _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds), N, D, _p(dh_alt), 1, st, tag="gather_bwd")
         dh, dh_alt = dh_alt, dh
+    if engine == ENGINE_TCGEN05 and T > 0 and fuse_gather:     # the gather of the last ds (step 0) has no following step to ride on
+        _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds_prev), N, D, _p(dh), 1, st, tag="gather_bwd")
+    _call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,
+           ptr_array([_p(t) for t in grads.tables]), st)
+    if on_small_grads_ready is not None:
+        on_small_grads_ready()
     if engine == ENGINE_TCGEN05 and T > 0:
-        if fuse_gather:     # the gather of the last ds (step 0) has no following step to ride on
-            _call("ddfa_gather_sum", _p(dg.indptr_t), _p(dg.indices_t), _p(ds_prev), N, D, _p(dh), 1, st, tag="gather_bwd")
         if batched_wgrad:
             _call("ddfa_gru_bwd_wgrad_batched", ptr_array([_p(saved.s[t]) for t in range(T)]), ptr_array([_p(saved.h_img[t]) for t in range(T)]),
                   T, N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st, tag="wgrad_batched")
@@ -392,8 +433,6 @@ def backward(params: ParamPack, dg: DeviceGraph, saved: Saved, grads: ParamPack,
             L.call("ddfa_gru_step_bwd_finish", N, D, _p(dw_fold), _p(grads.w_hh), _p(ws), ws_bytes, st)
     L.call("ddfa_fold_weights_bwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), _p(dw_fold), _p(db_fold), D,
            _p(grads.w_msg), _p(grads.b_msg), _p(grads.w_ih), st)
-    _call("ddfa_embed_concat_bwd", ptr_array([_p(t) for t in saved.idx]), _p(dh), _p(dx_direct), K, V, H, N,
-           ptr_array([_p(t) for t in grads.tables]), st)
 
 
 def graph_label_bce(dg: DeviceGraph, vuln: torch.Tensor, logits: Optional[torch.Tensor], pos_weight: float,

@@ -28,7 +28,7 @@ class FusedTrainer:
     def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False, max_graph_shapes: int = 8,
                  max_resident_graphs: int = 64, distributed: bool = True, bucket_nodes: int = 0, bucket_edges: int = 0,
-                 bucket_min_pad_nodes: int = 64):
+                 bucket_min_pad_nodes: int = 64, overlap_allreduce: bool = True):
         """``distributed=False`` makes this a single-rank trainer even inside an initialised process group (no all-reduce).
         ``bucket_nodes`` / ``bucket_edges`` > 0 switch on shape bucketing for HOST batches under ``use_cuda_graph``: every batch
         is padded with ONE dummy graph of isolated nodes up to the next multiple of ``bucket_nodes`` nodes (at least
@@ -43,6 +43,11 @@ class FusedTrainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.bucket_nodes, self.bucket_edges, self.bucket_min_pad_nodes = int(bucket_nodes), int(bucket_edges), int(bucket_min_pad_nodes)
+        # The gradient exchange is split in two: everything except the four GGNN weight matrices' gradients is final before the
+        # batched weight-gradient GEMM starts, so those ranges are all-reduced on a side stream WHILE that launch runs; only
+        # [w_msg, b_msg, w_ih, w_hh] (0.46 MB of the 1.5 MB) is reduced after it.  False: one all-reduce of the whole buffer.
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self._ar_stream = None
         self.use_cuda_graph = use_cuda_graph
         # a captured graph bakes in the batch SHAPE (and, for resident batches, the batch object): cap how many are kept so a
         # stream of ever-new shapes (un-bucketed real data) degrades to eager launches instead of growing without bound
@@ -54,6 +59,8 @@ class FusedTrainer:
             offs.append(total)
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = total
+        ntab = len(module._tables())
+        self._gemm_grad_range = (offs[ntab], offs[ntab + 4])     # flat offsets of [w_msg, b_msg, w_ih, w_hh]
         with torch.cuda.device(self.device):
             self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
             self.flat_g = torch.zeros(total + _ALIGN, dtype=torch.float32, device=self.device)  # [+ loss slot]
@@ -95,13 +102,31 @@ class FusedTrainer:
         _, logits, saved = E.forward(self.params, dg, idx, m.hparams.n_steps, training=True, engine=eng, alloc=self.ws)
         _, _, dlogits = E.graph_label_bce(dg, vuln, logits, pw, 1.0 / global_batch, 1.0 / global_batch, True,
                                           alloc=self.ws, loss_out=self.loss_slot, num_valid=num_valid)
-        E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws)
-        if self.world > 1:
+        split = self.world > 1 and self.overlap_allreduce
+        E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws,
+                   on_small_grads_ready=self._reduce_small_grads if split else None)
+        if split:
+            lo, hi = self._gemm_grad_range
+            dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            torch.cuda.current_stream().wait_stream(self._ar_stream)
+        elif self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
         L = _lib.lib()
         L.call("ddfa_adam_flat", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.numel, self.lr, self.betas[0], self.betas[1],
                self.eps, self.weight_decay, torch.cuda.current_stream().cuda_stream)
+
+    def _reduce_small_grads(self):
+        """All-reduce of the embedding / bias / readout / MLP gradients and the loss slot on a side stream (engine.backward
+        calls this before the weight-gradient launch)."""
+        lo, hi = self._gemm_grad_range
+        main = torch.cuda.current_stream()
+        if self._ar_stream is None:
+            self._ar_stream = torch.cuda.Stream(device=self.device)
+        self._ar_stream.wait_stream(main)
+        with torch.cuda.stream(self._ar_stream):
+            dist.all_reduce(self.flat_g[:lo], op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.flat_g[hi:], op=dist.ReduceOp.SUM, group=self.pg)      # ... b_ih, b_hh, gate, MLP, [loss]
 
     # ------------------------------------------------------------------------------------
     # ---- host batches through per-shape static buffers + captured graphs -------------------------------------------------

@@ -60,7 +60,8 @@ int ddfa_tuning_set(int key, int value);
 int ddfa_tuning_get(int key);
 /* development aid: in-kernel pipeline timeline of the tcgen05 kernels (SM-clock stamps per CTA / tile / event).
  * ddfa_debug_set(2, v): v = 0 off, 1 = forward + dgrad kernels, 2 = forward + wgrad kernels;
- * ddfa_debug_read(2 | 3, host, bytes): stamps of the backward (2) or forward (3) kernel's last launch. */
+ * ddfa_debug_read(2 | 3, host, bytes): stamps of the backward (2) or forward (3) kernel's last launch;
+ * ddfa_debug_read(4, host, 4): int32 count of timed-out mbarrier waits in the TMA-staged gather variants (0 when healthy). */
 int ddfa_debug_set(int key, int value);
 int ddfa_debug_read(int key, void *host_out, size_t bytes);
 /* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
@@ -130,9 +131,16 @@ int ddfa_embed_concat_bwd(const int64_t *const *idx, const float *dx, const floa
  * ------------------------------------------------------------------------------------- */
 int ddfa_gather_sum(const int32_t *indptr, const int32_t *indices, const float *h,
                     int32_t num_nodes, int32_t dim, float *out, int accumulate, void *stream);
-/* Tuning entry (scripts/gather_bench.py): same contract, explicit launch-shape variant (D == 128). */
+/* Tuning entry (scripts/gather_bench.py): same contract, explicit variant (D == 128): 0..9 register-path launch shapes,
+ * 10 = neighbour rows staged in shared memory by per-row TMA bulk copies (cp.async.bulk + mbarrier), 11 = by tensor-map
+ * tile::gather4 copies (four rows per UTMALDG) — csrc/gather_tma.cu. */
 int ddfa_gather_sum_variant(int variant, const int32_t *indptr, const int32_t *indices, const float *h,
                             int32_t num_nodes, int32_t dim, float *out, int accumulate, void *stream);
+/* The same gather for a source that exists only as its activation image (tcgen05 engine, steps t >= 1: h_t = hi + lo of the
+ * image the forward GEMM read; no fp32 copy of h_t is kept).  D == 128. */
+int ddfa_gather_sum_image_src(const int32_t *indptr, const int32_t *indices, const void *h_image,
+                              int32_t num_nodes, int32_t dim, void *out_image, void *stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * Weight folding (done once per forward): w_fold = W_ih @ W  [3D,D], b_fold = W_ih @ b [3D]
@@ -183,6 +191,16 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
                             const int32_t *indptr, int32_t num_nodes, int32_t dim, float *h_out,
                             void *h_out_image, float *save_gates, const void *workspace,
                             size_t workspace_bytes, void *stream);
+/* The form the training / inference drivers use from round 2 on (fewer bytes per step):
+ *   h            fp32 [N,128] or NULL — NULL: the z*h term takes h from h_image (h = hi + lo, 2^-17 relative);
+ *   h_out        fp32 or NULL (only the last step needs it, for the readout); h_out_image or NULL; at least one of the two;
+ *   save_gates_packed  NULL, or ddfa_gru_gates_packed_bytes(N, D) bytes: per element {half2(r, z), half2(n, gh_n)} — the
+ *                four saved gate values as ONE 8-byte store instead of four fp32 planes (fp16: 2^-12 absolute on r, z, n). */
+size_t ddfa_gru_gates_packed_bytes(int32_t num_nodes, int32_t dim);
+int ddfa_gru_step_fwd_image_v2(const void *s_image, const void *h_image, const float *h,
+                               const int32_t *indptr, int32_t num_nodes, int32_t dim, float *h_out,
+                               void *h_out_image, void *save_gates_packed, const void *workspace,
+                               size_t workspace_bytes, void *stream);
 
 /* Backward of one step on images (tcgen05 engine): like ddfa_gru_step_bwd below, but s arrives as its
  * activation image (the one ddfa_gather_sum_image wrote in the forward pass); the q matrices and h are turned
@@ -197,6 +215,13 @@ int ddfa_gru_step_bwd_image(const float *dh_out, const float *ds_prev, const int
                             const float *gates, const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
                             float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
                             void *workspace, size_t workspace_bytes, int wgrad_mode, void *stream);
+/* Same with the saved state of ddfa_gru_step_fwd_image_v2: gates_packed instead of four fp32 planes; h may be NULL
+ * (then h_image, required here, supplies h = hi + lo). */
+int ddfa_gru_step_bwd_image_v2(const float *dh_out, const float *ds_prev, const int32_t *indptr_t, const int32_t *indices_t,
+                               const float *h, const void *h_image, const void *s_image,
+                               const void *gates_packed, const int32_t *indptr, int32_t num_nodes, int32_t dim, float *ds, float *dh,
+                               float *dw_fold, float *db_fold, float *db_ih, float *dw_hh, float *db_hh,
+                               void *workspace, size_t workspace_bytes, int wgrad_mode, void *stream);
 /* wgrad_mode: 0 = dw_fold / dw_hh are updated before the call returns (stream order); 1 / 2 = deferred: the
  * weight-gradient GEMM accumulates per-CTA partial sums inside the workspace over the T steps of one backward pass
  * (1 = first step, overwrites; 2 = later steps) and ddfa_gru_step_bwd_finish adds them to dw_fold / dw_hh once. */

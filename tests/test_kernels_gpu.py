@@ -337,6 +337,103 @@ def test_gru_step_image_entries(graphs, nodes):
                _p(ws_b), wsb_b, 0, st())
 
 
+def decode_image(img: torch.Tensor, N: int) -> torch.Tensor:
+    """Activation image (include/ddfa_b200.h) -> fp64 [N,128] = hi + lo, undoing the SWIZZLE_128B unit permutation."""
+    tiles = img.numel() // 65536
+    raw = img.cpu().view(torch.int16).view(tiles, 4, 128, 8, 8)                   # [tile][chunk = 2 v + kb][row][physical 16-B unit][8 bf16]
+    rows = torch.arange(128).view(1, 1, 128, 1, 1)
+    units = torch.arange(8).view(1, 1, 1, 8, 1)
+    phys = (units ^ (rows & 7)).expand(tiles, 4, 128, 8, 8)
+    logical = torch.gather(raw, 3, phys)                                          # logical unit j sits at physical unit j ^ (row & 7)
+    vals = (logical.to(torch.int32) << 16).view(torch.float32).double().view(tiles, 2, 2, 128, 64)   # [tile][v][kb][row][col in block]
+    x = (vals[:, 0] + vals[:, 1]).permute(0, 2, 1, 3).reshape(tiles * 128, 128)   # hi + lo, [row][kb][64] -> 128 columns
+    assert float(x[N:].abs().max()) == 0.0 if x.shape[0] > N else True           # rows past N are zero
+    return x[:N]
+
+
+@pytest.mark.parametrize("graphs,nodes", [(3, 50), (24, 60), (40, 150)])
+def test_gru_step_image_entries_v2(graphs, nodes):
+    """The round-2 form of the image entries (what engine.py and ddfa_ggnn_fwd/bwd drive): h_t only as its activation image
+    (gather from the image, z*h from the image, backward from the image), gates saved as packed fp16."""
+    D = 128
+    g = synth.make_batch(graphs, nodes, seed=graphs, variable=True)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    src, dst = g.edges()
+    torch.manual_seed(100 + graphs)
+    k = 1.0 / D ** 0.5
+    mk = lambda *sh: (torch.rand(*sh, dtype=torch.float64) * 2 - 1) * k
+    wf, bf, bih, whh, bhh = mk(3 * D, D) * 1.5, mk(3 * D), mk(3 * D), mk(3 * D, D), mk(3 * D)
+    L = lib()
+    ib = L.call("ddfa_act_image_bytes", N)
+    h32 = torch.tanh(torch.randn(N, D)).to(DEV)
+    h_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_act_to_image", _p(h32), N, D, _p(h_img), st())
+    h = decode_image(h_img, N)                      # the exact value the image carries (hi + lo): the reference runs on it
+    assert (h - h32.cpu().double()).abs().max() < 2e-5
+    deg = torch.bincount(dst, minlength=N).double()
+    dh_part = torch.randn(N, D, dtype=torch.float64)
+    ds_prev = torch.randn(N, D, dtype=torch.float64)
+    leaves = [t.requires_grad_(True) for t in (h, wf, bf, bih, whh, bhh)]
+    s_ref = torch.zeros(N, D, dtype=torch.float64).index_add(0, dst, leaves[0][src])
+    # gather straight from the image
+    s_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gather_sum_image_src", _p(dg.indptr), _p(dg.indices), _p(h_img), N, D, _p(s_img), st())
+    s_got = decode_image(s_img, N)
+    assert (s_got - s_ref.detach()).abs().max() < 2e-5 * max(1.0, float(s_ref.abs().max()))
+    s_leaf = s_got.clone().requires_grad_(True)     # the forward step below consumes exactly this image
+    h_ref, r_ref, z_ref, n_ref, ghn_ref = _gru_reference(s_leaf, leaves[0], deg, *leaves[1:])
+    dh_in = dh_part + torch.zeros(N, D, dtype=torch.float64).index_add(0, src, ds_prev[dst])
+    (h_ref * dh_in).sum().backward()
+    wfd, bfd, bihd, whhd, bhhd = [dev(t.detach().float()) for t in leaves[1:]]
+    wsb = L.call("ddfa_gru_step_workspace_bytes", 0, D, ENGINE_TCGEN05)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gru_step_prepare", _p(wfd), _p(bfd), _p(bihd), _p(whhd), _p(bhhd), D, ENGINE_TCGEN05, _p(ws), wsb, st())
+    gpb = L.call("ddfa_gru_gates_packed_bytes", N, D)
+    assert gpb == N * D * 8
+    gates = torch.empty(gpb, dtype=torch.uint8, device=DEV)
+    o_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    h_out = torch.empty(N, D, device=DEV)
+    # middle step: h only as image in, image only out, packed gates
+    L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, None, _p(o_img), _p(gates), _p(ws), wsb, st())
+    assert (decode_image(o_img, N) - h_ref.detach()).abs().max() < 1e-4
+    gk = gates.cpu().view(torch.float16).view(N, D, 4).double()
+    for i, (ref, tol) in enumerate(((r_ref, 6e-4), (z_ref, 6e-4), (n_ref, 6e-4), (ghn_ref, None))):
+        err = (gk[:, :, i] - ref.detach()).abs()
+        bound = tol if tol is not None else 1e-3 * max(1.0, float(ref.abs().max()))
+        assert float(err.max()) < bound, (i, float(err.max()))
+    # last step: fp32 out, no image; inference: nothing saved — same h'
+    L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, _p(h_out), None, None, _p(ws), wsb, st())
+    assert (h_out.cpu().double() - h_ref.detach()).abs().max() < 1e-4
+    o_img2 = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_act_to_image", _p(h_out), N, D, _p(o_img2), st())
+    assert torch.equal(o_img, o_img2)               # the image written directly == the image of the fp32 result
+    # first step form: fp32 h operand given (h_0 = x)
+    h_out0 = torch.empty(N, D, device=DEV)
+    L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), _p(h32), _p(dg.indptr), N, D, _p(h_out0), None, None, _p(ws), wsb, st())
+    assert (h_out0 - h_out).abs().max() < 2e-5
+    with pytest.raises(DdfaError):
+        L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, None, None, None, _p(ws), wsb, st())
+    # backward from the image + packed gates, folded transposed gather
+    wsb_b = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, ENGINE_TCGEN05)
+    ws_b = torch.empty(wsb_b, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gru_step_prepare_bwd", _p(wfd), _p(whhd), D, ENGINE_TCGEN05, _p(ws_b), wsb_b, st())
+    ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
+    acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
+    L.call("ddfa_gru_step_bwd_image_v2", _p(dev(dh_part.float())), _p(dev(ds_prev.float())), _p(dg.indptr_t), _p(dg.indices_t), None, _p(h_img),
+           _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]),
+           _p(ws_b), wsb_b, 0, st())
+    torch.cuda.synchronize()
+    checks = [("ds", ds, s_leaf.grad), ("dh", dh, leaves[0].grad), ("dwf", acc["dwf"], wf.grad), ("dbf", acc["dbf"], bf.grad),
+              ("dbih", acc["dbih"], bih.grad), ("dwhh", acc["dwhh"], whh.grad), ("dbhh", acc["dbhh"], bhh.grad)]
+    worst = {}
+    for name, got, ref in checks:
+        scale = max(1.0, float(ref.abs().max()))
+        worst[name] = float((got.cpu().double() - ref).abs().max()) / scale
+    print(f"image v2 backward (fp16 gates), N={N}: worst |err| / max(1, |ref|max) per output: " + ", ".join(f"{k_}={v:.1e}" for k_, v in worst.items()))
+    assert max(worst.values()) < 1e-3, worst
+
+
 @pytest.mark.parametrize("D,T", [(128, 3), (128, 8), (128, 18), (32, 4), (128, 1), (128, 0)])
 def test_ggnn_fused_drivers(D, T):
     """ddfa_ggnn_fwd / ddfa_ggnn_bwd (the whole GatedGraphConv behind one call each) vs fp64 autograd of the oracle's

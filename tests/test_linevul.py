@@ -69,7 +69,7 @@ def test_cuda_encoder_under_the_reference_head(engine):
 @pytest.mark.gpu
 def test_eval_f1_gpu_encoder_vs_oracle_encoder_and_stream_overlap():
     """BASELINE configs[4]: DDFA GPU embeddings fed to a FROZEN LineVul classifier, eval F1.  2 048 synthetic functions (graph +
-    token ids); the head is fitted once on oracle embeddings (frozen encoders, 150 Adam steps on 512 other functions) so the F1
+    token ids); the head is fitted once on oracle embeddings (frozen encoders, 800 Adam steps on 1 024 other functions) so the F1
     is that of a working classifier; then ``linevul_main.evaluate``'s rule scores the same frozen head with (a) the oracle
     encoder on the CPU and (b) the CUDA encoder — with and without the side-stream overlap."""
     import deepdfa_b200 as D
@@ -92,16 +92,18 @@ def test_eval_f1_gpu_encoder_vs_oracle_encoder_and_stream_overlap():
             out.append((ids.to(device), y.to(device), g))
         return out
 
-    # fit the head on oracle embeddings (encoders frozen) — CPU, a few seconds
+    # fit a fresh head on oracle embeddings (encoders frozen; the fixture's head is scaled for spread, not for training) — CPU, ~1 s
+    from transformers import RobertaConfig
+    from deepdfa_b200.linevul import RobertaClassificationHead
     for p in cpu_model.parameters():
         p.requires_grad_(False)
-    for p in cpu_model.classifier.parameters():
-        p.requires_grad_(True)
+    torch.manual_seed(2)
+    cpu_model.classifier = RobertaClassificationHead(RobertaConfig(**data["roberta"]), oracle_flow.out_dim).eval()
     opt = torch.optim.Adam(cpu_model.classifier.parameters(), lr=3e-3)
-    train = batches(2000, 4, "cpu")
+    train = batches(2000, 8, "cpu")
     with torch.no_grad():
         feats = [(cpu_model.encoder.roberta(ids, attention_mask=ids.ne(1))[0], oracle_flow(g), y) for ids, y, g in train]
-    for step in range(150):
+    for step in range(800):
         h, f, y = feats[step % len(feats)]
         opt.zero_grad()
         loss = torch.nn.functional.cross_entropy(cpu_model.classifier(h, f), y)
@@ -134,6 +136,6 @@ def test_eval_f1_gpu_encoder_vs_oracle_encoder_and_stream_overlap():
     print(f"configs[4] eval, 2048 functions, frozen head: F1 oracle-encoder {res_cpu['eval_f1']:.4f} vs CUDA-encoder {res_gpu['eval_f1']:.4f}; "
           f"decision agreement {agree:.4f}; max|dprob| {dprob:.2e}; wall: cpu {t_cpu:.2f}s, gpu overlap {results[True][1] * 1e3:.1f} ms, "
           f"gpu serial {results[False][1] * 1e3:.1f} ms")
-    assert res_cpu["eval_f1"] > 0.8                          # the frozen head is a working classifier
+    assert res_cpu["eval_f1"] > 0.75                         # the frozen head is a working classifier
     assert agree >= 0.998 and abs(res_gpu["eval_f1"] - res_cpu["eval_f1"]) <= 0.005 and dprob < 5e-3
     assert np.array_equal(results[True][0]["probs"], results[False][0]["probs"])     # overlap changes scheduling, not numbers

@@ -224,7 +224,7 @@ def test_c1_logits_against_live_fp64_oracle(engine, variable):
 # per-parameter gradient bound, relative to the largest entry of that parameter's reference gradient.  The fp32 oracle itself is
 # ~1e-6 from fp64 on these; the tcgen05 engine multiplies with bf16x3 split operands (2^-16 per product) and uses ex2.approx
 # gate math, which is what the measured worst case (printed, and recorded in DESIGN.md §4) reflects.
-GRAD_TOL = {"simt": 2e-4, "tcgen05": 4e-3}
+GRAD_TOL = {"simt": 1e-5, "tcgen05": 1e-4}       # measured worst case (r03a): simt 1.1e-6, tcgen05 1.6e-5 (ggnn.gru.weight_hh)
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
@@ -243,7 +243,8 @@ def test_full_size_gradients_against_live_oracle(engine):
     worst = {}
     for (name, p), (_, q) in zip(m.named_parameters(), o.named_parameters()):
         ref = q.grad
-        scale = max(float(ref.abs().max()), 1e-6)
+        # pooling.gate_nn.bias: the softmax is shift-invariant, its true gradient is 0 (|ref| ~ 1e-10) — absolute floor
+        scale = max(float(ref.abs().max()), 1e-3)
         worst[name] = float((p.grad.cpu().double() - ref).abs().max()) / scale
     print(f"gradient worst case per parameter vs fp64 oracle, engine={engine}: " + ", ".join(f"{k}={v:.1e}" for k, v in worst.items()))
     bad = {k: v for k, v in worst.items() if v >= GRAD_TOL[engine]}
