@@ -60,23 +60,41 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 int pdl_mask();       // abi.cu: DDFA_TUNE_PDL_MASK — bit mask of the kernels launched programmatically (1 gather_image, 2 gru_fwd3, 4 gate_bwd, 8 dgrad3)
 int gather_variant(); // abi.cu: DDFA_TUNE_GATHER_VARIANT
+int fwd_pair();       // abi.cu: DDFA_TUNE_FWD_PAIR — forward GRU kernel as CTA pairs (cta_group::2)
 void chain_break();   // abi.cu: the next launch_chain() on this thread is a normal (fully serialised) launch
 bool chain_take_break();
 
+// cluster_x > 1: the grid is launched as thread-block clusters of that many CTAs along x (CTA pairs for cta_group::2 kernels)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t launch_chain_cluster(int which, int cluster_x, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   const bool brk = chain_take_break();
-  cfg.numAttrs = ((pdl_mask() & which) && !brk) ? 1 : 0;
+  if ((pdl_mask() & which) && !brk) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  return launch_chain_cluster(which, 1, kernel, grid, block, smem, stream, args...);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -31,7 +31,7 @@ GgnnLayout make_layout(int32_t N, int32_t D, int32_t T, int engine, int training
   L.db_fold = take((size_t)3 * D * 4);
   L.gru_ws_bytes = ddfa_gru_step_workspace_bytes(tc ? 0 : N, D, engine);
   L.gru_ws = take(L.gru_ws_bytes < 16 ? 16 : L.gru_ws_bytes);
-  // tcgen05: h_1 .. h_{T-1} exist only as activation images (no fp32 planes); the saved gates are packed fp16 (2 planes' worth)
+  // tcgen05: h_1 .. h_{T-1} exist only as activation images (no fp32 planes); the saved gates are packed 64-bit words (2 planes' worth)
   if (training) {
     L.n_h = (!tc && T > 1) ? T - 1 : 0;          // simt: h_1 .. h_{T-1} (h_0 = x and h_T = h_out belong to the caller)
     L.n_img = tc ? T : 0;                        // images of h_0 .. h_{T-1}

@@ -43,7 +43,7 @@ __device__ __forceinline__ float4 bf16x4_to_f4(const uint2 &p) {
 }
 // Two forms of the saved forward state:
 //   fp32:   h = [N,128] plane, gates = four [N,128] planes (r, z, n, gh_n)                       (ddfa_gru_step_bwd_image)
-//   packed: h = the activation image the forward GEMM read (hi + lo), gates_packed = [N,128] x {half2(r,z), half2(n,gh_n)}
+//   packed: h = the activation image the forward GEMM read (hi + lo), gates_packed = [N,128] x 64-bit words (pack_gates)
 //           — 64 instead of 96 bytes per lane-row                                               (ddfa_gru_step_bwd_image_v2)
 __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_out, const float *__restrict__ h,
                                         const uint8_t *__restrict__ h_img_src, const float *__restrict__ gates,
@@ -77,14 +77,10 @@ __device__ __forceinline__ void gb_load(GbRow &x, const float *__restrict__ dh_o
       x.hv = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
     }
     if (!gates) {
-      const float2 rz0 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.x)), ng0 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.y));
-      const float2 rz1 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.z)), ng1 = __half22float2(*reinterpret_cast<const __half2 *>(&g0.w));
-      const float2 rz2 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.x)), ng2 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.y));
-      const float2 rz3 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.z)), ng3 = __half22float2(*reinterpret_cast<const __half2 *>(&g1.w));
-      x.rr = make_float4(rz0.x, rz1.x, rz2.x, rz3.x);
-      x.zz = make_float4(rz0.y, rz1.y, rz2.y, rz3.y);
-      x.nn = make_float4(ng0.x, ng1.x, ng2.x, ng3.x);
-      x.gh = make_float4(ng0.y, ng1.y, ng2.y, ng3.y);
+      unpack_gates(make_uint2(g0.x, g0.y), x.rr.x, x.zz.x, x.nn.x, x.gh.x);
+      unpack_gates(make_uint2(g0.z, g0.w), x.rr.y, x.zz.y, x.nn.y, x.gh.y);
+      unpack_gates(make_uint2(g1.x, g1.y), x.rr.z, x.zz.z, x.nn.z, x.gh.z);
+      unpack_gates(make_uint2(g1.z, g1.w), x.rr.w, x.zz.w, x.nn.w, x.gh.w);
     }
   }
 }

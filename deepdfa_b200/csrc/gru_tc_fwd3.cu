@@ -43,7 +43,9 @@ constexpr int kXFloats = 4 * kXGateLd;                    // 544 floats = 2176 B
 constexpr int kOffX = kStages * kStageBytes;              // 192 KB
 constexpr int kXBytes = kEpiWarps * kXFloats * 4;         // 34 KB
 constexpr int kOffBar = kOffX + kXBytes;
-constexpr int kNumBars = 2 * kStages + 4 + 1;             // a_full, a_empty, acc_full[2], acc_empty[2], w_ready
+constexpr int kPairStages = 6;                            // CTA-pair form: six 32 KB stages (each CTA holds 64 of a tile's 128 nodes)
+constexpr int kPairStageBytes = kStageBytes / 2;
+constexpr int kNumBars = 3 * kPairStages + 4 + 1;         // a_full, a_empty, (pair: peer_full), acc_full[2], acc_empty[2], w_ready
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemAlloc = kOffTmemPtr + 16;              // the dynamic shared window itself is 1024-byte aligned (checked)
 constexpr int kThreads = 64 + 32 * kEpiWarps;             // 576
@@ -97,8 +99,15 @@ __global__ void pack_kernel(const float *__restrict__ w_fold, const float *__res
 }
 
 // HIMG: the z*h term reads h from the activation image (h == nullptr) instead of an fp32 plane.
-// GATES: 0 = nothing saved (inference), 1 = four fp32 planes (`gates`), 2 = packed fp16 (`gates_packed`).
-template <bool HIMG, int GATES>
+// GATES: 0 = nothing saved (inference), 1 = four fp32 planes (`gates`), 2 = packed 64-bit words (`gates_packed`, pack_gates).
+// PAIR: launched as 2-CTA clusters; the CTAs (2k, 2k+1) — two column slices of the same tile group — issue ONE
+//   tcgen05.mma.cta_group::2 (M = 256: rows 0-127 = the even CTA's slice, 128-255 = the odd CTA's) whose B operand, the 128-node
+//   activation tile, is split between their shared memories: each CTA copies only ITS 64 nodes of every s / h tile (4 x 8 KB
+//   pieces), so a tile is pulled from L2 twice instead of four times and the same 192 KB of shared memory hold six stages = three
+//   tiles in flight instead of one and a half.  Protocol: every CTA's copies complete on its own a_full; warp 1 of the odd CTA
+//   relays that to the leader's peer_full; the leader's MMA thread waits for both, issues, and commits with a multicast to
+//   a_empty / acc_full of BOTH CTAs; the epilogue warps of both CTAs report to the leader's acc_empty / w_ready.
+template <bool HIMG, int GATES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__restrict__ s_img, const uint8_t *__restrict__ h_img,
                                                                const float *__restrict__ h, const int32_t *__restrict__ indptr,
                                                                const uint8_t *__restrict__ packed, int32_t N,
@@ -108,11 +117,20 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();        // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t bar0 = sbase + kOffBar;
+  constexpr int NS = PAIR ? kPairStages : kStages;
+  constexpr uint32_t SB = PAIR ? kPairStageBytes : kStageBytes;
   auto a_full = [&](int i) { return bar0 + 8u * i; };
-  auto a_empty = [&](int i) { return bar0 + 8u * (kStages + i); };
-  auto acc_full = [&](int i) { return bar0 + 8u * (2 * kStages + i); };
-  auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kStages + 2 + i); };
-  const uint32_t w_ready = bar0 + 8u * (2 * kStages + 4);
+  auto a_empty = [&](int i) { return bar0 + 8u * (kPairStages + i); };
+  auto peer_full = [&](int i) { return bar0 + 8u * (2 * kPairStages + i); };
+  auto acc_full = [&](int i) { return bar0 + 8u * (3 * kPairStages + i); };
+  auto acc_empty = [&](int i) { return bar0 + 8u * (3 * kPairStages + 2 + i); };
+  const uint32_t w_ready = bar0 + 8u * (3 * kPairStages + 4);
+  auto WAIT = [](uint32_t bar, uint32_t parity) {     // pair form: bounded (a protocol error traps instead of hanging the device)
+    if constexpr (PAIR) mbar_wait_trap(bar, parity);
+    else mbar_wait(bar, parity);
+  };
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemPtr);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,17 +140,19 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
   const int my_tiles = (num_tiles > group) ? (num_tiles - 1 - group) / num_groups + 1 : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
-    mbar_init(w_ready, kEpiWarps);
+    for (int i = 0; i < NS; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); mbar_init(peer_full(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), PAIR ? 2 * kEpiWarps : kEpiWarps); }
+    mbar_init(w_ready, PAIR ? 2 * kEpiWarps : kEpiWarps);
     mbar_fence_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 512);
+    if constexpr (PAIR) tmem_alloc_pair(smem_u32((const void *)tmem_ptr_smem), 512);
+    else tmem_alloc(smem_u32((const void *)tmem_ptr_smem), 512);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anyone arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tron = g_trace_on;
@@ -147,52 +167,82 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       for (int k = 0; k < my_tiles; ++k) {
         const int tile = group + k * num_groups;
         for (int p = 0; p < 2; ++p, ++cc) {
-          const int stage = cc % kStages, use = cc / kStages;
-          if (use > 0) mbar_wait(a_empty(stage), (use - 1) & 1);
+          const int stage = cc % NS, use = cc / NS;
+          if (use > 0) WAIT(a_empty(stage), (use - 1) & 1);
           if (p == 0) trace_stamp(tron, k, 1);
-          mbar_arrive_expect_tx(a_full(stage), kStageBytes);
-          bulk_g2s(sbase + stage * kStageBytes, (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes, kStageBytes, a_full(stage));
+          mbar_arrive_expect_tx(a_full(stage), SB);
+          const uint8_t *src = (p == 0 ? s_img : h_img) + (size_t)tile * kImageTileBytes;
+          if constexpr (PAIR) {     // this CTA's 64 nodes of each of the four [128 x 64] chunks: rows 64 r .. 64 r + 63 = 8 KB each
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              bulk_g2s(sbase + stage * SB + ch * (kChunkBytes / 2), src + (size_t)ch * kChunkBytes + (size_t)rank * (kChunkBytes / 2),
+                       kChunkBytes / 2, a_full(stage));
+          } else {
+            bulk_g2s(sbase + stage * SB, src, SB, a_full(stage));
+          }
           if (p == 1) trace_stamp(tron, k, 2);
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (my_tiles > 0 && elect_one()) {
-      constexpr uint32_t kIdesc128 = make_idesc(128);
-      mbar_wait(w_ready, 0);
+    // ===== MMA issuer (pair form: leader CTA only; the odd CTA's warp 1 relays "my half of the stage has landed") =====
+    if (PAIR && !leader) {
+      if (my_tiles > 0 && elect_one()) {
+        for (int cc = 0; cc < 2 * my_tiles; ++cc) {
+          const int stage = cc % NS, use = cc / NS;
+          WAIT(a_full(stage), use & 1);
+          mbar_arrive_cluster(mapa_rank(peer_full(stage), 0));
+        }
+      }
+    } else if (my_tiles > 0 && elect_one()) {
+      constexpr uint32_t kIdesc = PAIR ? make_idesc_m256(128) : make_idesc(128);
+      constexpr uint32_t CB = PAIR ? kChunkBytes / 2 : kChunkBytes;       // bytes of one chunk inside a stage
+      if constexpr (PAIR) mbar_wait_cluster(w_ready, 0);
+      else WAIT(w_ready, 0);
       tc_fence_after();
       int cc = 0;
       for (int k = 0; k < my_tiles; ++k) {
         const int buf = k & 1, buse = k >> 1;
-        if (buse > 0) mbar_wait(acc_empty(buf), (buse - 1) & 1);
+        if (buse > 0) {
+          if constexpr (PAIR) mbar_wait_cluster(acc_empty(buf), (buse - 1) & 1);
+          else WAIT(acc_empty(buf), (buse - 1) & 1);
+        }
         tc_fence_after();
         trace_stamp(tron, k, 3);
         const uint32_t d_addr = tmem_base + (uint32_t)(kAccCol + buf * 128);
         for (int p = 0; p < 2; ++p, ++cc) {
-          const int stage = cc % kStages, use = cc / kStages;
-          mbar_wait(a_full(stage), use & 1);
+          const int stage = cc % NS, use = cc / NS;
+          WAIT(a_full(stage), use & 1);
+          if constexpr (PAIR) mbar_wait_cluster(peer_full(stage), use & 1);
           tc_fence_after();
           if (p == 0) trace_stamp(tron, k, 4);
           if (p == 1) trace_stamp(tron, k, 5);
-          const uint64_t b_base = make_desc(sbase + stage * kStageBytes);     // chunks [hi kb0 | hi kb1 | lo kb0 | lo kb1]
+          const uint64_t b_base = make_desc(sbase + stage * SB);     // chunks [hi kb0 | hi kb1 | lo kb0 | lo kb1]
           const uint32_t a_base = tmem_base + (uint32_t)(p * 64);
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint32_t kk2 = (uint32_t)(kb * 32 + k4 * 8);              // packed weight column of this K step
-              const uint64_t b_hi = desc_advance(b_base, (uint32_t)kb * kChunkBytes + k4 * 32);
-              const uint64_t b_lo = desc_advance(b_base, (uint32_t)(2 + kb) * kChunkBytes + k4 * 32);
+              const uint64_t b_hi = desc_advance(b_base, (uint32_t)kb * CB + k4 * 32);
+              const uint64_t b_lo = desc_advance(b_base, (uint32_t)(2 + kb) * CB + k4 * 32);
               const uint32_t first = (p == 0 && kb == 0 && k4 == 0) ? 0u : 1u;
-              umma_f16_ts(d_addr, a_base + kk2, b_hi, kIdesc128, first);                    // w_hi x_hi
-              umma_f16_ts(d_addr, a_base + kWColsHalf + kk2, b_hi, kIdesc128, 1u);          // w_lo x_hi
-              umma_f16_ts(d_addr, a_base + kk2, b_lo, kIdesc128, 1u);                       // w_hi x_lo
+              if constexpr (PAIR) {
+                umma_f16_ts_pair(d_addr, a_base + kk2, b_hi, kIdesc, first);                    // w_hi x_hi
+                umma_f16_ts_pair(d_addr, a_base + kWColsHalf + kk2, b_hi, kIdesc, 1u);          // w_lo x_hi
+                umma_f16_ts_pair(d_addr, a_base + kk2, b_lo, kIdesc, 1u);                       // w_hi x_lo
+              } else {
+                umma_f16_ts(d_addr, a_base + kk2, b_hi, kIdesc, first);
+                umma_f16_ts(d_addr, a_base + kWColsHalf + kk2, b_hi, kIdesc, 1u);
+                umma_f16_ts(d_addr, a_base + kk2, b_lo, kIdesc, 1u);
+              }
             }
           }
-          umma_commit(a_empty(stage));
+          if constexpr (PAIR) umma_commit_pair(a_empty(stage), (uint16_t)3);
+          else umma_commit(a_empty(stage));
         }
-        umma_commit(acc_full(buf));
+        if constexpr (PAIR) umma_commit_pair(acc_full(buf), (uint16_t)3);
+        else umma_commit(acc_full(buf));
         trace_stamp(tron, k, 6);
       }
     }
@@ -222,7 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(w_ready);
+    if (lane == 0) {
+      if (PAIR && !leader) mbar_arrive_cluster(mapa_rank(w_ready, 0));
+      else mbar_arrive(w_ready);
+    }
     pdl_wait();        // everything above (barriers, TMEM, the packed weights) is independent of the previous kernel
 
     const size_t plane = (size_t)N * kD;
@@ -291,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
         for (int i = 0; i < 8; ++i) deg[i] = __shfl_sync(0xffffffffu, dl, (i >> 2) * 16 + g + 4 * (i & 3));
       }
       prefetch(k + 1);
-      mbar_wait(acc_full(buf), buse & 1);
+      WAIT(acc_full(buf), buse & 1);
       tc_fence_after();
       if (tr) trace_stamp(tron, k, 8);
       float v0[16], v1[16];
@@ -301,7 +354,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(buf));   // this warp has read its part of the accumulator buffer
+      if (lane == 0) {                              // this warp has read its part of the accumulator buffer
+        if (PAIR && !leader) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0));
+        else mbar_arrive(acc_empty(buf));
+      }
       if (tr) trace_stamp(tron, k, 9);
       // Addresses: every output of this thread is (per-tile base) + (compile-time offset): node = node_w + 16 ch + g + 4 j, so
       // row-major planes move by (16 ch + 4 j) rows, and inside the image the 8-row group index is 4 e + 2 ch + (j >> 1) while
@@ -333,10 +389,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             const int row_off = (ch * 16 + 4 * j) * kD;
             if (valid) {
               if (ho) st_f32_hint(ho + row_off, hnew, pol_next);
-              if constexpr (GATES == 2) {     // the four saved gate values of an element as ONE 8-byte store: half2(r, z), half2(n, gh_n)
-                const __half2 rz = __floats2half2_rn(r, z), ng = __floats2half2_rn(n, ghn);
-                st_u2_hint(gpk + row_off, make_uint2(*reinterpret_cast<const uint32_t *>(&rz), *reinterpret_cast<const uint32_t *>(&ng)), pol_gates);
-              }
+              if constexpr (GATES == 2)       // the four saved gate values of an element as ONE 8-byte store (tc_common.cuh: pack_gates)
+                st_u2_hint(gpk + row_off, pack_gates(r, z, n, ghn), pol_gates);
               if constexpr (GATES == 1) {
                 st_f32_hint(gp0 + row_off, r, pol_gates);
                 st_f32_hint(gp0 + plane + row_off, z, pol_gates);
@@ -363,10 +417,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // neither CTA frees tensor memory (or exits) while the pair's MMAs may still touch it
+  else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -396,13 +452,20 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
     set_error("tcgen05 engine (fwd): fp32 gate planes go with the fp32 h operand (legacy form)");
     return DDFA_ERR_INVALID_ARG;
   }
-#define DDFA_FWD3_LAUNCH(HIMG, GATES)                                                                                                  \
-  do {                                                                                                                                 \
-    DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel<HIMG, GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc)); \
-    DDFA_CUDA(launch_chain(2, tc3::gru_fwd3_kernel<HIMG, GATES>, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), tc3::kSmemAlloc,  \
-                           stream, static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr,               \
-                           static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates,              \
-                           static_cast<uint2 *>(save_gates_packed), l2_hints()));                                                      \
+  // CTA-pair form (DDFA_TUNE_FWD_PAIR): needs an even number of CTAs per tile group, which kSlices = 4 gives
+  const bool pair = fwd_pair() != 0;
+#define DDFA_FWD3_LAUNCH_P(HIMG, GATES, PAIR)                                                                                              \
+  do {                                                                                                                                     \
+    DDFA_CUDA(cudaFuncSetAttribute(tc3::gru_fwd3_kernel<HIMG, GATES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemAlloc)); \
+    DDFA_CUDA(launch_chain_cluster(2, PAIR ? 2 : 1, tc3::gru_fwd3_kernel<HIMG, GATES, PAIR>, dim3(groups * tc3::kSlices), dim3(tc3::kThreads), \
+                                   tc3::kSmemAlloc, stream, static_cast<const uint8_t *>(s_img), static_cast<const uint8_t *>(h_img), h, indptr, \
+                                   static_cast<const uint8_t *>(packed), N, h_out, static_cast<uint8_t *>(h_out_img), save_gates,        \
+                                   static_cast<uint2 *>(save_gates_packed), l2_hints()));                                                \
+  } while (0)
+#define DDFA_FWD3_LAUNCH(HIMG, GATES)                \
+  do {                                               \
+    if (pair) DDFA_FWD3_LAUNCH_P(HIMG, GATES, true); \
+    else DDFA_FWD3_LAUNCH_P(HIMG, GATES, false);     \
   } while (0)
   if (h) {
     if (save_gates) DDFA_FWD3_LAUNCH(false, 1);
@@ -413,6 +476,7 @@ int gru_tc3_step_fwd(const void *s_img, const void *h_img, const float *h, const
     else DDFA_FWD3_LAUNCH(true, 0);
   }
 #undef DDFA_FWD3_LAUNCH
+#undef DDFA_FWD3_LAUNCH_P
   DDFA_CHECK_LAUNCH("tc3::gru_fwd3_kernel");
   return DDFA_OK;
 }

@@ -148,6 +148,89 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a 2-cluster issue ONE MMA with M = 256 — each CTA's tensor memory holds its own 128
+// rows of A and of D, the B operand (N x K) is split by rows of N between the two CTAs' shared memories (same offsets), the leader
+// (cluster rank 0) issues, and tcgen05.commit multicasts the completion to mbarriers of both CTAs ------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {      // arrive on an mbarrier of another CTA of the cluster
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cta-scope wait, bounded like the one below (used by every role of a pair-form kernel)
+__device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// wait with cluster-scope acquire (the arrivals come from the peer CTA); bounded: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {      // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+// D[tmem, 256 rows over the pair] (+)= A[tmem of each CTA] * B[shared memory of both CTAs]; issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0)
+      : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+// instruction descriptor with M = 256 (cta_group::2)
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B chunk
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
@@ -179,6 +262,32 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl
   split4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
   ph = make_uint4(h0.x, h0.y, h1.x, h1.y);
   pl = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+// ---- saved gate values of one element, 64 bits: r, z in [0,1] as 14-bit fixed point, n in [-1,1] as 16-bit fixed point, gh_n as a
+// 20-bit float (1 sign, 5 exponent bits with fp16's bias, 14 mantissa bits).  Absolute error <= 3.1e-5 on r, z, 1.6e-5 on n, relative
+// 3.1e-5 on gh_n (|gh_n| < 6.1e-5 flushes to 0) — an order below plain fp16 (2.4e-4 / 4.9e-4), which measurably moved the parameter
+// gradients (profiles/r03b: 1.6e-5 -> 2e-4 relative), at the same 8 bytes.  Layout: x = r | z << 14 | gh[3:0] << 28 ; y = n | gh[19:4] << 16.
+__device__ __forceinline__ uint2 pack_gates(float r, float z, float n, float ghn) {
+  const uint32_t rq = __float2uint_rn(__saturatef(r) * 16383.f), zq = __float2uint_rn(__saturatef(z) * 16383.f);
+  const uint32_t nq = (uint32_t)__float2int_rn(fminf(fmaxf(n, -1.f), 1.f) * 32767.f) & 0xffffu;
+  const uint32_t b = __float_as_uint(ghn);
+  int e = (int)((b >> 23) & 0xffu) - 127 + 15;
+  uint32_t m = ((b & 0x7fffffu) + 0x100u) >> 9;      // round the 23-bit mantissa to 14 bits
+  if (m == 0x4000u) { m = 0u; e += 1; }
+  uint32_t g = 0u;
+  if (e >= 31) g = (30u << 14) | 0x3fffu;             // clamp (|gh_n| > 65 000 does not occur: it is a bounded pre-activation)
+  else if (e > 0) g = ((uint32_t)e << 14) | m;
+  g |= (b >> 31) << 19;
+  return make_uint2(rq | (zq << 14) | ((g & 0xfu) << 28), nq | ((g >> 4) << 16));
+}
+__device__ __forceinline__ void unpack_gates(const uint2 &p, float &r, float &z, float &n, float &ghn) {
+  r = (float)(p.x & 0x3fffu) * (1.f / 16383.f);
+  z = (float)((p.x >> 14) & 0x3fffu) * (1.f / 16383.f);
+  n = (float)(int)(short)(p.y & 0xffffu) * (1.f / 32767.f);
+  const uint32_t g = ((p.y >> 16) << 4) | (p.x >> 28);
+  const uint32_t e = (g >> 14) & 31u;
+  ghn = e == 0u ? 0.f : __uint_as_float(((g >> 19) << 31) | ((e + 112u) << 23) | ((g & 0x3fffu) << 9));
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -31,7 +31,7 @@ def _p(t: Optional[torch.Tensor]) -> int:
 # Execution options of the backward pass (A/B switches for scripts and tests; both settings of each run the CUDA kernels):
 #   fuse_gather_bwd: the transposed edge gather of step t+1's ds rides in step t's gate_bwd launch (tcgen05 engine)
 #   batched_wgrad:   ONE weight-gradient launch over all T steps instead of a deferred accumulation per step
-#   packed_state:    tcgen05 engine: h_t kept only as its activation image and the saved gates as packed fp16 (round-2 form, the
+#   packed_state:    tcgen05 engine: h_t kept only as its activation image and the saved gates as packed 64-bit words (round-2 form, the
 #                    default); False = the round-1 form (fp32 copy of every h_t, four fp32 gate planes) for whole-step A/Bs
 OPTIONS = {"fuse_gather_bwd": os.environ.get("DDFA_FUSE_GATHER_BWD", "1") != "0",
            "batched_wgrad": os.environ.get("DDFA_BATCHED_WGRAD", "1") != "0",
@@ -162,7 +162,7 @@ class Saved:
     x: torch.Tensor
     h: List[Optional[torch.Tensor]]  # h[0..T] fp32; tcgen05 engine: only h[0] = x and h[T], the others live as images (None here)
     s: List[torch.Tensor]            # s[0..T-1] (tcgen05: activation images)
-    gates: List[torch.Tensor]        # per step: [4,N,D] fp32 planes (simt) or packed {half2(r,z), half2(n,gh_n)} bytes (tcgen05)
+    gates: List[torch.Tensor]        # per step: [4,N,D] fp32 planes (simt) or packed 64-bit words (tcgen05)
     w_fold: torch.Tensor
     b_fold: torch.Tensor
     pooled: torch.Tensor
@@ -295,7 +295,7 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     elif use_images:
         # tcgen05 engine: between steps h_t exists ONLY as its activation image (the GEMM operand; h = hi + lo to 2^-17) — the
         # gather, the z*h term and the backward pass read that; fp32 copies exist of h_0 = x and of h_T (for the readout).  The
-        # four saved gate values of an element travel as one 8-byte {half2(r,z), half2(n,gh_n)} word.
+        # four saved gate values of an element travel as one 8-byte word (14/14/16-bit fixed point + a 20-bit float, <= 3.1e-5).
         img_bytes = L.call("ddfa_act_image_bytes", N)
         gate_bytes = L.call("ddfa_gru_gates_packed_bytes", N, D)
         n_img = T if training else 2          # training keeps the image of every h_t (the weight-gradient GEMM reads it)

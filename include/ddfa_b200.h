@@ -54,7 +54,8 @@ enum {
   DDFA_TUNE_L2_HINTS = 0,       /* bit mask of L2 eviction-priority hints, default 23 (csrc/common.cuh) */
   DDFA_TUNE_PDL_MASK = 1,       /* bit mask of kernels launched with programmatic stream serialization, default 15 */
   DDFA_TUNE_GATHER_VARIANT = 2, /* launch shape of the D = 128 edge gather (ddfa_gather_sum_variant ids), default 9 */
-  DDFA_TUNE__COUNT = 3
+  DDFA_TUNE_FWD_PAIR = 3,       /* 1: forward GRU kernel launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (default 0) */
+  DDFA_TUNE__COUNT = 4
 };
 int ddfa_tuning_set(int key, int value);
 int ddfa_tuning_get(int key);
@@ -194,8 +195,9 @@ int ddfa_gru_step_fwd_image(const void *s_image, const void *h_image, const floa
 /* The form the training / inference drivers use from round 2 on (fewer bytes per step):
  *   h            fp32 [N,128] or NULL — NULL: the z*h term takes h from h_image (h = hi + lo, 2^-17 relative);
  *   h_out        fp32 or NULL (only the last step needs it, for the readout); h_out_image or NULL; at least one of the two;
- *   save_gates_packed  NULL, or ddfa_gru_gates_packed_bytes(N, D) bytes: per element {half2(r, z), half2(n, gh_n)} — the
- *                four saved gate values as ONE 8-byte store instead of four fp32 planes (fp16: 2^-12 absolute on r, z, n). */
+ *   save_gates_packed  NULL, or ddfa_gru_gates_packed_bytes(N, D) bytes: per element one 64-bit word — r, z as 14-bit,
+ *                n as 16-bit fixed point, gh_n as a 20-bit float (csrc/tc_common.cuh: pack_gates; <= 3.1e-5 error) — the four
+ *                saved gate values as ONE 8-byte store instead of four fp32 planes. */
 size_t ddfa_gru_gates_packed_bytes(int32_t num_nodes, int32_t dim);
 int ddfa_gru_step_fwd_image_v2(const void *s_image, const void *h_image, const float *h,
                                const int32_t *indptr, int32_t num_nodes, int32_t dim, float *h_out,

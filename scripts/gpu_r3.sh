@@ -35,6 +35,18 @@ for STAGE in "$@"; do
         -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum_image" -s 40 -c 10 \
         -f -o $OUT/${TAG}_prof_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_full.log 2>&1
       echo "ncu full exit: $?" ;;
+    ab-packed)    # whole-step A/B on this box: round-1 saved state (fp32 h_t + four fp32 gate planes) vs packed state
+      bash scripts/gpu_ab.sh ${TAG} DDFA_PACKED_STATE 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c1.log
+      bash scripts/gpu_ab.sh ${TAG}c0 DDFA_PACKED_STATE 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c0.log ;;
+    pairtest)     # the CTA-pair forward kernel alone, short timeout (first runs of a new synchronisation protocol)
+      timeout 240 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 200 -s -x -k "cta_pair" > $OUT/${TAG}_pytest_pair.log 2>&1
+      echo "pair pytest exit: $?"; tail -n 12 $OUT/${TAG}_pytest_pair.log | cut -c1-300 ;;
+    ab-pair)
+      bash scripts/gpu_ab.sh ${TAG} DDFA_FWD_PAIR 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c1.log
+      bash scripts/gpu_ab.sh ${TAG}c0 DDFA_FWD_PAIR 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c0.log ;;
+    kerneltests)
+      timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 300 -s -x > $OUT/${TAG}_pytest_kernels.log 2>&1
+      echo "pytest exit: $?"; tail -n 15 $OUT/${TAG}_pytest_kernels.log | cut -c1-300 ;;
     gatherab)
       timeout 900 python scripts/gather_bench.py > $OUT/${TAG}_gather_ab.log 2>&1; echo "gather exit: $?"; cat $OUT/${TAG}_gather_ab.log ;;
     *) echo "unknown stage $STAGE" ;;

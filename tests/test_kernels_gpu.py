@@ -351,6 +351,20 @@ def decode_image(img: torch.Tensor, N: int) -> torch.Tensor:
     return x[:N]
 
 
+def decode_gates(gates: torch.Tensor, N: int):
+    """Packed saved gates (csrc/tc_common.cuh: pack_gates) -> (r, z, n, gh_n) fp64 [N,128]."""
+    w = gates.cpu().view(torch.int32).view(N, 128, 2).to(torch.int64) & 0xffffffff
+    x, y = w[..., 0], w[..., 1]
+    r = (x & 0x3fff).double() / 16383.0
+    z = ((x >> 14) & 0x3fff).double() / 16383.0
+    nq = y & 0xffff
+    n = torch.where(nq >= 32768, nq - 65536, nq).double() / 32767.0
+    g = ((y >> 16) << 4) | (x >> 28)
+    e, m, sign = (g >> 14) & 31, (g & 0x3fff).double(), (g >> 19) & 1
+    ghn = torch.where(e == 0, torch.zeros_like(m), torch.pow(2.0, (e - 15).double()) * (1.0 + m / 16384.0))
+    return r, z, n, torch.where(sign == 1, -ghn, ghn)
+
+
 @pytest.mark.parametrize("graphs,nodes", [(3, 50), (24, 60), (40, 150)])
 def test_gru_step_image_entries_v2(graphs, nodes):
     """The round-2 form of the image entries (what engine.py and ddfa_ggnn_fwd/bwd drive): h_t only as its activation image
@@ -397,10 +411,10 @@ def test_gru_step_image_entries_v2(graphs, nodes):
     # middle step: h only as image in, image only out, packed gates
     L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, None, _p(o_img), _p(gates), _p(ws), wsb, st())
     assert (decode_image(o_img, N) - h_ref.detach()).abs().max() < 1e-4
-    gk = gates.cpu().view(torch.float16).view(N, D, 4).double()
-    for i, (ref, tol) in enumerate(((r_ref, 6e-4), (z_ref, 6e-4), (n_ref, 6e-4), (ghn_ref, None))):
-        err = (gk[:, :, i] - ref.detach()).abs()
-        bound = tol if tol is not None else 1e-3 * max(1.0, float(ref.abs().max()))
+    gk = decode_gates(gates, N)
+    for i, (ref, tol) in enumerate(((r_ref, 1.5e-4), (z_ref, 1.5e-4), (n_ref, 1.5e-4), (ghn_ref, None))):
+        err = (gk[i] - ref.detach()).abs()
+        bound = tol if tol is not None else 1.5e-4 * max(1.0, float(ref.abs().max()))
         assert float(err.max()) < bound, (i, float(err.max()))
     # last step: fp32 out, no image; inference: nothing saved — same h'
     L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, _p(h_out), None, None, _p(ws), wsb, st())
@@ -420,7 +434,8 @@ def test_gru_step_image_entries_v2(graphs, nodes):
     L.call("ddfa_gru_step_prepare_bwd", _p(wfd), _p(whhd), D, ENGINE_TCGEN05, _p(ws_b), wsb_b, st())
     ds, dh = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
     acc = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
-    L.call("ddfa_gru_step_bwd_image_v2", _p(dev(dh_part.float())), _p(dev(ds_prev.float())), _p(dg.indptr_t), _p(dg.indices_t), None, _p(h_img),
+    dpart_d, dsprev_d = dev(dh_part.float()), dev(ds_prev.float())        # (named: a temporary would be freed before the launch)
+    L.call("ddfa_gru_step_bwd_image_v2", _p(dpart_d), _p(dsprev_d), _p(dg.indptr_t), _p(dg.indices_t), None, _p(h_img),
            _p(s_img), _p(gates), _p(dg.indptr), N, D, _p(ds), _p(dh), _p(acc["dwf"]), _p(acc["dbf"]), _p(acc["dbih"]), _p(acc["dwhh"]), _p(acc["dbhh"]),
            _p(ws_b), wsb_b, 0, st())
     torch.cuda.synchronize()
@@ -430,8 +445,52 @@ def test_gru_step_image_entries_v2(graphs, nodes):
     for name, got, ref in checks:
         scale = max(1.0, float(ref.abs().max()))
         worst[name] = float((got.cpu().double() - ref).abs().max()) / scale
-    print(f"image v2 backward (fp16 gates), N={N}: worst |err| / max(1, |ref|max) per output: " + ", ".join(f"{k_}={v:.1e}" for k_, v in worst.items()))
-    assert max(worst.values()) < 1e-3, worst
+    print(f"image v2 backward (packed gates), N={N}: worst |err| / max(1, |ref|max) per output: " + ", ".join(f"{k_}={v:.1e}" for k_, v in worst.items()))
+    assert max(worst.values()) < 3e-4, worst
+
+
+@pytest.mark.parametrize("graphs,nodes", [(3, 50), (40, 150), (1024, 150)])
+def test_forward_cta_pair_form_is_bit_identical(graphs, nodes):
+    """DDFA_TUNE_FWD_PAIR: the forward GRU kernel launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (each CTA stages
+    half of every activation tile) multiplies the same operands in the same order — outputs must equal the single-CTA form
+    bit for bit (image, fp32 h', packed gates), for ragged tails, few tiles and the C1 size."""
+    from deepdfa_b200._lib import TUNE_FWD_PAIR
+    D = 128
+    g = synth.make_batch(graphs, nodes, seed=graphs, variable=graphs < 1000)
+    dg = prepare_graph(g, DEV)
+    N = g.num_nodes()
+    torch.manual_seed(7)
+    k = 1.0 / D ** 0.5
+    mk = lambda *sh: ((torch.rand(*sh) * 2 - 1) * k).to(DEV)
+    wf, bf, bih, whh, bhh = mk(3 * D, D) * 1.5, mk(3 * D), mk(3 * D), mk(3 * D, D), mk(3 * D)
+    L = lib()
+    ib = L.call("ddfa_act_image_bytes", N)
+    h32 = torch.tanh(torch.randn(N, D)).to(DEV)
+    h_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); s_img = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_act_to_image", _p(h32), N, D, _p(h_img), st())
+    L.call("ddfa_gather_sum_image_src", _p(dg.indptr), _p(dg.indices), _p(h_img), N, D, _p(s_img), st())
+    wsb = L.call("ddfa_gru_step_workspace_bytes", 0, D, ENGINE_TCGEN05)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L.call("ddfa_gru_step_prepare", _p(wf), _p(bf), _p(bih), _p(whh), _p(bhh), D, ENGINE_TCGEN05, _p(ws), wsb, st())
+    gpb = L.call("ddfa_gru_gates_packed_bytes", N, D)
+    outs = {}
+    try:
+        for pair in (0, 1):
+            L.call("ddfa_tuning_set", TUNE_FWD_PAIR, pair)
+            assert L.call("ddfa_tuning_get", TUNE_FWD_PAIR) == pair
+            o_img = torch.zeros(ib, dtype=torch.uint8, device=DEV); gates = torch.zeros(gpb, dtype=torch.uint8, device=DEV)
+            h_out = torch.empty(N, D, device=DEV)
+            for _ in range(2):      # twice: barrier phases / stage wrap-around of a second launch
+                L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, _p(h_out), _p(o_img), _p(gates), _p(ws), wsb, st())
+            h_first = torch.empty(N, D, device=DEV)
+            L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), _p(h32), _p(dg.indptr), N, D, _p(h_first), None, None, _p(ws), wsb, st())
+            torch.cuda.synchronize()
+            outs[pair] = (o_img, gates, h_out, h_first)
+    finally:
+        L.call("ddfa_tuning_set", TUNE_FWD_PAIR, 0)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert torch.isfinite(outs[1][2]).all() and float(outs[1][2].abs().max()) > 0.1
 
 
 @pytest.mark.parametrize("D,T", [(128, 3), (128, 8), (128, 18), (32, 4), (128, 1), (128, 0)])

@@ -376,7 +376,7 @@ def test_batched_weight_gradient_matches_per_step(monkeypatch):
     grads = {}
     from deepdfa_b200 import engine as E
     for key, opts in (("default", {}), ("per_step_wgrad", {"batched_wgrad": False}), ("unfused_gather", {"fuse_gather_bwd": False})):
-        monkeypatch.setattr(E, "OPTIONS", dict({"fuse_gather_bwd": True, "batched_wgrad": True}, **opts))
+        monkeypatch.setattr(E, "OPTIONS", dict(E.OPTIONS, **dict({"fuse_gather_bwd": True, "batched_wgrad": True}, **opts)))
         torch.manual_seed(11)
         m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 6, 2, concat_all_absdf=True, engine="tcgen05").to(DEV)
         loss = m.training_step((b, {}), 0)
