@@ -224,96 +224,86 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
 // ---- D = 128, input AND output as activation images ------------------------------------------------------------------------
 // The same gather for the steps whose h_t exists only as its image (tcgen05 engine, t >= 1: the forward GRU kernel no longer
 // writes an fp32 copy of h').  A node's image row is four 128-byte pieces [hi | lo] x [cols 0-63 | 64-127]; lane l fetches one
-// 16-byte unit (8 bf16) of piece l / 8, un-swizzling by row & 7, accumulates hi and lo parts separately in fp32 and the two
-// halves of the warp are combined at the end: s = sum hi + sum lo (every term exact in fp32).  Same mapping as above otherwise.
+// 16-byte unit (8 bf16) of each of two pieces (mapping: see the kernel).
 __global__ void __launch_bounds__(128) gather_sum_image_src_kernel(const int32_t *__restrict__ indptr,
                                                                    const int32_t *__restrict__ indices,
                                                                    const uint8_t *__restrict__ h_img, int32_t N,
                                                                    uint8_t *__restrict__ out_img) {
-  constexpr int RW = 2, PASSES = 2, ROWS = RW * PASSES, UNROLL = 4;
+  // A warp owns 4 consecutive destination rows; each HALF-warp sums two of them.  Lane j of a half owns columns 8 j .. 8 j + 7:
+  // per neighbour it fetches that unit's hi and lo 16-byte pieces (un-swizzling by row & 7), adds them (exact in fp32: h = hi + lo)
+  // and accumulates — so every lane ends with final sums, which it splits and stores as the two pieces of the output image.
+  constexpr int ROWS = 4, UNROLL = 2;
   const int lane = threadIdx.x & 31;
-  const int piece = lane >> 3, unit = lane & 7;
+  const int hf = lane >> 4, j = lane & 15;
+  const uint32_t piece_off = (uint32_t)((j >> 3) * 16384), unit16 = (uint32_t)((j & 7) << 4);
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t v0 = warp_global * ROWS;
   const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
   pdl_launch_dependents();
   pdl_wait();
-  if (v0 >= Npad) return;
-  const int nrows = (int)min((int64_t)ROWS, Npad - v0);
+  if (v0 >= Npad) return;        // Npad is a multiple of 4: a warp's four rows are all inside the padded range
   int32_t myptr = 0;
-  if (lane <= nrows) myptr = __ldcg(indptr + min(v0 + lane, (int64_t)N));
+  if (lane <= ROWS) myptr = __ldcg(indptr + min(v0 + lane, (int64_t)N));   // rows past N: empty neighbour list -> zeros
   const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
-  const int32_t total = __shfl_sync(0xffffffffu, myptr, nrows) - beg0;
+  const int32_t total = __shfl_sync(0xffffffffu, myptr, ROWS) - beg0;
   const int32_t pre = (lane < total) ? __ldcg(indices + beg0 + lane) : 0;
-#pragma unroll 1
-  for (int p = 0; p < PASSES; ++p) {
-    const int r0 = p * RW;
-    if (r0 >= nrows) break;
-    int32_t rend[RW];
+  // this half's two rows: edges [hbeg, hmid) belong to row 2 hf, [hmid, hend) to row 2 hf + 1 (offsets relative to beg0)
+  const int32_t hbeg = __shfl_sync(0xffffffffu, myptr, 2 * hf) - beg0;
+  const int32_t hmid = __shfl_sync(0xffffffffu, myptr, 2 * hf + 1) - beg0;
+  const int32_t hend = __shfl_sync(0xffffffffu, myptr, 2 * hf + 2) - beg0;
+  const int32_t len_other = __shfl_xor_sync(0xffffffffu, hend - hbeg, 16);
+  const int32_t trips = max(hend - hbeg, len_other);       // warp-uniform trip count (the shuffles below need all lanes)
+  float acc[2][8];
 #pragma unroll
-    for (int r = 0; r < RW; ++r) rend[r] = __shfl_sync(0xffffffffu, myptr, min(r0 + r + 1, nrows)) - beg0;
-    const int32_t pbeg = __shfl_sync(0xffffffffu, myptr, r0) - beg0;
-    const int32_t pend = rend[RW - 1];
-    float acc[RW][8];
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int r = 0; r < RW; ++r)
+    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+  for (int32_t t = 0; t < trips; t += UNROLL) {
+    uint4 vh[UNROLL], vl[UNROLL];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
-    for (int32_t b = pbeg; b < pend; b += UNROLL) {
-      uint4 v[UNROLL];
-#pragma unroll
-      for (int j = 0; j < UNROLL; ++j) {
-        const int32_t pos = min(b + j, pend - 1);
-        int32_t u = __shfl_sync(0xffffffffu, pre, pos & 31);
-        if (pos >= 32) u = __ldcg(indices + beg0 + pos);
-        const int row = u & 127;
-        const uint8_t *src = h_img + (size_t)(u >> 7) * 65536 + (size_t)piece * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4);
-        v[j] = (b + j < pend) ? __ldcg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int j = 0; j < UNROLL; ++j) {
-        const int32_t pos = b + j;
-        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-          const bool mine = (pos < rend[r]) && (r == 0 ? true : pos >= rend[r - 1]);
-          if (mine) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              acc[r][2 * i] += __uint_as_float(w[i] << 16);
-              acc[r][2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
-            }
-          }
-        }
-      }
+    for (int q = 0; q < UNROLL; ++q) {
+      const int32_t pos = hbeg + t + q;
+      const bool on = pos < hend;
+      const int32_t pc = on ? pos : 0;
+      int32_t u = __shfl_sync(0xffffffffu, pre, pc & 31);
+      if (on && pc >= 32) u = __ldcg(indices + beg0 + pc);
+      const uint8_t *src = h_img + (size_t)(u >> 7) * 65536 + (size_t)(u & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((u & 7) << 4));
+      vh[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
+      vl[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src + 32768)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      if (r0 + r < nrows) {            // warp-uniform
-        float x[8];
+    for (int q = 0; q < UNROLL; ++q) {
+      const int32_t pos = hbeg + t + q;
+      const uint32_t wh[4] = {vh[q].x, vh[q].y, vh[q].z, vh[q].w}, wl[4] = {vl[q].x, vl[q].y, vl[q].z, vl[q].w};
+      float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = acc[r][i] + __shfl_down_sync(0xffffffffu, acc[r][i], 16);    // lanes 0-15: hi sums + lo sums
-        if (lane < 16) {
-          const int64_t node = v0 + r0 + r;
-          const int row = (int)(node & 127);
-          uint4 ph, pl;
-          // split8 lives in tc_common.cuh; restated here on packed words to keep gather.cu free of the tensor-core header
-          uint32_t hw[4], lw[4];
+      for (int i = 0; i < 4; ++i) {
+        x[2 * i] = __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
+        x[2 * i + 1] = __uint_as_float(wh[i] & 0xffff0000u) + __uint_as_float(wl[i] & 0xffff0000u);
+      }
+      if (pos < hmid) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-            hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4 *>(dst + (size_t)piece * 16384) = ph;          // piece = 0 | 1 here: hi chunk of cols 0-63 | 64-127
-          *reinterpret_cast<uint4 *>(dst + (size_t)(2 + piece) * 16384) = pl;
-        }
+        for (int i = 0; i < 8; ++i) acc[0][i] += x[i];
+      } else if (pos < hend) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[1][i] += x[i];
       }
     }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int64_t node = v0 + 2 * hf + r;
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[r][2 * i]), h1 = __float2bfloat16_rn(acc[r][2 * i + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[r][2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(acc[r][2 * i + 1] - __bfloat162float(h1));
+      hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (size_t)(node & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((node & 7) << 4));
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4 *>(dst + 32768) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 

@@ -32,7 +32,7 @@ for STAGE in "$@"; do
       echo "ncu launches exit: $?" ;;
     ncu-full)
       env $PROF_ENV timeout 1500 ncu --set full --clock-control none --import-source on \
-        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum_image" -s 40 -c 10 \
+        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum_image|readout|embed_concat" -s 60 -c 48 \
         -f -o $OUT/${TAG}_prof_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_full.log 2>&1
       echo "ncu full exit: $?" ;;
     ab-packed)    # whole-step A/B on this box: round-1 saved state (fp32 h_t + four fp32 gate planes) vs packed state
