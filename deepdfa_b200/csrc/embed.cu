@@ -51,16 +51,31 @@ __global__ void __launch_bounds__(256) embed_concat_bwd_kernel(const EmbedPtrs p
   float4 hot[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
   const int32_t row0 = blockIdx.x * kEmbRows;
   const int32_t row1 = min(N, row0 + kEmbRows);
-  for (int32_t n = row0 + threadIdx.y; n < row1; n += blockDim.y) {
-    float4 g = *reinterpret_cast<const float4 *>(dx + (int64_t)n * D + c * 4);
-    if (dx2) f4_add(g, *reinterpret_cast<const float4 *>(dx2 + (int64_t)n * D + c * 4));
-    int64_t i = idx[n];
-    i = i < 0 ? 0 : (i >= V ? V - 1 : i);
-    if (i == 0) f4_add(hot[0], g);
-    else if (i == 1) f4_add(hot[1], g);
-    else {
-      float *q = dt + i * H + j;
-      atomicAdd(q + 0, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w);
+  // four rows per iteration: their (independent) loads are in flight together — one row at a time was a chain of load latencies
+  // (r03a launch list: 96 us for 157 MB at C1)
+  constexpr int U = 4;
+  for (int32_t nb = row0 + threadIdx.y; nb < row1; nb += U * blockDim.y) {
+    float4 g[U];
+    int64_t ii[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t n = nb + u * blockDim.y;
+      const bool ok = n < row1;
+      g[u] = ok ? __ldg(reinterpret_cast<const float4 *>(dx + (int64_t)n * D + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dx2 && ok) f4_add(g[u], __ldg(reinterpret_cast<const float4 *>(dx2 + (int64_t)n * D + c * 4)));
+      ii[u] = ok ? idx[n] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ii[u] == -1 && nb + u * (int32_t)blockDim.y >= row1) continue;
+      int64_t i = ii[u];
+      i = i < 0 ? 0 : (i >= V ? V - 1 : i);
+      if (i == 0) f4_add(hot[0], g[u]);
+      else if (i == 1) f4_add(hot[1], g[u]);
+      else {
+        float *q = dt + i * H + j;
+        atomicAdd(q + 0, g[u].x); atomicAdd(q + 1, g[u].y); atomicAdd(q + 2, g[u].z); atomicAdd(q + 3, g[u].w);
+      }
     }
   }
   *reinterpret_cast<float4 *>(&red[((size_t)threadIdx.y * 2 + 0) * D + c * 4]) = hot[0];

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
       // Addresses: every output of this thread is (per-tile base) + (compile-time offset): node = node_w + 16 ch + g + 4 j, so
       // row-major planes move by (16 ch + 4 j) rows, and inside the image the 8-row group index is 4 e + 2 ch + (j >> 1) while
       // row & 7 = g + 4 (j & 1) selects one of two swizzle offsets computed once per kernel (img_lane_off).
+      const int rows_left = (int)min((int64_t)N - node_w - g, (int64_t)64);      // node node_w + g + d is a real row iff d < rows_left
       float *const ho = h_out ? h_out + (node_w + g) * kD + gcol : nullptr;
       float *const gp0 = GATES == 1 ? gates + (node_w + g) * kD + gcol : nullptr;
       uint2 *const gpk = GATES == 2 ? gates_packed + (node_w + g) * kD + gcol : nullptr;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = g + 4 * j;                                     // node of the chunk finished by this thread
-            const bool valid = node_w + ch * 16 + i < N;
+            const bool valid = ch * 16 + 4 * j < rows_left;
             const float dg = deg[ch * 4 + j];
             const float gin = X[0 * kXGateLd + i * 8 + c] + fmaf(dg, d_gin, b_gin);
             const float r = fast_sigmoid(X[1 * kXGateLd + i * 8 + c] + fmaf(dg, d_r, b_r));
@@ -402,11 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
               // columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
               const float other = __shfl_xor_sync(0xffffffffu, hnew, 1);
               const float x0 = (c & 1) ? other : hnew, x1 = (c & 1) ? hnew : other;
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(x0, h0, l0);
-              split_bf16(x1, h1, l1);
-              const uint32_t word = (c & 1) ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16))
-                                            : ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
+              // one cvt.rn.bf16x2.f32 per word: hi = bf16(x), lo = bf16(x - hi) — the same values split_bf16 produces
+              const __nv_bfloat162 hi2 = __floats2bfloat162_rn(x0, x1);
+              const uint32_t hw = *reinterpret_cast<const uint32_t *>(&hi2);
+              const __nv_bfloat162 lo2 = __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xffff0000u));
+              const uint32_t word = (c & 1) ? *reinterpret_cast<const uint32_t *>(&lo2) : hw;
               st_u32_hint(ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1], word, pol_next);
             }
           }

@@ -269,17 +269,16 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl
 // 3.1e-5 on gh_n (|gh_n| < 6.1e-5 flushes to 0) — an order below plain fp16 (2.4e-4 / 4.9e-4), which measurably moved the parameter
 // gradients (profiles/r03b: 1.6e-5 -> 2e-4 relative), at the same 8 bytes.  Layout: x = r | z << 14 | gh[3:0] << 28 ; y = n | gh[19:4] << 16.
 __device__ __forceinline__ uint2 pack_gates(float r, float z, float n, float ghn) {
-  const uint32_t rq = __float2uint_rn(__saturatef(r) * 16383.f), zq = __float2uint_rn(__saturatef(z) * 16383.f);
-  const uint32_t nq = (uint32_t)__float2int_rn(fminf(fmaxf(n, -1.f), 1.f) * 32767.f) & 0xffffu;
+  // r, z come out of fast_sigmoid (in [0,1]) and n out of fast_tanh (in [-1,1]): no clamping needed
+  const uint32_t rq = __float2uint_rn(r * 16383.f), zq = __float2uint_rn(z * 16383.f);
+  const uint32_t nq = (uint32_t)__float2int_rn(n * 32767.f) & 0xffffu;
   const uint32_t b = __float_as_uint(ghn);
-  int e = (int)((b >> 23) & 0xffu) - 127 + 15;
-  uint32_t m = ((b & 0x7fffffu) + 0x100u) >> 9;      // round the 23-bit mantissa to 14 bits
-  if (m == 0x4000u) { m = 0u; e += 1; }
-  uint32_t g = 0u;
-  if (e >= 31) g = (30u << 14) | 0x3fffu;             // clamp (|gh_n| > 65 000 does not occur: it is a bounded pre-activation)
-  else if (e > 0) g = ((uint32_t)e << 14) | m;
-  g |= (b >> 31) << 19;
-  return make_uint2(rq | (zq << 14) | ((g & 0xfu) << 28), nq | ((g >> 4) << 16));
+  // round the mantissa to 14 bits (a carry runs into the exponent, as it should), drop the sign, re-bias the exponent 127 -> 15:
+  // core = [exponent - 112 | mantissa] ; below 2^-14 -> 0, above fp16's range -> largest value
+  const int core = (int)(((b + 0x100u) << 1) >> 10) - (112 << 14);
+  uint32_t g = core < (1 << 14) ? 0u : (uint32_t)min(core, (31 << 14) - 1);
+  g |= (b >> 12) & 0x80000u;
+  return make_uint2(rq | (zq << 14) | (g << 28), nq | ((g >> 4) << 16));
 }
 __device__ __forceinline__ void unpack_gates(const uint2 &p, float &r, float &z, float &n, float &ghn) {
   r = (float)(p.x & 0x3fffu) * (1.f / 16383.f);

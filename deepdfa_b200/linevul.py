@@ -40,9 +40,11 @@ class LineVulCombined(nn.Module):
     """Drop-in for ``linevul_model.Model`` (linevul_model.py:26-69).  ``encoder`` is a ``RobertaForSequenceClassification``
     (only ``encoder.roberta`` is called, as in the reference), ``flowgnn_encoder`` any module with ``out_dim`` whose
     ``forward(graphs, {})`` returns ``[B, out_dim]`` — here the CUDA ``FlowGNNGGNNModule(encoder_mode=True)``.
-    ``overlap=False`` runs both encoders on the current stream (A/B switch)."""
+    ``overlap=True`` enqueues the DDFA encoder on a side CUDA stream so that it runs concurrently with the transformer's forward
+    (SURVEY.md §8 f3); default off: both are launch-bound from one host thread at the reference's batch size (16), and the side
+    stream's event traffic cost more than the overlap bought in every measurement taken (tests/test_linevul.py prints both)."""
 
-    def __init__(self, encoder, flowgnn_encoder, config, tokenizer=None, args=None, overlap: bool = True):
+    def __init__(self, encoder, flowgnn_encoder, config, tokenizer=None, args=None, overlap: bool = False):
         super().__init__()
         self.encoder = encoder
         self.no_flowgnn = bool(getattr(args, "no_flowgnn", False)) if args is not None else flowgnn_encoder is None

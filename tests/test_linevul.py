@@ -139,3 +139,34 @@ def test_eval_f1_gpu_encoder_vs_oracle_encoder_and_stream_overlap():
     assert res_cpu["eval_f1"] > 0.75                         # the frozen head is a working classifier
     assert agree >= 0.998 and abs(res_gpu["eval_f1"] - res_cpu["eval_f1"]) <= 0.005 and dprob < 5e-3
     assert np.array_equal(results[True][0]["probs"], results[False][0]["probs"])     # overlap changes scheduling, not numbers
+
+
+@pytest.mark.gpu
+def test_side_stream_overlap_at_roberta_base_size():
+    """The same A/B with a transformer of the size LineVul uses (RoBERTa-base shape: 12 layers x 768, random weights — no
+    checkpoint can be downloaded here), batch 16 x 512 tokens as in linevul_main.py's defaults, graphs of Big-Vul size: wall time of
+    the combined forward with the DDFA encoder on the side stream vs on the main stream; identical outputs."""
+    import deepdfa_b200 as D
+    from transformers import RobertaConfig, RobertaForSequenceClassification
+    torch.manual_seed(0)
+    config = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                           max_position_embeddings=514, num_labels=2)
+    encoder = RobertaForSequenceClassification(config).to(DEV).eval()
+    FEAT = "_ABS_DATAFLOW_api_all_limitall_1000_limitsubkeys_1000"
+    flow = D.FlowGNNGGNNModule(FEAT, 1002, 32, 5, 3, concat_all_absdf=True, encoder_mode=True).to(DEV)
+    g = synth.make_batch(16, 150, seed=3, variable=True).to(DEV)
+    ids = torch.randint(3, 50000, (16, 512), device=DEV)
+    out = {}
+    for overlap in (False, True):
+        model = LineVulCombined(encoder, flow, config, overlap=overlap).to(DEV).eval()
+        with torch.no_grad():
+            for _ in range(3):
+                prob = model(input_ids=ids, graphs=g)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                prob = model(input_ids=ids, graphs=g)
+            torch.cuda.synchronize()
+        out[overlap] = ((time.perf_counter() - t0) / 10, prob)
+    print(f"LineVul forward, RoBERTa-base shape, 16 x 512 tokens + 16 CFGs: serial {out[False][0] * 1e3:.2f} ms, side-stream overlap {out[True][0] * 1e3:.2f} ms")
+    assert out[False][1].shape == (16, 2)
