@@ -183,6 +183,19 @@ __device__ __forceinline__ void st_u32_hint(void *p, uint32_t v, uint64_t pol) {
 __device__ __forceinline__ void st_u2_hint(void *p, const uint2 &v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
+// Predicated forms (`@p st`): a store under `if (cond)` becomes a branch, and a branch per output element splits the unrolled
+// epilogue of the forward GRU kernel into basic blocks the scheduler cannot interleave (r03 SASS: three branches + a BRA.DIV per
+// element); with the predicate inside the instruction the element bodies are straight-line code.
+__device__ __forceinline__ void st_f32_hint_if(bool pred, float *p, float v, uint64_t pol) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %3, 0;\n@q st.global.L2::cache_hint.f32 [%0], %1, %2;\n}" ::"l"(p), "f"(v), "l"(pol), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void st_u32_hint_if(bool pred, void *p, uint32_t v, uint64_t pol) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %3, 0;\n@q st.global.L2::cache_hint.u32 [%0], %1, %2;\n}" ::"l"(p), "r"(v), "l"(pol), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void st_u2_hint_if(bool pred, void *p, const uint2 &v, uint64_t pol) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n@q st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;\n}" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol), "r"((int)pred)
+               : "memory");
+}
 // abi.cu: DDFA_TUNE_L2_HINTS bit mask, default 23.  1: saved gates written evict_first; 2: saved activations read evict_first in the
 // backward pass; 4: ds / dh / dh'z written evict_last; 8: their last reads evict_first; 16: h' and its image written evict_last;
 // 32 / 64: operand tiles of the weight-gradient / dgrad kernels copied evict_first.  Whole-step A/B (one box, profiles/r02l-m):

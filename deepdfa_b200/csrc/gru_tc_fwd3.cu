@@ -388,19 +388,18 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
             const float n = fast_tanh(fmaf(r, ghn, gin));
             const float hnew = valid ? fmaf(z, hp[ch * 4 + j] - n, n) : 0.f;   // rows past N stay zero in the image
             const int row_off = (ch * 16 + 4 * j) * kD;
-            if (valid) {
-              if (ho) st_f32_hint(ho + row_off, hnew, pol_next);
-              if constexpr (GATES == 2)       // the four saved gate values of an element as ONE 8-byte store (tc_common.cuh: pack_gates)
-                st_u2_hint(gpk + row_off, pack_gates(r, z, n, ghn), pol_gates);
-              if constexpr (GATES == 1) {
-                st_f32_hint(gp0 + row_off, r, pol_gates);
-                st_f32_hint(gp0 + plane + row_off, z, pol_gates);
-                st_f32_hint(gp0 + 2 * plane + row_off, n, pol_gates);
-                st_f32_hint(gp0 + 3 * plane + row_off, ghn, pol_gates);
-              }
+            // every store is predicated, not branched (common.cuh): the four element bodies of a chunk stay one basic block
+            st_f32_hint_if(valid && ho != nullptr, ho + row_off, hnew, pol_next);
+            if constexpr (GATES == 2)       // the four saved gate values of an element as ONE 8-byte store (tc_common.cuh: pack_gates)
+              st_u2_hint_if(valid, gpk + row_off, pack_gates(r, z, n, ghn), pol_gates);
+            if constexpr (GATES == 1) {
+              st_f32_hint_if(valid, gp0 + row_off, r, pol_gates);
+              st_f32_hint_if(valid, gp0 + plane + row_off, z, pol_gates);
+              st_f32_hint_if(valid, gp0 + 2 * plane + row_off, n, pol_gates);
+              st_f32_hint_if(valid, gp0 + 3 * plane + row_off, ghn, pol_gates);
             }
-            if (ip) {
-              // columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
+            {
+              // image word: columns (c, c+1), c even: the even lane writes the hi word, the odd lane the lo word
               const float other = __shfl_xor_sync(0xffffffffu, hnew, 1);
               const float x0 = (c & 1) ? other : hnew, x1 = (c & 1) ? hnew : other;
               // one cvt.rn.bf16x2.f32 per word: hi = bf16(x), lo = bf16(x - hi) — the same values split_bf16 produces
@@ -408,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd3_kernel(const uint8_t *__
               const uint32_t hw = *reinterpret_cast<const uint32_t *>(&hi2);
               const __nv_bfloat162 lo2 = __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xffff0000u));
               const uint32_t word = (c & 1) ? *reinterpret_cast<const uint32_t *>(&lo2) : hw;
-              st_u32_hint(ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1], word, pol_next);
+              st_u32_hint_if(ip != nullptr, ip + (ch * 2 + (j >> 1)) * 1024 + img_lane_off[j & 1], word, pol_next);
             }
           }
           __syncwarp();

@@ -5,9 +5,9 @@ embedding) -> dropout -> dense -> tanh -> dropout -> out_proj(2)``) and ``Model.
 return tuples, ``CrossEntropyLoss``, ``softmax`` probabilities).  Submodule names are the reference's (``encoder``,
 ``flowgnn_encoder``, ``classifier.dense`` / ``classifier.out_proj``), so a checkpoint written by ``linevul_main.py`` loads.
 
-What is new here is only scheduling: the DDFA encoder (``FlowGNNGGNNModule(encoder_mode=True)``, hand-written kernels) is
-enqueued on a SIDE CUDA stream, so its ~100 launches overlap the transformer's forward on the main stream; the two meet at the
-classifier head.  The transformer itself is the stock Hugging Face RoBERTa — out of scope of this repository.
+What is new here is only scheduling: with ``overlap=True`` the DDFA encoder (``FlowGNNGGNNModule(encoder_mode=True)``,
+hand-written kernels) is enqueued on a SIDE CUDA stream, so its launches overlap the transformer's forward on the main stream and
+the two meet at the classifier head.  The transformer itself is the stock Hugging Face RoBERTa — out of scope of this repository.
 """
 from __future__ import annotations
 

@@ -30,11 +30,15 @@ for STAGE in "$@"; do
       env $PROF_ENV timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
         --log-file $OUT/${TAG}_launches_c1.csv python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_list.log 2>&1
       echo "ncu launches exit: $?" ;;
-    ncu-full)
-      env $PROF_ENV timeout 1500 ncu --set full --clock-control none --import-source on \
-        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum_image|readout|embed_concat" -s 60 -c 48 \
-        -f -o $OUT/${TAG}_prof_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_full.log 2>&1
-      echo "ncu full exit: $?" ;;
+    ncu-full)     # (1) --set full of the dominant kernel only (the .ncu-rep must stay well below gpurun's 64 MiB return limit);
+                  # (2) a metrics-only pass over one whole step for every kernel of the path
+      env $PROF_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gru_fwd3_kernel" -s 12 -c 3 \
+        -f -o $OUT/${TAG}_prof_fwd3_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_full.log 2>&1
+      echo "ncu full (fwd3) exit: $?"
+      env $PROF_ENV timeout 900 ncu --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum \
+        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum|readout|embed_concat|sgemm_small" -s 80 -c 70 \
+        -f -o $OUT/${TAG}_prof_step_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_step.log 2>&1
+      echo "ncu step metrics exit: $?"; ls -la $OUT/*.ncu-rep ;;
     ab-packed)    # whole-step A/B on this box: round-1 saved state (fp32 h_t + four fp32 gate planes) vs packed state
       bash scripts/gpu_ab.sh ${TAG} DDFA_PACKED_STATE 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_PACKED_STATE 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c0.log ;;
@@ -44,6 +48,19 @@ for STAGE in "$@"; do
     ab-pair)
       bash scripts/gpu_ab.sh ${TAG} DDFA_FWD_PAIR 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_FWD_PAIR 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c0.log ;;
+    ab-lib)       # same-box A/B of two builds: deepdfa_b200/lib/libddfa_b200_prev.so (previous commit) vs the current library
+      for rep in 1 2; do
+        for v in prev cur; do
+          LIBP=deepdfa_b200/lib/libddfa_b200.so; [ $v = prev ] && LIBP=deepdfa_b200/lib/libddfa_b200_prev.so
+          env DDFA_LIB_PATH=$PWD/$LIBP DDFA_BENCH_SKIP_CPU=1 timeout 600 python bench.py --steps 30 --warmup 5 --no-secondary --no-variable ${AB_ARGS:-} > $OUT/${TAG}_lib_${v}_r${rep}.json 2> $OUT/${TAG}_lib_${v}_r${rep}.err
+          python - <<PY | tee -a $OUT/${TAG}_ab_lib.log
+import json
+d = json.load(open("$OUT/${TAG}_lib_${v}_r${rep}.json"))
+print("lib=$v rep $rep: %.0f graphs/s  %.4f ms/step  e2e %.0f | " % (d["value"], d["ms_per_step"], d["e2e"]["value"]) +
+      " ".join("%s %.1fus" % (l["kernel"][:12], l["avg_launch_us"]) for l in d["roofline_kernels"]))
+PY
+        done
+      done ;;
     kerneltests)
       timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 300 -s -x > $OUT/${TAG}_pytest_kernels.log 2>&1
       echo "pytest exit: $?"; tail -n 15 $OUT/${TAG}_pytest_kernels.log | cut -c1-300 ;;
