@@ -553,7 +553,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = D.FlowGNNGGNNModule(FEAT, CFG["input_dim"], CFG["hidden_dim"], CFG["n_steps"], CFG["layers"], concat_all_absdf=True,
                                 engine=args.engine).to(dev)
-    ctx.trainer = trainer = D.FusedTrainer(model)
+    # DDFA_AR_OVERLAP=0: one all-reduce of the whole flat buffer after the backward pass (A/B of the split exchange)
+    ctx.trainer = trainer = D.FusedTrainer(model, overlap_allreduce=os.environ.get("DDFA_AR_OVERLAP", "1") != "0")
 
     # ---- data-parallel self-check (SURVEY.md §8(e) "Determinism"): k steps sharded over the N ranks vs the same k steps of the
     # unsharded global batch on one rank, same seeds — the loss curves must agree (fp32 summation order is the only difference).
@@ -608,6 +609,8 @@ def run_ours(args):
         "roofline": primary.get("roofline"), "roofline_kernels": primary.get("roofline_kernels"),
         "secondary_workloads": secondary,
         "dp_parity": dp_parity,
+        "allreduce": None if world == 1 else ("split: small gradients on a side stream during the weight-gradient launch, GGNN weight "
+                                              "gradients after it" if trainer.overlap_allreduce else "single call after the backward pass"),
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_done} full train steps of one {args.graphs}-graph {workload_tag(args.graphs)} batch, oracle/ggnn_oracle.py (torch CPU)"},
         "final_loss": primary["final_loss"], "e2e_last_loss": primary["e2e_last_loss"],

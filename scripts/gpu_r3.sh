@@ -39,6 +39,10 @@ for STAGE in "$@"; do
         -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum|readout|embed_concat|sgemm_small" -s 80 -c 70 \
         -f -o $OUT/${TAG}_prof_step_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_step.log 2>&1
       echo "ncu step metrics exit: $?"; ls -la $OUT/*.ncu-rep ;;
+    ncu-gb)       # --set full + source of the gate backward kernel (two launches)
+      env $PROF_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_bwd_image" -s 10 -c 2 \
+        -f -o $OUT/${TAG}_prof_gatebwd_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_gb.log 2>&1
+      echo "ncu gate_bwd exit: $?" ;;
     ab-packed)    # whole-step A/B on this box: round-1 saved state (fp32 h_t + four fp32 gate planes) vs packed state
       bash scripts/gpu_ab.sh ${TAG} DDFA_PACKED_STATE 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_PACKED_STATE 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_packed_c0.log ;;
