@@ -1,0 +1,145 @@
+// K10' — the data-parallel exchange FUSED with the optimizer, over NVLink peer memory (no NCCL call in the step).
+//
+// Replaces, for R ranks on one NVSwitch domain, the sequence "all-reduce of the flat gradient buffer; Adam on every rank"
+// (reference: single-GPU `torch.optim.Adam`, DDFA/configs/config_default.yaml:43-47 — DDP is this repo's extension)
+// by ONE kernel per rank working on symmetric buffers every rank can address:
+//
+//   phase 1  "gradients complete": rank r tells every peer (a flag word in the PEER's memory, st.release.sys), then waits for
+//            the R flags in its own memory (ld.acquire.sys).  The kernels that produced the gradients precede this launch in
+//            stream order, so their writes are performed before the flag is.
+//   reduce-scatter + Adam + all-gather in one pass: rank r owns the r-th 1/R of the flat buffers.  For its elements it sums the R
+//            gradient copies straight out of the peers' memory (16-byte loads over NVLink, L1-bypassing), applies Adam with coupled L2
+//            (moments live only on the owner: optimizer state is sharded), and stores the new parameters into EVERY rank's
+//            parameter buffer (16-byte peer stores).  Bytes over the links per rank: (R-1)/R of the buffer in, the same out —
+//            1.3 MB each way at R = 8 for the 1.5 MB buffer, against the 2 x 2(R-1)/R of a ring all-reduce plus its latency steps.
+//   phase 2  "parameters complete": the last CTA of the grid (atomic ticket) fences, tells every peer, and waits for every peer's
+//            word — so when the kernel completes, (a) every rank has finished READING this rank's gradients (they may be zeroed for
+//            the next step) and (b) every owner has finished WRITING this rank's parameters (the next forward may read them).
+// The loss (one fp32 per rank after the gradients) is summed by every rank into a local output word.
+// Flags are epochs (step count + 1, identical on all ranks, read from device memory: the launch is CUDA-graph capturable);
+// every wait is bounded and traps instead of hanging the device.
+#include "common.cuh"
+
+namespace ddfa {
+namespace p2p {
+
+constexpr int kMaxRanks = 16;
+struct Peers {
+  float *params[kMaxRanks];
+  const float *grads[kMaxRanks];
+  uint32_t *flags[kMaxRanks];      // per rank: [0, R) phase-1 words, [R, 2R) phase-2 words, written by the rank of that index
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// peer gradients: system-scope relaxed load — never served from this SM's L1 (peer lines are L1-cacheable, B300_MICROARCH)
+__device__ __forceinline__ float4 ld_sys_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_epoch(const uint32_t *p, uint32_t epoch) {
+  for (uint32_t it = 0; it < (1u << 28); ++it)
+    if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return;
+  __trap();
+}
+
+__global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(const Peers pp, int rank, int world, float *__restrict__ m,
+                                                                 float *__restrict__ v, const int32_t *__restrict__ step_count,
+                                                                 int64_t numel, int64_t loss_off, float *__restrict__ loss_out,
+                                                                 uint32_t *__restrict__ ticket, float lr, float beta1, float beta2,
+                                                                 float eps, float wd) {
+  __shared__ float s_c[2];
+  __shared__ int s_last;
+  const int32_t t0 = *step_count;
+  const uint32_t epoch = (uint32_t)t0 + 1u;
+  if (threadIdx.x == 0) {
+    const double t = (double)(t0 + 1);
+    s_c[0] = (float)((double)lr / (1.0 - pow((double)beta1, t)));   // step_size
+    s_c[1] = (float)sqrt(1.0 - pow((double)beta2, t));              // bias_correction2_sqrt
+  }
+  // ---- phase 1
+  __threadfence_system();
+  if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(pp.flags[threadIdx.x] + rank, epoch);
+  if (threadIdx.x < world) wait_epoch(pp.flags[rank] + threadIdx.x, epoch);
+  __syncthreads();
+  const float step_size = s_c[0], bc2s = s_c[1];
+  // ---- this rank's slice, in 16-byte units (numel is a multiple of 4: the trainer aligns every parameter to 64 elements)
+  const int64_t n4 = numel >> 2;
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = (int64_t)rank * per, hi = min(n4, lo + per);
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < world; ++p) f4_add(g, ld_sys_f4(pp.grads[p] + 4 * i));     // rank order: the same sum on every run
+    float4 w = *reinterpret_cast<const float4 *>(pp.params[rank] + 4 * i);
+    float4 mi = *reinterpret_cast<const float4 *>(m + 4 * i), vi = *reinterpret_cast<const float4 *>(v + 4 * i);
+#define DDFA_ADAM1(f)                                        \
+  {                                                          \
+    const float gi = fmaf(wd, w.f, g.f);                     \
+    mi.f = fmaf(beta1, mi.f, (1.f - beta1) * gi);            \
+    vi.f = fmaf(beta2, vi.f, (1.f - beta2) * gi * gi);       \
+    w.f = w.f - step_size * (mi.f / (sqrtf(vi.f) / bc2s + eps)); \
+  }
+    DDFA_ADAM1(x) DDFA_ADAM1(y) DDFA_ADAM1(z) DDFA_ADAM1(w)
+#undef DDFA_ADAM1
+    *reinterpret_cast<float4 *>(m + 4 * i) = mi;
+    *reinterpret_cast<float4 *>(v + 4 * i) = vi;
+    for (int p = 0; p < world; ++p) *reinterpret_cast<float4 *>(pp.params[p] + 4 * i) = w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) {
+    float s = 0.f;
+    for (int p = 0; p < world; ++p) {
+      float x;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(pp.grads[p] + loss_off) : "memory");
+      s += x;
+    }
+    *loss_out = s;
+  }
+  // ---- phase 2
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence_system();
+  if (threadIdx.x < world) st_release_sys(pp.flags[threadIdx.x] + world + rank, epoch);
+  if (threadIdx.x < world) wait_epoch(pp.flags[rank] + world + threadIdx.x, epoch);
+}
+
+}  // namespace p2p
+}  // namespace ddfa
+
+extern "C" int ddfa_allreduce_adam_p2p(void *const *peer_params, const void *const *peer_grads, void *const *peer_flags, int32_t rank,
+                                       int32_t world, float *exp_avg, float *exp_avg_sq, int32_t *step_count, int64_t numel,
+                                       int64_t loss_offset, float *loss_out, uint32_t *ticket, float lr, float beta1, float beta2,
+                                       float eps, float weight_decay, void *stream_) {
+  using namespace ddfa;
+  DDFA_REQUIRE(world >= 1 && world <= p2p::kMaxRanks && rank >= 0 && rank < world, "ddfa_allreduce_adam_p2p: rank %d / world %d (max %d ranks)", rank,
+               world, p2p::kMaxRanks);
+  DDFA_REQUIRE(numel >= 0 && numel % 4 == 0, "ddfa_allreduce_adam_p2p: numel (%lld) must be a multiple of 4", (long long)numel);
+  DDFA_REQUIRE(peer_params && peer_grads && peer_flags && exp_avg && exp_avg_sq && step_count && ticket, "ddfa_allreduce_adam_p2p: NULL pointer");
+  p2p::Peers pp = {};
+  for (int p = 0; p < world; ++p) {
+    DDFA_REQUIRE(peer_params[p] && peer_grads[p] && peer_flags[p] && aligned16(peer_params[p]) && aligned16(peer_grads[p]),
+                 "ddfa_allreduce_adam_p2p: peer %d pointer NULL or unaligned", p);
+    pp.params[p] = static_cast<float *>(peer_params[p]);
+    pp.grads[p] = static_cast<const float *>(peer_grads[p]);
+    pp.flags[p] = static_cast<uint32_t *>(peer_flags[p]);
+  }
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t per = ((numel >> 2) + world - 1) / world;
+  int blocks = (int)((per + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;        // all CTAs must be co-resident: they spin on flags (64 x 256 threads fit any idle B200)
+  p2p::allreduce_adam_p2p_kernel<<<blocks, 256, 0, stream>>>(pp, rank, world, exp_avg, exp_avg_sq, step_count, numel, loss_offset, loss_out, ticket,
+                                                             lr, beta1, beta2, eps, weight_decay);
+  DDFA_CHECK_LAUNCH("allreduce_adam_p2p_kernel");
+  return adam_step_inc_launch(step_count, stream);
+}

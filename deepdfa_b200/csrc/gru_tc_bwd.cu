@@ -185,6 +185,196 @@ __global__ void __launch_bounds__(32 * kGbWarps, 2) gate_bwd_image_kernel(const 
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// (1') gate backward, TMA-staged (packed saved state).  The register-path kernel above is load-latency-bound: ncu on C1
+// (profiles/r03i) shows 170 us for 731 MB = 4.3 TB/s, DRAM 52 %, 85 % of the stall samples on long_scoreboard — 16 warps per SM
+// with ~128 bytes of streaming loads in flight per lane do not cover the loaded DRAM latency, and the register file (128 x 512)
+// admits no more.  Here the three STREAMING operands of a row block — dh (fp32), the packed gates and h (image pieces, or fp32 for
+// step 0) — are contiguous in memory, so a producer warp moves them with TMA bulk copies into a three-stage shared-memory ring
+// (3 x 64 KB in flight per SM, no registers), and 16 consumer warps read them with LDS; only the gathered ds rows of the folded
+// transposed edge gather (data-dependent addresses) remain register loads, and they hit L2 (dgrad wrote them a kernel ago).
+// One CTA per SM, block of 32 consecutive rows per stage, warp w owns rows w and w + 16 of the block, lane = 4 columns as before:
+// same arithmetic, same summation order of the gather, same outputs.
+// -------------------------------------------------------------------------------------------------
+constexpr int kGtRows = 32, kGtStages = 3, kGtConsumers = 16, kGtPre = 2;
+constexpr int kGtOffD = 0, kGtOffG = kGtRows * kD * 4, kGtOffH = kGtOffG + kGtRows * kD * 8;          // 16 KB | 32 KB | 16 KB
+constexpr int kGtStageBytes = kGtOffH + kGtRows * kD * 4;                                              // 64 KB
+constexpr int kGtOffBar = kGtStages * kGtStageBytes;
+constexpr int kGtSmem = kGtOffBar + 2 * kGtStages * 8 + 16;
+constexpr int kGtThreads = 32 * kGtConsumers;
+
+template <bool HF32>      // h operand: fp32 rows (step 0: h_0 = x) or the activation image
+__global__ void __launch_bounds__(kGtThreads, 1) gate_bwd_tma_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
+                                                                     const uint8_t *__restrict__ h_img_src, const uint2 *__restrict__ gates_packed,
+                                                                     const int32_t *__restrict__ indptr, const float *__restrict__ ds_in,
+                                                                     const int32_t *__restrict__ indptr_t, const int32_t *__restrict__ indices_t,
+                                                                     int32_t N, uint8_t *__restrict__ q_img, size_t img_stride,
+                                                                     float *__restrict__ dhz, float *__restrict__ db_fold, float *__restrict__ db_ih,
+                                                                     float *__restrict__ db_hh, int hints) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kGtOffBar;
+  auto full = [&](int i) { return bar0 + 8u * i; };
+  auto empty = [&](int i) { return bar0 + 8u * (kGtStages + i); };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t Npad = ((int64_t)N + kTileM - 1) / kTileM * kTileM;
+  const int num_blocks = (int)(Npad / kGtRows);
+  const int my_blocks = (num_blocks > (int)blockIdx.x) ? (num_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGtStages; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), kGtConsumers); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  float4 sum[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // the copies of block k into its stage: issued by one lane of warp 0 — ahead of the loop for the first kGtStages blocks, then
+  // each time warp 0 has finished a block (a dedicated producer warp would make 17 warps = 640 allocated threads = 96 registers;
+  // 16 warps get 128 and the kernel does not spill)
+  auto fill = [&](int k) {
+    const uint64_t pol_saved = l2_policy((hints & 2) ? 1 : 0), pol_dh = l2_policy((hints & 8) ? 1 : 0);
+    const int stage = k % kGtStages;
+    const int64_t r0 = (int64_t)(blockIdx.x + (int64_t)k * gridDim.x) * kGtRows;
+    const int valid = (int)max((int64_t)0, min((int64_t)kGtRows, (int64_t)N - r0));      // rows that exist in the [N, ...] arrays
+    const uint32_t dst = sbase + stage * kGtStageBytes;
+    const uint32_t bytes = (uint32_t)valid * (kD * 4 + kD * 8) + (HF32 ? (uint32_t)valid * kD * 4 : (uint32_t)kGtRows * kD * 4);
+    mbar_arrive_expect_tx(full(stage), bytes);
+    if (valid > 0) {
+      bulk_g2s_hint(dst + kGtOffD, dh_out + r0 * kD, (uint32_t)valid * kD * 4, full(stage), pol_dh);
+      bulk_g2s_hint(dst + kGtOffG, gates_packed + r0 * kD, (uint32_t)valid * kD * 8, full(stage), pol_saved);
+    }
+    if (HF32) {
+      if (valid > 0) bulk_g2s_hint(dst + kGtOffH, h + r0 * kD, (uint32_t)valid * kD * 4, full(stage), pol_saved);
+    } else {      // the block's 32 rows of each of the four [128 x 64] bf16 chunks: 4 KB pieces (the image is padded to whole tiles)
+      const uint8_t *tile = h_img_src + (size_t)(r0 >> 7) * kImageTileBytes + (size_t)(r0 & 127) * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) bulk_g2s_hint(dst + kGtOffH + ch * (kGtRows * 128), tile + (size_t)ch * kChunkBytes, kGtRows * 128, full(stage), pol_saved);
+    }
+  };
+  if (warp == 0 && elect_one())
+    for (int k = 0; k < kGtStages && k < my_blocks; ++k) fill(k);
+  __syncwarp();
+  {
+    // ===== consumers =====
+    const int col = lane * 4;
+    const uint64_t pol_tmp = l2_policy((hints & 4) ? 2 : 0);
+    for (int k = 0; k < my_blocks; ++k) {
+      const int stage = k % kGtStages, use = k / kGtStages;
+      const int64_t r0 = (int64_t)(blockIdx.x + (int64_t)k * gridDim.x) * kGtRows;
+      // the two rows of this warp and their CSR data (global, independent of the staged operands: requested before the wait)
+      int64_t node[2];
+      bool ok[2];
+      int tb[2], te[2], ip0[2], ip1[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        node[r] = r0 + warp + 16 * r;
+        ok[r] = node[r] < N;
+        tb[r] = te[r] = ip0[r] = ip1[r] = 0;
+        if (ok[r]) {
+          ip0[r] = __ldcg(indptr + node[r]); ip1[r] = __ldcg(indptr + node[r] + 1);
+          if (indptr_t) { tb[r] = __ldcg(indptr_t + node[r]); te[r] = __ldcg(indptr_t + node[r] + 1); }
+        }
+      }
+      // the first kGtPre neighbours of both rows are fetched ahead of the stage (a CFG node has ~2 in-edges); longer lists finish below
+      int id[2][kGtPre];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < kGtPre; ++q) id[r][q] = (tb[r] + q < te[r]) ? __ldcg(indices_t + tb[r] + q) : -1;
+      float4 gv[2][kGtPre];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < kGtPre; ++q) gv[r][q] = id[r][q] >= 0 ? ldg_cg_f4(ds_in + (size_t)id[r][q] * kD + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(full(stage), use & 1);
+      const uint8_t *st = smem + stage * kGtStageBytes;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = warp + 16 * r;                   // row inside the block
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), hv = d, rr = d, zz = d, nn = d, gh = d;
+        if (ok[r]) {
+          d = *reinterpret_cast<const float4 *>(st + kGtOffD + row * (kD * 4) + col * 4);
+          const uint4 g0 = *reinterpret_cast<const uint4 *>(st + kGtOffG + row * (kD * 8) + col * 8);
+          const uint4 g1 = *reinterpret_cast<const uint4 *>(st + kGtOffG + row * (kD * 8) + col * 8 + 16);
+          unpack_gates(make_uint2(g0.x, g0.y), rr.x, zz.x, nn.x, gh.x);
+          unpack_gates(make_uint2(g0.z, g0.w), rr.y, zz.y, nn.y, gh.y);
+          unpack_gates(make_uint2(g1.x, g1.y), rr.z, zz.z, nn.z, gh.z);
+          unpack_gates(make_uint2(g1.z, g1.w), rr.w, zz.w, nn.w, gh.w);
+          if (HF32) {
+            hv = *reinterpret_cast<const float4 *>(st + kGtOffH + row * (kD * 4) + col * 4);
+          } else {      // piece [v][kb = col / 64] of 32 rows x 128 B; 16-byte units swizzled by (global row) & 7 == row & 7 (blocks start at multiples of 32)
+            const uint32_t off = (uint32_t)((col >> 6) * (kGtRows * 128) + row * 128 + (((((col & 63) >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
+            const uint2 hh = *reinterpret_cast<const uint2 *>(st + kGtOffH + off);
+            const uint2 hl = *reinterpret_cast<const uint2 *>(st + kGtOffH + 2 * (kGtRows * 128) + off);
+            const float4 a = bf16x4_to_f4(hh), b = bf16x4_to_f4(hl);
+            hv = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+          }
+#pragma unroll
+          for (int q = 0; q < kGtPre; ++q) f4_add(d, gv[r][q]);
+          for (int j = tb[r] + kGtPre; j < te[r]; ++j) f4_add(d, ldg_cg_f4(ds_in + (size_t)__ldcg(indices_t + j) * kD + col));
+        }
+        float4 qr = make_float4(0.f, 0.f, 0.f, 0.f), qz = qr, qn = qr, qnr = qr;
+        if (ok[r]) {
+          const float deg = (float)(ip1[r] - ip0[r]);
+          st_f4_hint(dhz + (size_t)node[r] * kD + col, make_float4(d.x * zz.x, d.y * zz.y, d.z * zz.z, d.w * zz.w), pol_tmp);
+#define BWDQ2(f)                                         \
+  {                                                      \
+    const float dz_ = d.f * (hv.f - nn.f);               \
+    const float dn_ = d.f * (1.f - zz.f);                \
+    qn.f = dn_ * (1.f - nn.f * nn.f);                    \
+    qz.f = dz_ * zz.f * (1.f - zz.f);                    \
+    qr.f = qn.f * gh.f * rr.f * (1.f - rr.f);            \
+    qnr.f = qn.f * rr.f;                                 \
+  }
+          BWDQ2(x) BWDQ2(y) BWDQ2(z) BWDQ2(w)
+#undef BWDQ2
+          f4_add(sum[0], qr); f4_add(sum[1], qz); f4_add(sum[2], qn); f4_add(sum[3], qnr);
+          f4_fma(sum[4], deg, qr); f4_fma(sum[5], deg, qz); f4_fma(sum[6], deg, qn);
+        }
+        if (node[r] < Npad) {      // rows N .. Npad-1 are written as zeros (the weight-gradient GEMM sums over all 128 rows of a tile)
+          const size_t o_hi = image_offset(node[r], col, 0), o_lo = image_offset(node[r], col, 1);
+          uint2 ph, pl;
+          split4(qr, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 0 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 0 * img_stride + o_lo) = pl;
+          split4(qz, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 1 * img_stride + o_lo) = pl;
+          split4(qn, ph, pl);  *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 2 * img_stride + o_lo) = pl;
+          split4(qnr, ph, pl); *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_hi) = ph; *reinterpret_cast<uint2 *>(q_img + 3 * img_stride + o_lo) = pl;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty(stage));      // this warp has read its rows of the stage
+      if (warp == 0 && k + kGtStages < my_blocks) {  // refill the stage with block k + kGtStages once all 16 warps have released it
+        if (elect_one()) {
+          mbar_wait(empty(stage), use & 1);
+          fill(k + kGtStages);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // bias gradients: column sums of the 16 consumer warps, through the (now idle) first stage
+  __syncthreads();
+  float *red = reinterpret_cast<float *>(smem);
+  {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) *reinterpret_cast<float4 *>(&red[(warp * 7 + i) * kD + lane * 4]) = sum[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 7 * kD; i += kGtThreads) {
+    float v_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGtConsumers; ++w) v_ += red[(w * 7) * kD + i];
+    const int which = i >> 7, c_ = i & 127;
+    if (which == 0) { atomicAdd(db_ih + c_, v_); atomicAdd(db_hh + c_, v_); }
+    else if (which == 1) { atomicAdd(db_ih + kD + c_, v_); atomicAdd(db_hh + kD + c_, v_); }
+    else if (which == 2) atomicAdd(db_ih + 2 * kD + c_, v_);
+    else if (which == 3) atomicAdd(db_hh + 2 * kD + c_, v_);
+    else atomicAdd(db_fold + (which - 4) * kD + c_, v_);
+  }
+}
+
 // =================================================================================================
 // (2) dgrad, weight-in-TMEM orientation ("dgrad3")
 // =================================================================================================
@@ -696,6 +886,22 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     const int64_t want = (rows + tc2b::kGbWarps - 1) / tc2b::kGbWarps;
     gb_grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
   }
+  if (gates_packed && gate_bwd_tma()) {
+    // TMA-staged form (packed saved state only): one CTA per SM, three 64 KB stages
+    const int blocks32 = (int)(rows / tc2b::kGtRows);
+    const int grid = blocks32 < kNumSMs ? blocks32 : kNumSMs;
+    if (h) {
+      DDFA_CUDA(cudaFuncSetAttribute(tc2b::gate_bwd_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kGtSmem));
+      DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_tma_kernel<true>, dim3(grid), dim3(tc2b::kGtThreads), tc2b::kGtSmem, stream, dh_out, h,
+                             static_cast<const uint8_t *>(h_img_in), static_cast<const uint2 *>(gates_packed), indptr, ds_in,
+                             ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, dhz, db_fold, db_ih, db_hh, l2_hints()));
+    } else {
+      DDFA_CUDA(cudaFuncSetAttribute(tc2b::gate_bwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kGtSmem));
+      DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_tma_kernel<false>, dim3(grid), dim3(tc2b::kGtThreads), tc2b::kGtSmem, stream, dh_out, h,
+                             static_cast<const uint8_t *>(h_img_in), static_cast<const uint2 *>(gates_packed), indptr, ds_in,
+                             ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, dhz, db_fold, db_ih, db_hh, l2_hints()));
+    }
+  } else
   DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h,
                          static_cast<const uint8_t *>(h_img_in), gates, static_cast<const uint4 *>(gates_packed), indptr, ds_in,
                          ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, h_img_in ? nullptr : h_img_ws, dhz, db_fold, db_ih, db_hh,

@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float *__restrict__ p, c
 }
 __global__ void adam_step_inc_kernel(int32_t *step_count) { *step_count += 1; }
 
+int adam_step_inc_launch(int32_t *step_count, cudaStream_t stream) {
+  adam_step_inc_kernel<<<1, 1, 0, stream>>>(step_count);
+  DDFA_CHECK_LAUNCH("adam_step_inc_kernel");
+  return DDFA_OK;
+}
+
 }  // namespace ddfa
 
 extern "C" {
@@ -116,9 +122,7 @@ int ddfa_adam_flat(float *params, const float *grads, float *exp_avg, float *exp
                                                                          beta1, beta2, eps, weight_decay);
     DDFA_CHECK_LAUNCH("adam_flat_kernel");
   }
-  adam_step_inc_kernel<<<1, 1, 0, stream>>>(step_count);
-  DDFA_CHECK_LAUNCH("adam_step_inc_kernel");
-  return DDFA_OK;
+  return adam_step_inc_launch(step_count, stream);
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ class FusedTrainer:
     def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False, max_graph_shapes: int = 8,
                  max_resident_graphs: int = 64, distributed: bool = True, bucket_nodes: int = 0, bucket_edges: int = 0,
-                 bucket_min_pad_nodes: int = 64, overlap_allreduce: bool = True):
+                 bucket_min_pad_nodes: int = 64, overlap_allreduce: bool = True, exchange: str = "nccl"):
         """``distributed=False`` makes this a single-rank trainer even inside an initialised process group (no all-reduce).
         ``bucket_nodes`` / ``bucket_edges`` > 0 switch on shape bucketing for HOST batches under ``use_cuda_graph``: every batch
         is padded with ONE dummy graph of isolated nodes up to the next multiple of ``bucket_nodes`` nodes (at least
@@ -48,6 +48,12 @@ class FusedTrainer:
         # [w_msg, b_msg, w_ih, w_hh] (0.46 MB of the 1.5 MB) is reduced after it.  False: one all-reduce of the whole buffer.
         self.overlap_allreduce = bool(overlap_allreduce)
         self._ar_stream = None
+        # exchange = "p2p": no NCCL call in the step — the flat parameter and gradient buffers live in symmetric (peer-mapped)
+        # memory and ONE kernel per rank does reduce-scatter + Adam + all-gather over NVLink (ddfa_allreduce_adam_p2p); optimizer
+        # moments are sharded (each rank keeps them for its 1/R slice only).  Single node.  "nccl" (default): all-reduce + ddfa_adam_flat.
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {exchange!r}")
+        self.exchange = exchange if self.world > 1 else "nccl"
         self.use_cuda_graph = use_cuda_graph
         # a captured graph bakes in the batch SHAPE (and, for resident batches, the batch object): cap how many are kept so a
         # stream of ever-new shapes (un-bucketed real data) degrades to eager launches instead of growing without bound
@@ -62,8 +68,11 @@ class FusedTrainer:
         ntab = len(module._tables())
         self._gemm_grad_range = (offs[ntab], offs[ntab + 4])     # flat offsets of [w_msg, b_msg, w_ih, w_hh]
         with torch.cuda.device(self.device):
-            self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
-            self.flat_g = torch.zeros(total + _ALIGN, dtype=torch.float32, device=self.device)  # [+ loss slot]
+            if self.exchange == "p2p":
+                self._setup_p2p(total)
+            else:
+                self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
+                self.flat_g = torch.zeros(total + _ALIGN, dtype=torch.float32, device=self.device)  # [+ loss slot]
             self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
             self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
             self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -76,7 +85,10 @@ class FusedTrainer:
         K, nl = len(module._tables()), module._num_layers
         self.params = E.ParamPack.from_flat_list([p.data for p in plist], K, nl)
         self.grads = E.ParamPack.from_flat_list(gviews, K, nl)
-        self.loss_slot = self.flat_g[total:total + 1]
+        self.loss_slot = self.flat_g[total:total + 1]          # this rank's share of the loss goes here (the kernels' loss_out)
+        if self.exchange == "p2p":                                # ... and the global loss into a local word (peers read the slot above)
+            self._loss_local = self.loss_slot
+            self.loss_slot = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.ws = E.Workspace(self.device)
         self._graphs = {}
         self._stream_slots = {}
@@ -84,6 +96,28 @@ class FusedTrainer:
         self._warm_shapes = set()
 
     # ------------------------------------------------------------------------------------
+    def _setup_p2p(self, total: int):
+        """Symmetric allocations + rendezvous (torch.distributed._symmetric_memory): every rank gets device pointers to every
+        rank's parameter / gradient / flag buffers."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            self.flat_p = symm.empty(total, dtype=torch.float32, device=self.device)
+            self.flat_g = symm.empty(total + _ALIGN, dtype=torch.float32, device=self.device)
+            self._flags = symm.empty(64, dtype=torch.int32, device=self.device)
+            self.flat_p.zero_(); self.flat_g.zero_(); self._flags.zero_()
+            torch.cuda.synchronize(self.device)
+            hp, hg, hf = (symm.rendezvous(t, group) for t in (self.flat_p, self.flat_g, self._flags))
+            self._peer_ptrs = tuple([int(x) for x in h.buffer_ptrs] for h in (hp, hg, hf))
+            self._symm_handles = (hp, hg, hf)
+            self._p2p_rank = dist.get_rank(group)
+        except Exception as exc:       # no silent downgrade to NCCL: the caller asked for the peer-memory exchange
+            raise _lib.DdfaError(f"exchange='p2p': symmetric-memory setup failed ({type(exc).__name__}: {exc})") from exc
+        if len(self._peer_ptrs[0]) != self.world or 2 * self.world > 64:
+            raise _lib.DdfaError("exchange='p2p': unexpected symmetric-memory world size")
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group)            # every rank's flag words are zero before anyone's first kernel can write one
+
     def _global_batch(self, global_batch: Optional[int], local_graphs: int) -> int:
         """The divisor of the mean BCE (base_module.py:74,183).  Ranks generally hold different numbers of graphs
         (batched_graph.split_batch balances by nodes), so with more than one rank the caller must say what the global batch is."""
@@ -101,7 +135,16 @@ class FusedTrainer:
         self.flat_g.zero_()
         _, logits, saved = E.forward(self.params, dg, idx, m.hparams.n_steps, training=True, engine=eng, alloc=self.ws)
         _, _, dlogits = E.graph_label_bce(dg, vuln, logits, pw, 1.0 / global_batch, 1.0 / global_batch, True,
-                                          alloc=self.ws, loss_out=self.loss_slot, num_valid=num_valid)
+                                          alloc=self.ws, loss_out=self._loss_local if self.exchange == "p2p" else self.loss_slot,
+                                          num_valid=num_valid)
+        if self.exchange == "p2p":
+            E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws)
+            pp, pg_, pf = self._peer_ptrs
+            _lib.lib().call("ddfa_allreduce_adam_p2p", _lib.ptr_array(pp), _lib.ptr_array(pg_), _lib.ptr_array(pf), self._p2p_rank, self.world,
+                            self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.numel, self.numel,
+                            self.loss_slot.data_ptr(), self._ticket.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                            self.weight_decay, torch.cuda.current_stream().cuda_stream)
+            return
         split = self.world > 1 and self.overlap_allreduce
         E.backward(self.params, dg, saved, self.grads, dlogits=dlogits, engine=eng, alloc=self.ws,
                    on_small_grads_ready=self._reduce_small_grads if split else None)
@@ -369,7 +412,8 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------------------------
     @staticmethod
-    def dp_self_check(engine: str, device, rank: int, world: int, steps: int = 5, graphs_per_rank: int = 24, nodes: int = 60) -> dict:
+    def dp_self_check(engine: str, device, rank: int, world: int, steps: int = 5, graphs_per_rank: int = 24, nodes: int = 60,
+                      exchange: str = "nccl") -> dict:
         """On-hardware data-parallel parity (SURVEY.md §8(e) "Determinism"): ``steps`` optimisation steps of a global batch
         sharded over the ``world`` ranks (node-balanced shards of different sizes, NCCL all-reduce) against the same steps of
         the UNSHARDED batch on this rank alone, same seeds.  fp32 summation order is the only difference.  Collective: every
@@ -381,7 +425,7 @@ class FusedTrainer:
         def make(distributed):
             torch.manual_seed(4321)
             m = FlowGNNGGNNModule(feat, 1002, 32, 8, 2, concat_all_absdf=True, positive_weight=4.0, engine=engine).to(device)
-            return m, FusedTrainer(m, distributed=distributed)
+            return m, FusedTrainer(m, distributed=distributed, exchange=exchange if distributed else "nccl")
         m_dp, tr_dp = make(True)
         m_1, tr_1 = make(False)
         l_dp, l_1 = [], []
@@ -393,4 +437,4 @@ class FusedTrainer:
         dparam = max(float((p.data - q.data).abs().max()) for p, q in zip(m_dp.param_list(), m_1.param_list()))
         return {"steps": steps, "world": world, "global_batch": graphs_per_rank * world, "loss_sharded": l_dp, "loss_single_rank": l_1,
                 "max_abs_loss_diff": max(abs(a - b) for a, b in zip(l_dp, l_1)), "max_abs_param_diff": dparam,
-                "shard_sizes_differ": True}
+                "shard_sizes_differ": True, "exchange": exchange}

@@ -55,7 +55,8 @@ enum {
   DDFA_TUNE_PDL_MASK = 1,       /* bit mask of kernels launched with programmatic stream serialization, default 15 */
   DDFA_TUNE_GATHER_VARIANT = 2, /* launch shape of the D = 128 edge gather (ddfa_gather_sum_variant ids), default 9 */
   DDFA_TUNE_FWD_PAIR = 3,       /* 1: forward GRU kernel launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (default 0) */
-  DDFA_TUNE__COUNT = 4
+  DDFA_TUNE_GATE_BWD_TMA = 4,   /* 1 (default): gate backward streams dh / gates / h through a TMA-fed shared-memory ring; 0: register loads */
+  DDFA_TUNE__COUNT = 5
 };
 int ddfa_tuning_set(int key, int value);
 int ddfa_tuning_get(int key);
@@ -329,6 +330,23 @@ int ddfa_graph_label_bce_valid(const float *logits, const int32_t *vuln, const i
 int ddfa_adam_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                    int32_t *step_count, int64_t numel, float lr, float beta1, float beta2, float eps,
                    float weight_decay, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K10'  The data-parallel exchange fused with the optimizer over NVLink peer memory: ONE kernel per rank does
+ * reduce-scatter (16-byte loads from every peer's gradient buffer) + Adam with coupled L2 on the rank's 1/R slice (moments are
+ * sharded: exp_avg / exp_avg_sq are touched only inside the slice) + all-gather (16-byte stores of the new parameters into every
+ * peer's parameter buffer), bracketed by two flag barriers in peer memory (csrc/allreduce_adam.cu).  Replaces
+ * ncclAllReduce(flat gradients) + ddfa_adam_flat on every rank.  Collective: every rank launches it once per step.
+ *   peer_params / peer_grads / peer_flags: HOST arrays of `world` device pointers, entry p = rank p's buffer as addressable from
+ *   this device (symmetric allocation, peer-mapped); flags: >= 2 * world uint32 per rank, zero-initialised once;
+ *   numel % 4 == 0; loss_offset: element index inside the gradient buffers of the per-rank loss word (summed into *loss_out,
+ *   a LOCAL word; may be NULL); ticket: one zero-initialised local uint32; step_count as in ddfa_adam_flat (read as the
+ *   barrier epoch, then incremented).  CUDA-graph capturable; waits are bounded (trap, not hang).
+ * ------------------------------------------------------------------------------------- */
+int ddfa_allreduce_adam_p2p(void *const *peer_params, const void *const *peer_grads, void *const *peer_flags,
+                            int32_t rank, int32_t world, float *exp_avg, float *exp_avg_sq, int32_t *step_count,
+                            int64_t numel, int64_t loss_offset, float *loss_out, uint32_t *ticket, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Generic row-major fp32 GEMM on the SIMT engine (building block, exported for tests):

@@ -1,6 +1,7 @@
 #!/bin/bash
 # N-GPU bench lines on one box (run under `gpurun --gpus N`):  bash scripts/gpu_n2.sh <tag> <N>
-# split vs single all-reduce, C1 per GPU; then C0 (where the exchange is 4x larger relative to the step)
+# exchange A/B on one box: NCCL split (default) / fused peer-memory kernel / NCCL single call — C1 per GPU, then C0 (where the
+# exchange is 4x larger relative to the step)
 set -u
 TAG=$1; N=${2:-2}
 OUT=gpurun_out; mkdir -p $OUT
@@ -17,7 +18,8 @@ except Exception as e:
 PY
 }
 run c1_split "DDFA_AR_OVERLAP=1" ""
+run c1_p2p "DDFA_EXCHANGE=p2p" ""
 run c1_single "DDFA_AR_OVERLAP=0" ""
 run c0_split "DDFA_AR_OVERLAP=1" "--graphs 256"
+run c0_p2p "DDFA_EXCHANGE=p2p" "--graphs 256"
 run c0_single "DDFA_AR_OVERLAP=0" "--graphs 256"
-run c1_split_2 "DDFA_AR_OVERLAP=1" ""

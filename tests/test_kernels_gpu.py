@@ -447,6 +447,30 @@ def test_gru_step_image_entries_v2(graphs, nodes):
         worst[name] = float((got.cpu().double() - ref).abs().max()) / scale
     print(f"image v2 backward (packed gates), N={N}: worst |err| / max(1, |ref|max) per output: " + ", ".join(f"{k_}={v:.1e}" for k_, v in worst.items()))
     assert max(worst.values()) < 3e-4, worst
+    # the TMA-staged gate backward (default) and the register-path kernel: same q images -> identical ds / dh, same bias sums
+    # up to the order of their float atomics; also the step-0 form (fp32 h operand given)
+    from deepdfa_b200._lib import TUNE_GATE_BWD_TMA
+    outs = {}
+    try:
+        for mode in (1, 0):
+            L.call("ddfa_tuning_set", TUNE_GATE_BWD_TMA, mode)
+            for h_arg in (None, _p(h32)):
+                ds2, dh2 = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
+                acc2 = {n_: torch.zeros(sh, device=DEV) for n_, sh in (("dwf", (3 * D, D)), ("dbf", (3 * D,)), ("dbih", (3 * D,)), ("dwhh", (3 * D, D)), ("dbhh", (3 * D,)))}
+                L.call("ddfa_gru_step_bwd_image_v2", _p(dpart_d), _p(dsprev_d), _p(dg.indptr_t), _p(dg.indices_t), h_arg, _p(h_img), _p(s_img), _p(gates),
+                       _p(dg.indptr), N, D, _p(ds2), _p(dh2), _p(acc2["dwf"]), _p(acc2["dbf"]), _p(acc2["dbih"]), _p(acc2["dwhh"]), _p(acc2["dbhh"]),
+                       _p(ws_b), wsb_b, 0, st())
+                torch.cuda.synchronize()
+                outs[(mode, h_arg is None)] = (ds2, dh2, acc2)
+    finally:
+        L.call("ddfa_tuning_set", TUNE_GATE_BWD_TMA, 1)
+    for key in ((1, True), (1, False)):
+        a, b = outs[key], outs[(0, key[1])]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), key
+        for n_ in ("dbf", "dbih", "dbhh"):
+            assert (a[2][n_] - b[2][n_]).abs().max() < 1e-4 * max(1.0, float(b[2][n_].abs().max())), (key, n_)
+    assert torch.equal(outs[(1, True)][0], ds) and torch.equal(outs[(1, True)][1], dh)
+    assert (outs[(1, False)][0] - ds).abs().max() < 1e-3 * max(1.0, float(ds.abs().max()))      # fp32 h vs hi + lo: 2^-17 apart
 
 
 @pytest.mark.parametrize("graphs,nodes", [(3, 50), (40, 150), (1024, 150)])
@@ -635,3 +659,47 @@ def test_adam_flat_matches_torch_adam():
         lib().call("ddfa_adam_flat", _p(p), _p(dk(g)), _p(m), _p(v), _p(step), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, st())
     assert int(step) == 6
     assert (p.cpu() - ref.detach()).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_allreduce_adam_p2p_protocol_on_one_device(world):
+    """ddfa_allreduce_adam_p2p (reduce-scatter + Adam + all-gather over peer memory, two flag barriers): `world` ranks emulated
+    on ONE device — every rank has its own parameter / gradient / flag / moment buffers and its kernel runs on its own stream,
+    concurrently with the others (they spin on each other's flags, as over NVLink).  Against torch.optim.Adam (coupled L2) on the
+    summed gradient, several steps (epochs advance, flags are reused)."""
+    torch.manual_seed(world)
+    n = 64 * 97                                            # multiple of 64 like the trainer's flat buffers; not a multiple of world * 256
+    p0 = torch.randn(n, device=DEV)
+    params = [p0.clone() for _ in range(world)]
+    grads = [torch.zeros(n + 64, device=DEV) for _ in range(world)]
+    flags = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
+    m = [torch.zeros(n, device=DEV) for _ in range(world)]
+    v = [torch.zeros(n, device=DEV) for _ in range(world)]
+    step = [torch.zeros(1, dtype=torch.int32, device=DEV) for _ in range(world)]
+    ticket = [torch.zeros(1, dtype=torch.int32, device=DEV) for _ in range(world)]
+    loss_out = [torch.zeros(1, device=DEV) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-2)
+    L = lib()
+    pp, pg, pf = ptr_array([_p(t) for t in params]), ptr_array([_p(t) for t in grads]), ptr_array([_p(t) for t in flags])
+    for it in range(4):
+        gs = [torch.randn(n, device=DEV) * 0.1 for _ in range(world)]
+        for r in range(world):
+            grads[r][:n].copy_(gs[r])
+            grads[r][n] = float(r + 1 + it)               # the per-rank loss word
+        torch.cuda.synchronize()
+        for r in range(world):
+            L.call("ddfa_allreduce_adam_p2p", pp, pg, pf, r, world, _p(m[r]), _p(v[r]), _p(step[r]), n, n, _p(loss_out[r]), _p(ticket[r]),
+                   1e-3, 0.9, 0.999, 1e-8, 1e-2, streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        ref.grad = torch.stack(gs).sum(0)
+        opt.step()
+        for r in range(world):
+            assert (params[r] - ref.detach()).abs().max() < 2e-6, (it, r)
+            assert torch.equal(params[r], params[0])      # every rank holds the same bits
+            assert abs(float(loss_out[r]) - sum(q + 1 + it for q in range(world))) < 1e-5
+            assert int(step[r]) == it + 1 and int(ticket[r]) == 0
+    with pytest.raises(DdfaError):
+        L.call("ddfa_allreduce_adam_p2p", pp, pg, pf, world, world, _p(m[0]), _p(v[0]), _p(step[0]), n, n, None, _p(ticket[0]),
+               1e-3, 0.9, 0.999, 1e-8, 1e-2, st())
