@@ -49,6 +49,9 @@ for STAGE in "$@"; do
     pairtest)     # the CTA-pair forward kernel alone, short timeout (first runs of a new synchronisation protocol)
       timeout 240 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 200 -s -x -k "cta_pair" > $OUT/${TAG}_pytest_pair.log 2>&1
       echo "pair pytest exit: $?"; tail -n 12 $OUT/${TAG}_pytest_pair.log | cut -c1-300 ;;
+    ab-gbtma)     # gate backward: register-path kernel vs TMA-staged kernel, same library, same box
+      bash scripts/gpu_ab.sh ${TAG} DDFA_GATE_BWD_TMA 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_gbtma_c1.log
+      bash scripts/gpu_ab.sh ${TAG}c0 DDFA_GATE_BWD_TMA 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_gbtma_c0.log ;;
     ab-pair)
       bash scripts/gpu_ab.sh ${TAG} DDFA_FWD_PAIR 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_FWD_PAIR 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c0.log ;;
