@@ -370,7 +370,7 @@ def measure_workload(ctx, args, graphs, full):
     torch.cuda.synchronize()
     launches_per_step = L.call("ddfa_launch_count") - l0
 
-    if full:
+    if full and not args.quick:
         # ---- instrumented region (eager launches): CUDA-event pairs around every gather / GRU-step call -> roofline -----
         prof = SpanProfiler(["gather_fwd", "gather_bwd", "ddfa_gru_step_fwd", "ddfa_gru_step_bwd", "wgrad_batched"])
         E.profile_hook = prof
@@ -445,7 +445,7 @@ def measure_workload(ctx, args, graphs, full):
                           + (" (one CUDA graph per batch shape, two static input-buffer sets, next batch prefetched on a copy stream)"
                              if trainer.use_cuda_graph else " (eager launches)")}
     res["e2e_last_loss"] = state["loss"]
-    if not full:
+    if not full or args.quick:
         return res
 
     # ---- batch producer: the same step fed from a device-resident graph arena by graph-id lists.  Reported
@@ -589,7 +589,7 @@ def run_ours(args):
         return leave()
 
     # ---- cpu baseline on this box's host cores (bounded sample) ----------------------------------------
-    if os.environ.get("DDFA_BENCH_SKIP_CPU") == "1":     # profiler runs only
+    if os.environ.get("DDFA_BENCH_SKIP_CPU") == "1" or args.quick:     # profiler / scaling A/B runs only
         cpu_val, cpu_s, cpu_done, cpu_threads = None, None, 0, 0
     else:
         cpu_val, cpu_s, cpu_done, cpu_threads = cpu_train_steps(args.graphs, 8, 1, budget_s=20.0)
@@ -633,6 +633,7 @@ def main():
     ap.add_argument("--no-graphs", dest="cuda_graphs", action="store_false", help="launch every kernel eagerly in the timed region")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false", help="skip the C0 second workload of the default run")
     ap.add_argument("--no-variable", dest="variable", action="store_false", help="skip the variable-shape stream line")
+    ap.add_argument("--quick", action="store_true", help="headline value + e2e only (no per-kernel spans, arena / module-API lines, CPU baseline): scaling A/Bs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -35,10 +35,13 @@ if which == "fwd":
     wsb = L.call("ddfa_gru_step_workspace_bytes", 0, D, ENGINE_TCGEN05)
     ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
     L.call("ddfa_gru_step_prepare", _p(wf), _p(bf), _p(bih), _p(whh), _p(bhh), D, ENGINE_TCGEN05, _p(ws), wsb, st)
+    gpk = torch.zeros(L.call("ddfa_gru_gates_packed_bytes", N, D), dtype=torch.uint8, device=DEV)
+
+    def fwd_v2(train):      # the form the training / inference drivers use: h from the image, image out, packed gates when training
+        L.call("ddfa_gru_step_fwd_image_v2", _p(s_img), _p(h_img), None, _p(dg.indptr), N, D, None, _p(o_img), _p(gpk) if train else None,
+               _p(ws), wsb, st)
     for i in range(6):
-        train = i % 2 == 1
-        L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(h), _p(dg.indptr), N, D, _p(out), _p(o_img) if train else None,
-               _p(gates) if train else None, _p(ws), wsb, st)
+        fwd_v2(i % 2 == 1)
 else:
     wsb = L.call("ddfa_gru_step_bwd_workspace_bytes", N, D, ENGINE_TCGEN05)
     ws = torch.zeros(wsb, dtype=torch.uint8, device=DEV)
@@ -93,8 +96,7 @@ if os.environ.get("DDFA_TRACE"):
     L.call("ddfa_debug_set", 2, 1)
     if which == "fwd":
         for train in (False, True):
-            L.call("ddfa_gru_step_fwd_image", _p(s_img), _p(h_img), _p(h), _p(dg.indptr), N, D, _p(out), _p(o_img) if train else None,
-                   _p(gates) if train else None, _p(ws), wsb, st)
+            fwd_v2(train)
             torch.cuda.synchronize()
             dump_trace(3, "gru_fwd3_kernel " + ("train" if train else "infer"))
     else:
