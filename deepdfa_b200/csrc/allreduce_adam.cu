@@ -45,7 +45,7 @@ __device__ __forceinline__ float4 ld_sys_f4(const float *p) {
   return v;
 }
 __device__ __forceinline__ void wait_epoch(const uint32_t *p, uint32_t epoch) {
-  for (uint32_t it = 0; it < (1u << 28); ++it)
+  for (uint32_t it = 0; it < (1u << 23); ++it)      // ~10 s of polling: a rank that never arrives ends in a trap, not a hung device
     if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return;
   __trap();
 }
