@@ -283,9 +283,12 @@ def timed_regions(ctx, fn_step, steps, min_ms=MIN_TIMED_MS, max_regions=25):
 def roofline_lines(prof, ms_region, N, Eg, engine, peaks, mode_tag):
     """Per-kernel roofline entries from the CUDA-event spans of the instrumented (eager) region.
     P = one [N,128] fp32 plane = one activation image (hi+lo bf16).  Design bytes per launch:
-      forward GRU step (train): read s image, h image, h (3P); write h', h' image, 4 gate planes (6P)            = 9P
-      backward GRU step (tcgen05: gate_bwd with the transposed gather folded in + dgrad3): gate_bwd reads dh, gates x4, h
-        (6P) + E gathered ds rows, writes q x4 + dh'z (5P); dgrad reads q x4 + dh'z (5P), writes ds, dh (2P)   = 18P + E rows
+      forward GRU step (train), packed state (round 2, the default): read s image, h image (2P); write h' image and the
+        packed gate words, 8 B per element (3P)                                                                   = 5P
+        (round-1 form, DDFA_PACKED_STATE=0: read s image, h image, h; write h', h' image, 4 gate planes         = 9P)
+      backward GRU step (tcgen05: gate_bwd with the transposed gather folded in + dgrad3): gate_bwd reads dh, packed gates,
+        h image (4P; round-1 form 6P) + E gathered ds rows, writes q x4 + dh'z (5P); dgrad reads q x4 + dh'z (5P),
+        writes ds, dh (2P)                                                                     = 16P (18P) + E rows
       weight gradient, ONE launch per backward pass over all T steps: per step q x4 + s image + h image          = 6P x T
       edge gather: SURVEY.md §8(d) — E rows gathered + N rows written (+ the CSR arrays)
     and next to them SURVEY.md §8(d)'s own definitions: the GRU step's algorithmic bytes are 3P (read a/s, h; write h') and
@@ -310,9 +313,12 @@ def roofline_lines(prof, ms_region, N, Eg, engine, peaks, mode_tag):
                      "avg_launch_us": t_ms * 1e3, "launches_timed": launches, "share_of_step": sh}, **extra)
 
     tc = engine == "tcgen05"
+    from deepdfa_b200 import engine as _E
+    packed = tc and bool(_E.OPTIONS.get("packed_state"))
+    fwd_P, bwd_P = (5, 16) if packed else (9, 18)
     tr = ncu_traffic("gru_fwd3_kernel", N, "train") if tc else None
     fwd_line = hbm_line("gru_fwd3_kernel (GRU step forward, tcgen05: weights in TMEM, bf16x3)" if tc else "GRU step forward (simt engine)",
-                        9 * P, gru_f_ms, gru_f_n, share["ddfa_gru_step_fwd"],
+                        fwd_P * P, gru_f_ms, gru_f_n, share["ddfa_gru_step_fwd"], design_bytes=f"{fwd_P}P (P = N x 128 x 4 B)",
                         traffic=tr["bytes"] if tr else None, traffic_source=tr["source"] if tr else None,
                         algorithmic_bytes_8d=int(3 * P), frac_8d=3 * P / (gru_f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         flops_8d=flops_8d, tensor_frac_8d=flops_8d / (gru_f_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
@@ -320,8 +326,9 @@ def roofline_lines(prof, ms_region, N, Eg, engine, peaks, mode_tag):
                         tensor_frac_issued=(3 * flops_fold / (gru_f_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if tc else None)
     wg_spans = prof.spans["wgrad_batched"]
     batched = tc and len(wg_spans) > 0
-    bwd_line = hbm_line("GRU step backward: gate_bwd_image (+ folded transposed gather) + dgrad3 kernels" if tc else "GRU step backward (simt engine)",
-                        (18 * P + Eg * Dh * 4) if batched else 24 * P, gru_b_ms, gru_b_n, share["ddfa_gru_step_bwd"], traffic=None,
+    bwd_line = hbm_line("GRU step backward: gate_bwd_tma_kernel / gate_bwd_image_kernel (+ folded transposed gather) + dgrad3_kernel" if tc
+                        else "GRU step backward (simt engine)",
+                        (bwd_P * P + Eg * Dh * 4) if batched else 24 * P, gru_b_ms, gru_b_n, share["ddfa_gru_step_bwd"], traffic=None,
                         tensor_tflops_issued=(3 if batched else 6) * flops_fold / (gru_b_ms * 1e-3) / 1e12 if tc else None)
     gtr = ncu_traffic("gather_sum_image_kernel", N, "train") if tc else None
     gather_line = hbm_line("gather_sum_kernel / gather_sum_image_kernel (CSR edge gather, fwd over CSR + bwd over transposed CSR)",
@@ -335,7 +342,7 @@ def roofline_lines(prof, ms_region, N, Eg, engine, peaks, mode_tag):
         lines.insert(2, hbm_line(f"wgrad_kernel + wgrad_reduce_kernel (weight gradients of all {T} steps in one launch)",
                                  6 * P * T, wg_ms, wg_n, share["wgrad_batched"], traffic=None,
                                  tensor_tflops_issued=3 * flops_fold * T / (wg_ms * 1e-3) / 1e12))
-    roofline = dict(fwd_line, note="dominant single kernel by time; the other hot kernels are in roofline_kernels; frac = design bytes (9P) "
+    roofline = dict(fwd_line, note="dominant single kernel by time; the other hot kernels are in roofline_kernels; frac = design bytes (bytes_per_launch; 5P with the packed saved state) "
                                    "over the launch time vs the measured HBM peak, frac_8d / tensor_frac_8d = SURVEY.md §8(d)'s algorithmic bytes / FLOPs")
     return roofline, lines
 
