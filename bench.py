@@ -561,15 +561,16 @@ def run_ours(args):
     model = D.FlowGNNGGNNModule(FEAT, CFG["input_dim"], CFG["hidden_dim"], CFG["n_steps"], CFG["layers"], concat_all_absdf=True,
                                 engine=args.engine).to(dev)
     # DDFA_AR_OVERLAP=0: one all-reduce of the whole flat buffer after the backward pass (A/B of the split exchange)
-    # DDFA_EXCHANGE=p2p: the fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory instead of NCCL + ddfa_adam_flat
-    exchange = os.environ.get("DDFA_EXCHANGE", "nccl")
+    # DDFA_EXCHANGE=p2p | nccl | auto (default; = the FusedTrainer default): p2p is the fused reduce-scatter + Adam + all-gather kernel
+    # over NVLink peer memory, nccl the all-reduce + ddfa_adam_flat; auto takes p2p when the symmetric-memory set-up succeeds on all ranks
+    exchange = os.environ.get("DDFA_EXCHANGE", "auto")
     ctx.trainer = trainer = D.FusedTrainer(model, overlap_allreduce=os.environ.get("DDFA_AR_OVERLAP", "1") != "0", exchange=exchange)
 
     # ---- data-parallel self-check (SURVEY.md §8(e) "Determinism"): k steps sharded over the N ranks vs the same k steps of the
     # unsharded global batch on one rank, same seeds — the loss curves must agree (fp32 summation order is the only difference).
     dp_parity = None
     if world > 1 and hasattr(D.FusedTrainer, "dp_self_check"):
-        dp_parity = D.FusedTrainer.dp_self_check(args.engine, dev, rank, world, exchange=os.environ.get("DDFA_EXCHANGE", "nccl"))
+        dp_parity = D.FusedTrainer.dp_self_check(args.engine, dev, rank, world, exchange=trainer.exchange)
 
     primary = measure_workload(ctx, args, args.graphs, full=True)
     secondary = []
@@ -621,6 +622,7 @@ def run_ours(args):
         "allreduce": None if world == 1 else ("fused peer-memory kernel: reduce-scatter + Adam + all-gather over NVLink (ddfa_allreduce_adam_p2p), no NCCL in the step"
                                               if trainer.exchange == "p2p" else "split: small gradients on a side stream during the weight-gradient launch, GGNN weight "
                                               "gradients after it" if trainer.overlap_allreduce else "single call after the backward pass"),
+        "exchange": None if world == 1 else {"requested": exchange, "used": trainer.exchange, "note": trainer.exchange_note},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_done} full train steps of one {args.graphs}-graph {workload_tag(args.graphs)} batch, oracle/ggnn_oracle.py (torch CPU)"},
         "final_loss": primary["final_loss"], "e2e_last_loss": primary["e2e_last_loss"],

@@ -174,17 +174,32 @@ __global__ void __launch_bounds__(kReadoutWarps * 32) readout_mlp_fwd_kernel(
     const float *W = mlp.w[layer];
     const float *bias = mlp.b[layer];
     const int rows = (layer == L - 1) ? 1 : D2;
-    for (int r = warp; r < rows; r += kReadoutWarps) {
-      const float *wr = W + (int64_t)r * D2;
-      float sacc = 0.f;
+    // R output rows per warp iteration: their weight loads are independent (a row at a time was a chain of L2 latencies,
+    // 2D / 8 of them per warp and layer); per row the same lane partition and shuffle tree as before, so the sums are unchanged
+    constexpr int R = 4;
+    for (int r0 = warp * R; r0 < rows; r0 += kReadoutWarps * R) {
+      float sacc[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) sacc[j] = 0.f;
       for (int k = lane * 4; k < D2; k += 128) {
-        const float4 wv = ldg_nc_f4(wr + k);
         const float4 iv = *reinterpret_cast<const float4 *>(&s_in[k]);
-        sacc += f4_dot(wv, iv);
+        float4 wv[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          wv[j] = (r0 + j < rows) ? ldg_nc_f4(W + (int64_t)(r0 + j) * D2 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < R; ++j) sacc[j] += f4_dot(wv[j], iv);
       }
-      sacc = warp_sum(sacc);
-      if (lane == 0) {
-        float y = sacc + bias[r];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int j = 0; j < R; ++j) sacc[j] += __shfl_xor_sync(0xffffffffu, sacc[j], off);
+      float mine = sacc[0];
+#pragma unroll
+      for (int j = 1; j < R; ++j) mine = (lane == j) ? sacc[j] : mine;
+      const int r = r0 + lane;
+      if (lane < R && r < rows) {
+        float y = mine + bias[r];
         if (layer == L - 1) {
           logits[b] = y;
         } else {

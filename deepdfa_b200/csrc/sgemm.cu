@@ -140,59 +140,95 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
   }
 }
 
-// Small problems (weight folding, MLP head backward: M, N <= a few hundred) would occupy 1-6 of the 148 SMs with the
-// 128x128 tile and run for tens of microseconds; this kernel uses 32x32 output tiles (256 threads, 2x2 per thread,
-// K staged 32 at a time through shared memory) so the same work spreads over dozens of CTAs.
+// Small problems (weight folding, MLP head forward / backward: M, N <= a few hundred) would occupy 1-6 of the 148 SMs with the
+// 128x128 tile and run for tens of microseconds; this kernel uses 32x32 output tiles so the same work spreads over dozens of
+// CTAs.  64 threads, 4x4 outputs per thread (16 FFMA per two LDS.128 — the 2x2 form of round 1 was bound by its shared-memory
+// loads), K staged 32 at a time through shared memory with the next stage prefetched into registers.
+// KC: the operand tile [32 (mn) x 32 (k)] is contiguous along k in memory (element (mn, k) at p[mn * ld + k]); else along mn.
+template <bool KC>
+__device__ __forceinline__ void small_fetch(const float *__restrict__ p, int ld, int mn0, int MN, int k0, int K, bool vec, float4 (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e4 = threadIdx.x + 64 * i;                 // 256 float4 per operand stage
+    const int mn = KC ? (e4 >> 3) : 4 * (e4 & 7), k = KC ? 4 * (e4 & 7) : (e4 >> 3);
+    const int gmn = mn0 + mn, gk = k0 + k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KC) {
+      if (gmn < MN) {
+        const float *q = p + (int64_t)gmn * ld + gk;
+        if (vec && gk + 3 < K) v = *reinterpret_cast<const float4 *>(q);
+        else {
+          if (gk + 0 < K) v.x = q[0];
+          if (gk + 1 < K) v.y = q[1];
+          if (gk + 2 < K) v.z = q[2];
+          if (gk + 3 < K) v.w = q[3];
+        }
+      }
+    } else if (gk < K) {
+      const float *q = p + (int64_t)gk * ld + gmn;
+      if (vec && gmn + 3 < MN) v = *reinterpret_cast<const float4 *>(q);
+      else {
+        if (gmn + 0 < MN) v.x = q[0];
+        if (gmn + 1 < MN) v.y = q[1];
+        if (gmn + 2 < MN) v.z = q[2];
+        if (gmn + 3 < MN) v.w = q[3];
+      }
+    }
+    r[i] = v;
+  }
+}
+template <bool KC>
+__device__ __forceinline__ void small_stage(float (*s)[36], const float4 (&r)[4]) {      // s[k][mn]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e4 = threadIdx.x + 64 * i;
+    if (KC) {
+      const int mn = e4 >> 3, k = 4 * (e4 & 7);
+      s[k + 0][mn] = r[i].x; s[k + 1][mn] = r[i].y; s[k + 2][mn] = r[i].z; s[k + 3][mn] = r[i].w;
+    } else {
+      *reinterpret_cast<float4 *>(&s[e4 >> 3][4 * (e4 & 7)]) = r[i];
+    }
+  }
+}
+
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) sgemm_small_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
-                                                          const float *__restrict__ B, int ldb, float beta, float *__restrict__ C,
-                                                          int ldc) {
-  constexpr int KB = 64;            // K staged 64 at a time; the next stage is fetched into registers while this one is used
-  __shared__ float As[KB][33];      // [k][m]
-  __shared__ float Bs[KB][33];      // [k][n]
+__global__ void __launch_bounds__(64) sgemm_small_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
+                                                         const float *__restrict__ B, int ldb, float beta, float *__restrict__ C,
+                                                         int ldc, int vec_a, int vec_b) {
+  constexpr int KB = 32;
+  __shared__ __align__(16) float As[KB][36];      // [k][m]   (row stride 36 floats: 16-byte aligned rows for the LDS.128 below)
+  __shared__ __align__(16) float Bs[KB][36];      // [k][n]
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float ra[8], rb[8];
-  auto fetch = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int e = threadIdx.x + i * 256;      // 2048 elements per operand stage
-      {  // A element (m, k); the fastest-varying index follows the memory layout for coalescing
-        const int m = TA ? (e & 31) : (e >> 6), k = TA ? (e >> 5) : (e & 63);
-        const int gm = m0 + m, gk = k0 + k;
-        ra[i] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.f;
-      }
-      {  // B element (k, n)
-        const int n = TB ? (e >> 6) : (e & 31), k = TB ? (e & 63) : (e >> 5);
-        const int gn = n0 + n, gk = k0 + k;
-        rb[i] = (gn < N && gk < K) ? (TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]) : 0.f;
-      }
-    }
-  };
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  fetch(0);
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  float4 ra[4], rb[4];
+  float acc[4][4] = {};
+  small_fetch<!TA>(A, lda, m0, M, 0, K, vec_a != 0, ra);      // A element (m, k) at A[m*lda + k] (k-contiguous) unless transposed
+  small_fetch<TB>(B, ldb, n0, N, 0, K, vec_b != 0, rb);       // B element (k, n) at B[k*ldb + n] (n-contiguous) unless transposed
   for (int k0 = 0; k0 < K; k0 += KB) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int e = threadIdx.x + i * 256;
-      As[TA ? (e >> 5) : (e & 63)][TA ? (e & 31) : (e >> 6)] = ra[i];
-      Bs[TB ? (e & 63) : (e >> 5)][TB ? (e >> 6) : (e & 31)] = rb[i];
-    }
+    small_stage<!TA>(As, ra);
+    small_stage<TB>(Bs, rb);
     __syncthreads();
-    if (k0 + KB < K) fetch(k0 + KB);
+    if (k0 + KB < K) {
+      small_fetch<!TA>(A, lda, m0, M, k0 + KB, K, vec_a != 0, ra);
+      small_fetch<TB>(B, ldb, n0, N, k0 + KB, K, vec_b != 0, rb);
+    }
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
-      const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+      const float4 a = *reinterpret_cast<const float4 *>(&As[k][4 * ty]);
+      const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][4 * tx]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + 4 * ty + i, n = n0 + 4 * tx + j;
       if (m < M && n < N) {
         float *c = C + (int64_t)m * ldc + n;
         const float v = alpha * acc[i][j];
@@ -207,7 +243,8 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
   if (split_k < 1) split_k = 1;
   if (split_k == 1 && (int64_t)M * N <= 512 * 512 && K <= 4096) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
-#define LAUNCH_S(TA, TB) sgemm_small_kernel<TA, TB><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)
+    const int va = aligned16(A) && (lda % 4 == 0), vb = aligned16(B) && (ldb % 4 == 0);
+#define LAUNCH_S(TA, TB) sgemm_small_kernel<TA, TB><<<grid, 64, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, va, vb)
     if (!ta && !tb) LAUNCH_S(false, false);
     else if (!ta && tb) LAUNCH_S(false, true);
     else if (ta && !tb) LAUNCH_S(true, false);

@@ -77,6 +77,20 @@ class DeviceGraph:
     device: torch.device
 
 
+def per_node_view(g, dg: DeviceGraph) -> DeviceGraph:
+    """The same batch with every node as its own one-node graph (graph_ptr = 0..N): what label_style="node" hands to the readout /
+    label kernels (ggnn.py:101-107 without the pooling, base_module.py:84-85).  Cached on the graph object."""
+    key = f"devgraph_nodes:{dg.device}"
+    view = g._cache.get(key)
+    if view is None or view.indptr is not dg.indptr:
+        with torch.cuda.device(dg.device):
+            ptr = torch.arange(dg.num_nodes + 1, dtype=torch.int32, device=dg.device)
+        view = DeviceGraph(dg.num_nodes, dg.num_edges, dg.num_nodes, dg.indptr, dg.indices, dg.indptr_t, dg.indices_t, ptr, dg.device)
+        view._csr_ws = getattr(dg, "_csr_ws", None)
+        g._cache[key] = view
+    return view
+
+
 def prepare_graph(g, device=None, need_transpose: bool = True) -> DeviceGraph:
     """COO (as handed over by DGL / BatchedCFG) -> DeviceGraph, entirely on the device, no host sync.
     Cached on the graph object."""

@@ -171,10 +171,16 @@ class FlowGNNGGNNModule(nn.Module):
 
         if label_style == "graph":
             self.pooling = GlobalAttentionPoolingParams(nn.Linear(output_in_size, 1))
+        elif label_style == "node":
+            # ggnn.py:101-107 without the pooling: the head runs on every node's [ggnn_out | feat_embed] row.  Same kernels:
+            # every node is handed to the readout as a one-node graph — softmax over one node is exactly 1, so "pooled" is the
+            # row itself — with an all-zero gate that is no parameter (the reference has no pooling module in this style).
+            self.register_buffer("_node_gate_w", torch.zeros(1, output_in_size), persistent=False)
+            self.register_buffer("_node_gate_b", torch.zeros(1), persistent=False)
         else:
             raise NotImplementedError(
-                f"label_style={label_style!r}: only the shipped 'graph' style is implemented on the B200 path "
-                "(reference base_module.py:83-95)")
+                f"label_style={label_style!r}: the 'graph' (shipped) and 'node' styles are implemented on the B200 path; the "
+                "dataflow_solution_* styles (reference base_module.py:88-91) are not")
 
         self._num_layers = 0
         if not encoder_mode:  # ggnn.py:70-80
@@ -214,10 +220,12 @@ class FlowGNNGGNNModule(nn.Module):
 
     def param_list(self):
         """Parameters in ParamPack.flat_list() order."""
-        lin, gru, gate = self.ggnn.linears[0], self.ggnn.gru, self.pooling.gate_nn
+        lin, gru = self.ggnn.linears[0], self.ggnn.gru
+        gate_w, gate_b = ((self.pooling.gate_nn.weight, self.pooling.gate_nn.bias) if self.hparams.label_style == "graph"
+                          else (self._node_gate_w, self._node_gate_b))
         mlp = self._mlp_linears()
         return [*self._tables(), lin.weight, lin.bias, gru.weight_ih, gru.weight_hh, gru.bias_ih, gru.bias_hh,
-                gate.weight, gate.bias, *[m.weight for m in mlp], *[m.bias for m in mlp]]
+                gate_w, gate_b, *[m.weight for m in mlp], *[m.bias for m in mlp]]
 
     @property
     def device(self):
@@ -230,6 +238,8 @@ class FlowGNNGGNNModule(nn.Module):
                             "There is no CPU fallback.")
         g = as_batched_cfg(graph)
         dg = E.prepare_graph(g, dev, need_transpose=True)
+        if self.hparams.label_style == "node":
+            dg = E.per_node_view(g, dg)
         idx = E.node_indices(g, self.concat_all_absdf, self.feature_keys["feature"], dev)
         return g, dg, idx
 
@@ -297,8 +307,8 @@ class FlowGNNGGNNModule(nn.Module):
         self._raise_deferred_input_errors(wait=True)
 
     def get_label(self, batch):
-        """base_module.py:83-95 (graph style): per-graph max of ndata['_VULN'] as float — a fused
-        segment-max kernel instead of dgl.unbatch + a Python loop."""
+        """base_module.py:83-95: graph style — per-graph max of ndata['_VULN'] as float, a fused segment-max kernel instead of
+        dgl.unbatch + a Python loop; node style — ndata['_VULN'] as float (the same kernel over one-node segments)."""
         g, dg, _ = self._prepare(batch)
         vuln = g.ndata["_VULN"].to(self.device, non_blocking=True)
         with torch.cuda.device(self.device):
@@ -315,10 +325,26 @@ class FlowGNNGGNNModule(nn.Module):
             loss, labels = _BCEFunction.apply(out, dg, vuln, pw)
         return loss, labels
 
+    def resample(self, batch, out, label):
+        """base_module.py:96-135 without the Lightning logging (node style): keep every vulnerable node and
+        ``round(#vulnerable * undersample_node_on_loss_factor)`` non-vulnerable ones drawn with ``random.sample``.  Like the
+        reference this reads the labels on the host (one sync); it is not part of the shipped (graph-style) configuration."""
+        import random
+        vuln_indices = label.nonzero().flatten().tolist()
+        num_indices_to_sample = round(len(vuln_indices) * self.hparams.undersample_node_on_loss_factor)
+        nonvuln_indices = random.sample((label == 0).nonzero().flatten().tolist(), num_indices_to_sample)
+        indices = vuln_indices + nonvuln_indices
+        return out[indices], label[indices]
+
     def training_step(self, batch_data, batch_idx=0):
         """base_module.py:171-199 without the Lightning logging: returns the loss tensor."""
         batch, extrafeats = batch_data
         out = self.forward(batch, extrafeats)
+        if self.hparams.label_style == "node" and self.hparams.undersample_node_on_loss_factor is not None:
+            # base_module.py:178-183: the loss over the resampled subset of nodes is the reference's own torch expression on a
+            # short vector (self.loss_fn); gradients reach the kernels' backward through the indexing
+            out, label = self.resample(batch, out, self.get_label(batch))
+            return self.loss_fn(out, label)
         loss, _ = self.loss_and_labels(batch, out)
         return loss
 

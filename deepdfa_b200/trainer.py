@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -28,7 +30,7 @@ class FusedTrainer:
     def __init__(self, module: FlowGNNGGNNModule, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, process_group=None, use_cuda_graph: bool = False, max_graph_shapes: int = 8,
                  max_resident_graphs: int = 64, distributed: bool = True, bucket_nodes: int = 0, bucket_edges: int = 0,
-                 bucket_min_pad_nodes: int = 64, overlap_allreduce: bool = True, exchange: str = "nccl"):
+                 bucket_min_pad_nodes: int = 64, overlap_allreduce: bool = True, exchange: str = "auto"):
         """``distributed=False`` makes this a single-rank trainer even inside an initialised process group (no all-reduce).
         ``bucket_nodes`` / ``bucket_edges`` > 0 switch on shape bucketing for HOST batches under ``use_cuda_graph``: every batch
         is padded with ONE dummy graph of isolated nodes up to the next multiple of ``bucket_nodes`` nodes (at least
@@ -37,6 +39,9 @@ class FusedTrainer:
         captured graphs.  The dummy graph has zero loss weight (``ddfa_graph_label_bce_valid``): no gradient comes from it."""
         if module.device.type != "cuda":
             raise _lib.DdfaError("FusedTrainer needs the module on a CUDA device (no CPU fallback)")
+        if module.hparams.label_style != "graph" or module.hparams.encoder_mode:
+            raise NotImplementedError("FusedTrainer fuses the shipped configuration (label_style='graph', a classifier head); train "
+                                      "label_style='node' / encoder_mode modules through module.training_step + torch.optim")
         self.module = module
         self.device = module.device
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -50,9 +55,19 @@ class FusedTrainer:
         self._ar_stream = None
         # exchange = "p2p": no NCCL call in the step — the flat parameter and gradient buffers live in symmetric (peer-mapped)
         # memory and ONE kernel per rank does reduce-scatter + Adam + all-gather over NVLink (ddfa_allreduce_adam_p2p); optimizer
-        # moments are sharded (each rank keeps them for its 1/R slice only).  Single node.  "nccl" (default): all-reduce + ddfa_adam_flat.
-        if exchange not in ("nccl", "p2p"):
-            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {exchange!r}")
+        # moments are sharded (each rank keeps them for its 1/R slice only).  Single node.  "nccl": all-reduce + ddfa_adam_flat.
+        # "auto" (default): "p2p" when every rank of the group is on this node and the symmetric-memory set-up succeeds on ALL
+        # ranks, else "nccl" (the reason is kept in ``exchange_note``).  Measured at N = 2 / 4 / 8: profiles/r03k, r03n, r03o.
+        if exchange not in ("auto", "nccl", "p2p"):
+            raise ValueError(f"exchange must be 'auto', 'nccl' or 'p2p', got {exchange!r}")
+        self.exchange_note = None
+        auto = exchange == "auto"
+        if auto:
+            exchange = "p2p"
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+            if self.world > 1 and (dist.get_backend(process_group) != "nccl" or (local and local != self.world)
+                                   or torch.cuda.device_count() < self.world):
+                exchange, self.exchange_note = "nccl", "auto: ranks span more than this node (or a non-NCCL group): NCCL all-reduce"
         self.exchange = exchange if self.world > 1 else "nccl"
         self.use_cuda_graph = use_cuda_graph
         # a captured graph bakes in the batch SHAPE (and, for resident batches, the batch object): cap how many are kept so a
@@ -69,8 +84,20 @@ class FusedTrainer:
         self._gemm_grad_range = (offs[ntab], offs[ntab + 4])     # flat offsets of [w_msg, b_msg, w_ih, w_hh]
         with torch.cuda.device(self.device):
             if self.exchange == "p2p":
-                self._setup_p2p(total)
-            else:
+                try:
+                    self._setup_p2p(total)
+                    ok, why = 1, None
+                except _lib.DdfaError as exc:
+                    if not auto:
+                        raise
+                    ok, why = 0, str(exc)
+                if auto:       # all ranks take the same path: one failed set-up sends every rank to NCCL
+                    flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+                    if int(flag.item()) == 0:
+                        self.exchange = "nccl"
+                        self.exchange_note = "auto: symmetric-memory set-up failed on a rank (" + (why or "another rank") + "): NCCL all-reduce"
+            if self.exchange != "p2p":
                 self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
                 self.flat_g = torch.zeros(total + _ALIGN, dtype=torch.float32, device=self.device)  # [+ loss slot]
             self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -413,7 +440,7 @@ class FusedTrainer:
     # ------------------------------------------------------------------------------------
     @staticmethod
     def dp_self_check(engine: str, device, rank: int, world: int, steps: int = 5, graphs_per_rank: int = 24, nodes: int = 60,
-                      exchange: str = "nccl") -> dict:
+                      exchange: str = "auto") -> dict:
         """On-hardware data-parallel parity (SURVEY.md §8(e) "Determinism"): ``steps`` optimisation steps of a global batch
         sharded over the ``world`` ranks (node-balanced shards of different sizes, NCCL all-reduce) against the same steps of
         the UNSHARDED batch on this rank alone, same seeds.  fp32 summation order is the only difference.  Collective: every

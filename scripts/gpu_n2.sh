@@ -22,6 +22,11 @@ if [ "${ONLY:-}" = "c0" ]; then
   run c0_p2p "DDFA_EXCHANGE=p2p" "--graphs 256"
   run c0_single "DDFA_AR_OVERLAP=0" "--graphs 256"
   run c1_p2p "DDFA_EXCHANGE=p2p" ""
+elif [ "${ONLY:-}" = "ab" ]; then
+  run c1_split "DDFA_AR_OVERLAP=1" ""
+  run c1_p2p "DDFA_EXCHANGE=p2p" ""
+  run c0_split "DDFA_AR_OVERLAP=1" "--graphs 256"
+  run c0_p2p "DDFA_EXCHANGE=p2p" "--graphs 256"
 else
   run c1_split "DDFA_AR_OVERLAP=1" ""
   run c1_p2p "DDFA_EXCHANGE=p2p" ""

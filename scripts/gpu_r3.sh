@@ -36,9 +36,13 @@ for STAGE in "$@"; do
         -f -o $OUT/${TAG}_prof_fwd3_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_full.log 2>&1
       echo "ncu full (fwd3) exit: $?"
       env $PROF_ENV timeout 900 ncu --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum \
-        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd_image|gather_sum|readout|embed_concat|sgemm_small" -s 80 -c 70 \
+        -k regex:"gru_fwd3_kernel|dgrad3_kernel|wgrad_kernel|gate_bwd|gather_sum|readout|embed_concat|sgemm_small" -s 80 -c 70 \
         -f -o $OUT/${TAG}_prof_step_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_step.log 2>&1
       echo "ncu step metrics exit: $?"; ls -la $OUT/*.ncu-rep ;;
+    ncu-c0)       # --set full of the forward kernel at C0 (38 400 nodes), isolated launches (scripts/kernel_only.py), inference + training form
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gru_fwd3_kernel" -s 2 -c 4 \
+        -f -o $OUT/${TAG}_prof_fwd3_c0 python scripts/kernel_only.py fwd 256 > $OUT/${TAG}_ncu_c0.log 2>&1
+      echo "ncu full (fwd3, C0) exit: $?" ;;
     ncu-gb)       # --set full + source of the gate backward kernel (two launches)
       env $PROF_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_bwd_image" -s 10 -c 2 \
         -f -o $OUT/${TAG}_prof_gatebwd_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_gb.log 2>&1

@@ -134,6 +134,14 @@ def main():
         dict(name="concat_D128_T8_L2_pw_train", ctor=dict(feat=feat, input_dim=64, hidden_dim=32, n_steps=8, num_output_layers=2,
                                                          concat_all_absdf=True, positive_weight=3.0),
              graphs=dict(sizes=[150, 3, 77, 140, 1, 129, 260, 31], seed=16, vuln_rate=0.4, input_dim=64)),
+        # label_style="node" (ggnn.py:101-107 without the pooling; base_module.py:84-85 per-node labels), training step without
+        # the undersampling (undersample_node_on_loss_factor=None, the ctor default)
+        dict(name="node_single_T3_L2_train", ctor=dict(feat=feat, input_dim=60, hidden_dim=24, n_steps=3, num_output_layers=2,
+                                                      concat_all_absdf=False, label_style="node", positive_weight=2.0),
+             graphs=dict(sizes=[5, 17, 1, 30], seed=17, vuln_rate=0.5, input_dim=60)),
+        dict(name="node_concat_D128_T4_L2_train", ctor=dict(feat=feat, input_dim=64, hidden_dim=32, n_steps=4, num_output_layers=2,
+                                                           concat_all_absdf=True, label_style="node"),
+             graphs=dict(sizes=[150, 3, 77, 1, 129], seed=18, vuln_rate=0.4, input_dim=64)),
     ]
     for i, spec in enumerate(specs):
         torch.manual_seed(100 + i)

@@ -114,7 +114,9 @@ def test_module_mirrors_reference_constructor_and_state_dict():
 
 def test_module_rejects_unsupported_and_has_no_cpu_fallback():
     with pytest.raises(NotImplementedError):
-        D.FlowGNNGGNNModule(FEAT, 50, 8, 2, 1, label_style="node")
+        D.FlowGNNGGNNModule(FEAT, 50, 8, 2, 1, label_style="dataflow_solution_out")
+    node = D.FlowGNNGGNNModule(FEAT, 50, 8, 2, 2, label_style="node")      # ggnn.py:66-68: no pooling module in this style
+    assert not hasattr(node, "pooling") and not any(k.startswith(("pooling", "_node")) for k in node.state_dict())
     with pytest.raises(TypeError):
         D.FlowGNNGGNNModule(FEAT, 50, 8, 2, 1, num_node_types=3)    # stale kwargs of other revisions
     with pytest.raises(ValueError):

@@ -201,7 +201,7 @@ def test_oracle_matches_reference_control_flow():
     from deepdfa_b200.batched_graph import BatchedCFG
     path = os.path.join(os.path.dirname(__file__), "golden", "reference_ctrlflow_golden.pt")
     data = torch.load(path, weights_only=False)
-    assert len(data["cases"]) == 6 and any("grads" in c and c["ctor"]["hidden_dim"] == 32 for c in data["cases"])
+    assert len(data["cases"]) == 8 and sum(c["ctor"].get("label_style") == "node" for c in data["cases"]) == 2 and any("grads" in c and c["ctor"]["hidden_dim"] == 32 for c in data["cases"])
     for case in data["cases"]:
         gd = case["graph"]
         g = BatchedCFG(gd["src"], gd["dst"], gd["batch_num_nodes"], gd["ndata"])

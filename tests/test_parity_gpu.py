@@ -516,3 +516,42 @@ def test_module_matches_reference_control_flow_goldens(engine):
                     assert (p.grad.cpu() - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), (case["name"], k)
             checked_grads += 1
     assert checked_grads >= 1, "no reference-code gradient case ran for this engine"
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_node_label_style_with_undersampling_matches_oracle(engine):
+    """label_style="node" (ggnn.py:101-107 without the pooling; base_module.py:84-85 labels; base_module.py:96-135,178-183 the
+    undersampled training loss): per-node logits, per-node labels, validation loss, and the training step with
+    undersample_node_on_loss_factor — same `random` seed on both sides, so the same nodes are drawn."""
+    import random
+    hd = 32 if engine == "tcgen05" else 8
+    ctor = dict(feat=FEAT, input_dim=50, hidden_dim=hd, n_steps=3, num_output_layers=2, concat_all_absdf=True, label_style="node",
+                positive_weight=1.5)
+    g = synth.make_batch(sizes=[12, 40, 1, 7, 25], seed=5, vuln_rate=0.8, input_dim=50)
+    assert 0 < int(g.ndata["_VULN"].sum()) < g.num_nodes() // 2
+    torch.manual_seed(7)
+    o = O.OracleFlowGNNGGNN(**ctor)
+    m = D.FlowGNNGGNNModule(**ctor, undersample_node_on_loss_factor=1.0, engine=engine)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV)
+    with torch.no_grad():
+        ref = o(g).double()
+    vloss, prob, labels = m.validation_step((g, {}), 0)
+    assert prob.shape == (g.num_nodes(),) and torch.equal(labels.cpu(), o.get_label(g).int())
+    assert (torch.logit(prob.double().cpu()) - ref).abs().max() < (1e-4 if engine == "simt" else 1e-3)
+    assert abs(float(vloss) - float(o.loss_fn(ref.float(), o.get_label(g)))) < 1e-4
+    random.seed(3)
+    loss = m.training_step((g, {}), 0)
+    loss.backward()
+    random.seed(3)
+    out, label = o(g), o.get_label(g)
+    vi = label.nonzero().flatten().tolist()
+    idx = vi + random.sample((label == 0).nonzero().flatten().tolist(), round(len(vi) * 1.0))
+    lo = o.loss_fn(out[idx], label[idx])
+    lo.backward()
+    assert abs(float(loss) - float(lo)) < 1e-4
+    ref_g = dict(o.named_parameters())
+    tol = 2e-4 if engine == "simt" else 2e-3
+    for k, p in m.named_parameters():
+        r = ref_g[k].grad
+        assert (p.grad.cpu() - r).abs().max() < tol * max(1.0, float(r.abs().max())), k
