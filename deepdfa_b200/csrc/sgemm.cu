@@ -194,7 +194,7 @@ __device__ __forceinline__ void small_stage(float (*s)[36], const float4 (&r)[4]
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(64) sgemm_small_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
                                                          const float *__restrict__ B, int ldb, float beta, float *__restrict__ C,
-                                                         int ldc, int vec_a, int vec_b) {
+                                                         int ldc, int vec_a, int vec_b, int k_per_split, int use_atomic) {
   constexpr int KB = 32;
   __shared__ __align__(16) float As[KB][36];      // [k][m]   (row stride 36 floats: 16-byte aligned rows for the LDS.128 below)
   __shared__ __align__(16) float Bs[KB][36];      // [k][n]
@@ -202,9 +202,11 @@ __global__ void __launch_bounds__(64) sgemm_small_kernel(int M, int N, int K, fl
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   float4 ra[4], rb[4];
   float acc[4][4] = {};
-  small_fetch<!TA>(A, lda, m0, M, 0, K, vec_a != 0, ra);      // A element (m, k) at A[m*lda + k] (k-contiguous) unless transposed
-  small_fetch<TB>(B, ldb, n0, N, 0, K, vec_b != 0, rb);       // B element (k, n) at B[k*ldb + n] (n-contiguous) unless transposed
-  for (int k0 = 0; k0 < K; k0 += KB) {
+  const int kbeg = blockIdx.z * k_per_split;                   // split-K: gridDim.z slices of K, accumulated with RED.ADD (beta == 1)
+  K = min(K, kbeg + k_per_split);
+  small_fetch<!TA>(A, lda, m0, M, kbeg, K, vec_a != 0, ra);   // A element (m, k) at A[m*lda + k] (k-contiguous) unless transposed
+  small_fetch<TB>(B, ldb, n0, N, kbeg, K, vec_b != 0, rb);    // B element (k, n) at B[k*ldb + n] (n-contiguous) unless transposed
+  for (int k0 = kbeg; k0 < K; k0 += KB) {
     small_stage<!TA>(As, ra);
     small_stage<TB>(Bs, rb);
     __syncthreads();
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(64) sgemm_small_kernel(int M, int N, int K, fl
       if (m < M && n < N) {
         float *c = C + (int64_t)m * ldc + n;
         const float v = alpha * acc[i][j];
-        *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
+        if (use_atomic) atomicAdd(c, v);
+        else *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
       }
     }
 }
@@ -243,8 +246,21 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float *A, int 
   if (split_k < 1) split_k = 1;
   if (split_k == 1 && (int64_t)M * N <= 512 * 512 && K <= 4096) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
+    // An accumulating product (beta == 1) with a long K and few output tiles — the MLP head's weight gradients, K = batch size —
+    // is a chain of K/32 load latencies on a handful of SMs: slice K over gridDim.z and accumulate with RED.ADD instead.
+    int split = 1;
+    const int tiles = (int)(grid.x * grid.y);
+    if (beta == 1.f && K >= 256 && tiles < 148) {
+      split = (2 * 148 + tiles - 1) / tiles;
+      if (split > K / 64) split = K / 64;
+      if (split < 1) split = 1;
+    }
+    int kps = ((K + split - 1) / split + 31) / 32 * 32;
+    if (kps < 32) kps = 32;
+    grid.z = K > kps ? (K + kps - 1) / kps : 1;
+    const int atomic = grid.z > 1;
     const int va = aligned16(A) && (lda % 4 == 0), vb = aligned16(B) && (ldb % 4 == 0);
-#define LAUNCH_S(TA, TB) sgemm_small_kernel<TA, TB><<<grid, 64, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, va, vb)
+#define LAUNCH_S(TA, TB) sgemm_small_kernel<TA, TB><<<grid, 64, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, va, vb, kps, atomic)
     if (!ta && !tb) LAUNCH_S(false, false);
     else if (!ta && tb) LAUNCH_S(false, true);
     else if (ta && !tb) LAUNCH_S(true, false);

@@ -124,7 +124,8 @@ def test_eval_f1_gpu_encoder_vs_oracle_encoder_and_stream_overlap():
         flow.load_state_dict(flow_sd)
         gpu_model.classifier.load_state_dict(head_sd)
         held_gpu = [(ids.to(DEV), y.to(DEV), g.to(DEV)) for ids, y, g in held_cpu]
-        evaluate(gpu_model, held_gpu[:2])                   # warm-up
+        evaluate(gpu_model, held_gpu)                       # warm-up pass over the SAME batches: device CSRs cached, the caching
+                                                            # allocator's per-stream pools filled (the side stream has its own)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         res = evaluate(gpu_model, held_gpu)
