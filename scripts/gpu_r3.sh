@@ -44,7 +44,7 @@ for STAGE in "$@"; do
         -f -o $OUT/${TAG}_prof_fwd3_c0 python scripts/kernel_only.py fwd 256 > $OUT/${TAG}_ncu_c0.log 2>&1
       echo "ncu full (fwd3, C0) exit: $?" ;;
     ncu-gb)       # --set full + source of the gate backward kernel (two launches)
-      env $PROF_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_bwd_image" -s 10 -c 2 \
+      env $PROF_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_bwd" -s 10 -c 2 \
         -f -o $OUT/${TAG}_prof_gatebwd_c1 python bench.py --steps 2 --warmup 1 --no-secondary --no-variable > $OUT/${TAG}_ncu_gb.log 2>&1
       echo "ncu gate_bwd exit: $?" ;;
     ab-packed)    # whole-step A/B on this box: round-1 saved state (fp32 h_t + four fp32 gate planes) vs packed state
