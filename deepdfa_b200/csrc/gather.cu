@@ -24,6 +24,20 @@
 
 namespace ddfa {
 
+// bf16 hi/lo split for the activation images, two values per conversion (cvt.rn.bf16x2.f32 = F2FP.PACK_AB: converts and packs;
+// the scalar F2F form is a quarter-rate instruction per value plus a shift/OR per pair).  Same values as tc_common.cuh split_bf16.
+__device__ __forceinline__ uint32_t bf16x2_word(float lo_half, float hi_half) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);      // .x -> bits 0-15, .y -> bits 16-31
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
+__device__ __forceinline__ void split4_bf16x2(const float4 &x, uint2 &ph, uint2 &pl) {
+  ph.x = bf16x2_word(x.x, x.y);
+  ph.y = bf16x2_word(x.z, x.w);
+  pl.x = bf16x2_word(x.x - __uint_as_float(ph.x << 16), x.y - __uint_as_float(ph.x & 0xffff0000u));
+  pl.y = bf16x2_word(x.z - __uint_as_float(ph.y << 16), x.w - __uint_as_float(ph.y & 0xffff0000u));
+}
+
+
 template <int G, int CH, int RW, int UNROLL, int PASSES, int NIDX, int THREADS>
 __global__ void __launch_bounds__(THREADS) gather_sum_kernel(const int32_t *__restrict__ indptr,
                                                              const int32_t *__restrict__ indices,
@@ -198,18 +212,8 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
       if (r0 + r < nrows) {
         const int64_t node = v0 + r0 + r;
         // bf16 hi/lo split of 4 consecutive columns -> two 8-byte stores into the swizzled image
-        __nv_bfloat16 hi[4], lo[4];
-        const float xs[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          hi[i] = __float2bfloat16_rn(xs[i]);
-          lo[i] = __float2bfloat16_rn(xs[i] - __bfloat162float(hi[i]));
-        }
         uint2 ph, pl;
-        ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
-        ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
-        pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
-        pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+        split4_bf16x2(acc[r], ph, pl);
         const int col = lane * 4, row = (int)(node & 127);
         const size_t tile_off = (size_t)(node >> 7) * 65536;
         const uint32_t sw = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((((col & 63) >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
@@ -296,10 +300,8 @@ __global__ void __launch_bounds__(128) gather_sum_image_src_kernel(const int32_t
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[r][2 * i]), h1 = __float2bfloat16_rn(acc[r][2 * i + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(acc[r][2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(acc[r][2 * i + 1] - __bfloat162float(h1));
-      hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      hw[i] = bf16x2_word(acc[r][2 * i], acc[r][2 * i + 1]);
+      lw[i] = bf16x2_word(acc[r][2 * i] - __uint_as_float(hw[i] << 16), acc[r][2 * i + 1] - __uint_as_float(hw[i] & 0xffff0000u));
     }
     uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (size_t)(node & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((node & 7) << 4));
     *reinterpret_cast<uint4 *>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);

@@ -203,7 +203,9 @@ constexpr int kGtOffBar = kGtStages * kGtStageBytes;
 constexpr int kGtSmem = kGtOffBar + 2 * kGtStages * 8 + 16;
 constexpr int kGtThreads = 32 * kGtConsumers;
 
-template <bool HF32>      // h operand: fp32 rows (step 0: h_0 = x) or the activation image
+// HF32: h operand as fp32 rows (step 0: h_0 = x) or the activation image.  CSRP: the CSR scalars / neighbour ids of the folded
+// gather pipelined across iterations, one value per lane (DDFA_TUNE_GATE_BWD_TMA = 2, default; 1 = fetched inside the iteration).
+template <bool HF32, bool CSRP>
 __global__ void __launch_bounds__(kGtThreads, 1) gate_bwd_tma_kernel(const float *__restrict__ dh_out, const float *__restrict__ h,
                                                                      const uint8_t *__restrict__ h_img_src, const uint2 *__restrict__ gates_packed,
                                                                      const int32_t *__restrict__ indptr, const float *__restrict__ ds_in,
@@ -261,29 +263,72 @@ __global__ void __launch_bounds__(kGtThreads, 1) gate_bwd_tma_kernel(const float
     // ===== consumers =====
     const int col = lane * 4;
     const uint64_t pol_tmp = l2_policy((hints & 4) ? 2 : 0);
+    // The CSR data of the warp's two rows — indptr (in-degree), indptr_t and the first kGtPre transposed neighbour ids — is a chain of
+    // dependent global loads (indptr_t -> indices_t -> ds row); fetched inside the iteration that uses it, the chain was 59 % of the
+    // kernel's stall samples (profiles/r03r: long_scoreboard on these lines).  It is warp-uniform, so it is kept ONE VALUE PER LANE
+    // and pipelined across iterations: lanes 0-3 hold indptr[node_r + {0,1}], lanes 4-7 indptr_t[node_r + {0,1}] (r = (lane >> 1) & 1)
+    // of a block, lanes 8-11 its ids id[r][q] (q = lane & 1); iteration k requests the scalars of block k + 2 and the ids of block
+    // k + 1 (from the scalars that arrived during iteration k - 1) and broadcasts block k's values by shuffle — only the ds rows
+    // themselves are still requested in the iteration that adds them.
+    static_assert(kGtPre == 2, "lane slots below assume two prefetched neighbours per row");
+    auto load_scalars = [&](int kk) -> int {
+      int v = 0;
+      if (kk < my_blocks && lane < 8) {
+        const int64_t nd = (int64_t)(blockIdx.x + (int64_t)kk * gridDim.x) * kGtRows + warp + 16 * ((lane >> 1) & 1);
+        const int32_t *base = lane < 4 ? indptr : indptr_t;
+        if (nd < N && base) v = __ldcg(base + nd + (lane & 1));
+      }
+      return v;
+    };
+    auto load_ids = [&](int sc) -> int {
+      const int r_ = (lane >> 1) & 1, q_ = lane & 1;
+      const int tb_ = __shfl_sync(0xffffffffu, sc, 4 + 2 * r_), te_ = __shfl_sync(0xffffffffu, sc, 5 + 2 * r_);
+      int v = -1;
+      if (lane >= 8 && lane < 12 && tb_ + q_ < te_) v = __ldcg(indices_t + tb_ + q_);
+      return v;
+    };
+    int sc_cur = 0, sc_next = 0, id_cur = -1;
+    if constexpr (CSRP) {
+      sc_cur = load_scalars(0); sc_next = load_scalars(1);
+      id_cur = load_ids(sc_cur);
+    }
     for (int k = 0; k < my_blocks; ++k) {
       const int stage = k % kGtStages, use = k / kGtStages;
       const int64_t r0 = (int64_t)(blockIdx.x + (int64_t)k * gridDim.x) * kGtRows;
-      // the two rows of this warp and their CSR data (global, independent of the staged operands: requested before the wait)
+      // the two rows of this warp and their CSR data
       int64_t node[2];
       bool ok[2];
       int tb[2], te[2], ip0[2], ip1[2];
+      int id[2][kGtPre];      // the first kGtPre neighbours of both rows (a CFG node has ~2 in-edges); longer lists finish below
+      if constexpr (CSRP) {
+        const int sc_next2 = load_scalars(k + 2);
+        const int id_next = load_ids(sc_next);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        node[r] = r0 + warp + 16 * r;
-        ok[r] = node[r] < N;
-        tb[r] = te[r] = ip0[r] = ip1[r] = 0;
-        if (ok[r]) {
-          ip0[r] = __ldcg(indptr + node[r]); ip1[r] = __ldcg(indptr + node[r] + 1);
-          if (indptr_t) { tb[r] = __ldcg(indptr_t + node[r]); te[r] = __ldcg(indptr_t + node[r] + 1); }
+        for (int r = 0; r < 2; ++r) {
+          node[r] = r0 + warp + 16 * r;
+          ok[r] = node[r] < N;
+          ip0[r] = __shfl_sync(0xffffffffu, sc_cur, 2 * r); ip1[r] = __shfl_sync(0xffffffffu, sc_cur, 2 * r + 1);
+          tb[r] = __shfl_sync(0xffffffffu, sc_cur, 4 + 2 * r); te[r] = __shfl_sync(0xffffffffu, sc_cur, 5 + 2 * r);
+#pragma unroll
+          for (int q = 0; q < kGtPre; ++q) id[r][q] = __shfl_sync(0xffffffffu, id_cur, 8 + 2 * r + q);
         }
+        sc_cur = sc_next; sc_next = sc_next2; id_cur = id_next;
+      } else {      // everything requested inside the iteration (global, independent of the staged operands: before the wait)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          node[r] = r0 + warp + 16 * r;
+          ok[r] = node[r] < N;
+          tb[r] = te[r] = ip0[r] = ip1[r] = 0;
+          if (ok[r]) {
+            ip0[r] = __ldcg(indptr + node[r]); ip1[r] = __ldcg(indptr + node[r] + 1);
+            if (indptr_t) { tb[r] = __ldcg(indptr_t + node[r]); te[r] = __ldcg(indptr_t + node[r] + 1); }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int q = 0; q < kGtPre; ++q) id[r][q] = (tb[r] + q < te[r]) ? __ldcg(indices_t + tb[r] + q) : -1;
       }
-      // the first kGtPre neighbours of both rows are fetched ahead of the stage (a CFG node has ~2 in-edges); longer lists finish below
-      int id[2][kGtPre];
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int q = 0; q < kGtPre; ++q) id[r][q] = (tb[r] + q < te[r]) ? __ldcg(indices_t + tb[r] + q) : -1;
       float4 gv[2][kGtPre];
 #pragma unroll
       for (int r = 0; r < 2; ++r)
@@ -890,17 +935,17 @@ int gru_tc2_step_bwd(const float *dh_out, const float *ds_in, const int32_t *ind
     // TMA-staged form (packed saved state only): one CTA per SM, three 64 KB stages
     const int blocks32 = (int)(rows / tc2b::kGtRows);
     const int grid = blocks32 < kNumSMs ? blocks32 : kNumSMs;
-    if (h) {
-      DDFA_CUDA(cudaFuncSetAttribute(tc2b::gate_bwd_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kGtSmem));
-      DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_tma_kernel<true>, dim3(grid), dim3(tc2b::kGtThreads), tc2b::kGtSmem, stream, dh_out, h,
-                             static_cast<const uint8_t *>(h_img_in), static_cast<const uint2 *>(gates_packed), indptr, ds_in,
-                             ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, dhz, db_fold, db_ih, db_hh, l2_hints()));
-    } else {
-      DDFA_CUDA(cudaFuncSetAttribute(tc2b::gate_bwd_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kGtSmem));
-      DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_tma_kernel<false>, dim3(grid), dim3(tc2b::kGtThreads), tc2b::kGtSmem, stream, dh_out, h,
-                             static_cast<const uint8_t *>(h_img_in), static_cast<const uint2 *>(gates_packed), indptr, ds_in,
-                             ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, dhz, db_fold, db_ih, db_hh, l2_hints()));
-    }
+    const bool csrp = gate_bwd_tma() >= 2;
+#define DDFA_GT_LAUNCH(HF32, CSRP)                                                                                                             \
+  do {                                                                                                                                         \
+    DDFA_CUDA(cudaFuncSetAttribute(tc2b::gate_bwd_tma_kernel<HF32, CSRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2b::kGtSmem));        \
+    DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_tma_kernel<HF32, CSRP>, dim3(grid), dim3(tc2b::kGtThreads), tc2b::kGtSmem, stream, dh_out, h,     \
+                           static_cast<const uint8_t *>(h_img_in), static_cast<const uint2 *>(gates_packed), indptr, ds_in,                    \
+                           ds_in ? indptr_t : nullptr, indices_t, N, q_img, img, dhz, db_fold, db_ih, db_hh, l2_hints()));                    \
+  } while (0)
+    if (h) { if (csrp) DDFA_GT_LAUNCH(true, true); else DDFA_GT_LAUNCH(true, false); }
+    else   { if (csrp) DDFA_GT_LAUNCH(false, true); else DDFA_GT_LAUNCH(false, false); }
+#undef DDFA_GT_LAUNCH
   } else
   DDFA_CUDA(launch_chain(4, tc2b::gate_bwd_image_kernel, dim3(gb_grid), dim3(32 * tc2b::kGbWarps), 0, stream, dh_out, h,
                          static_cast<const uint8_t *>(h_img_in), gates, static_cast<const uint4 *>(gates_packed), indptr, ds_in,

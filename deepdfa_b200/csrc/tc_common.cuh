@@ -245,15 +245,18 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
-// 4 consecutive fp32 -> packed 4 x bf16 hi and 4 x bf16 lo (8 bytes each)
+// 4 consecutive fp32 -> packed 4 x bf16 hi and 4 x bf16 lo (8 bytes each).  Two values per conversion instruction
+// (cvt.rn.bf16x2.f32 = F2FP.BF16.F32.PACK_AB, which also does the packing) instead of eight scalar F2F on the quarter-rate
+// conversion pipe plus shifts and ORs; the values are those of split_bf16 (both round to nearest even).
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo_half, float hi_half) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);      // .x -> bits 0-15, .y -> bits 16-31
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
 __device__ __forceinline__ void split4(const float4 &x, uint2 &ph, uint2 &pl) {
-  __nv_bfloat16 hi[4], lo[4];
-  split_bf16(x.x, hi[0], lo[0]); split_bf16(x.y, hi[1], lo[1]);
-  split_bf16(x.z, hi[2], lo[2]); split_bf16(x.w, hi[3], lo[3]);
-  ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
-  ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
-  pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
-  pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+  ph.x = bf16x2_bits(x.x, x.y);
+  ph.y = bf16x2_bits(x.z, x.w);
+  pl.x = bf16x2_bits(x.x - __uint_as_float(ph.x << 16), x.y - __uint_as_float(ph.x & 0xffff0000u));
+  pl.y = bf16x2_bits(x.z - __uint_as_float(ph.y << 16), x.w - __uint_as_float(ph.y & 0xffff0000u));
 }
 // 8 consecutive fp32 (one 16-byte bf16 unit) -> hi / lo uint4
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl) {
@@ -269,9 +272,11 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &ph, uint4 &pl
 // 3.1e-5 on gh_n (|gh_n| < 6.1e-5 flushes to 0) — an order below plain fp16 (2.4e-4 / 4.9e-4), which measurably moved the parameter
 // gradients (profiles/r03b: 1.6e-5 -> 2e-4 relative), at the same 8 bytes.  Layout: x = r | z << 14 | gh[3:0] << 28 ; y = n | gh[19:4] << 16.
 __device__ __forceinline__ uint2 pack_gates(float r, float z, float n, float ghn) {
-  // r, z come out of fast_sigmoid (in [0,1]) and n out of fast_tanh (in [-1,1]): no clamping needed
-  const uint32_t rq = __float2uint_rn(r * 16383.f), zq = __float2uint_rn(z * 16383.f);
-  const uint32_t nq = (uint32_t)__float2int_rn(n * 32767.f) & 0xffffu;
+  // r, z come out of fast_sigmoid (in [0,1]) and n out of fast_tanh (in [-1,1]): no clamping needed.  Rounding to the nearest
+  // integer by adding 2^23 (1.5 * 2^23 for the signed value) inside an FMA and reading the low mantissa bits: one FFMA on the
+  // main pipe instead of FMUL + F2I (the forward epilogue's conversion / MUFU pipe is its busiest unit), and a single rounding.
+  const uint32_t rq = __float_as_uint(fmaf(r, 16383.f, 8388608.f)) & 0x3fffu, zq = __float_as_uint(fmaf(z, 16383.f, 8388608.f)) & 0x3fffu;
+  const uint32_t nq = __float_as_uint(fmaf(n, 32767.f, 12582912.f)) & 0xffffu;
   const uint32_t b = __float_as_uint(ghn);
   // round the mantissa to 14 bits (a carry runs into the exponent, as it should), drop the sign, re-bias the exponent 127 -> 15:
   // core = [exponent - 112 | mantissa] ; below 2^-14 -> 0, above fp16's range -> largest value
@@ -283,7 +288,8 @@ __device__ __forceinline__ uint2 pack_gates(float r, float z, float n, float ghn
 __device__ __forceinline__ void unpack_gates(const uint2 &p, float &r, float &z, float &n, float &ghn) {
   r = (float)(p.x & 0x3fffu) * (1.f / 16383.f);
   z = (float)((p.x >> 14) & 0x3fffu) * (1.f / 16383.f);
-  n = (float)(int)(short)(p.y & 0xffffu) * (1.f / 32767.f);
+  // signed 16-bit -> float without I2F: (value + 32768) placed in the mantissa of 2^23, minus (2^23 + 32768) — exact
+  n = (__uint_as_float(((p.y & 0xffffu) ^ 0x4b008000u)) - 8421376.f) * (1.f / 32767.f);
   const uint32_t g = ((p.y >> 16) << 4) | (p.x >> 28);
   const uint32_t e = (g >> 14) & 31u;
   ghn = e == 0u ? 0.f : __uint_as_float(((g >> 19) << 31) | ((e + 112u) << 23) | ((g & 0x3fffu) << 9));

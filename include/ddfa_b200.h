@@ -55,7 +55,7 @@ enum {
   DDFA_TUNE_PDL_MASK = 1,       /* bit mask of kernels launched with programmatic stream serialization, default 15 */
   DDFA_TUNE_GATHER_VARIANT = 2, /* launch shape of the D = 128 edge gather (ddfa_gather_sum_variant ids), default 9 */
   DDFA_TUNE_FWD_PAIR = 3,       /* 1: forward GRU kernel launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (default 0) */
-  DDFA_TUNE_GATE_BWD_TMA = 4,   /* 1 (default): gate backward streams dh / gates / h through a TMA-fed shared-memory ring; 0: register loads */
+  DDFA_TUNE_GATE_BWD_TMA = 4,   /* gate backward: 0 register loads; 1 dh / gates / h stream through a TMA-fed shared-memory ring; 2 (default) = 1 + the folded gather's CSR scalars pipelined across iterations */
   DDFA_TUNE__COUNT = 5
 };
 int ddfa_tuning_set(int key, int value);

@@ -56,6 +56,9 @@ for STAGE in "$@"; do
     ab-gbtma)     # gate backward: register-path kernel vs TMA-staged kernel, same library, same box
       bash scripts/gpu_ab.sh ${TAG} DDFA_GATE_BWD_TMA 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_gbtma_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_GATE_BWD_TMA 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_gbtma_c0.log ;;
+    ab-csrp)      # TMA-staged gate backward: CSR scalars fetched inside the iteration (1) vs pipelined one value per lane (2)
+      bash scripts/gpu_ab.sh ${TAG} DDFA_GATE_BWD_TMA 1 2 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_csrp_c1.log
+      bash scripts/gpu_ab.sh ${TAG}c0 DDFA_GATE_BWD_TMA 1 2 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_csrp_c0.log ;;
     ab-pair)
       bash scripts/gpu_ab.sh ${TAG} DDFA_FWD_PAIR 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_FWD_PAIR 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c0.log ;;

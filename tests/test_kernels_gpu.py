@@ -452,7 +452,7 @@ def test_gru_step_image_entries_v2(graphs, nodes):
     from deepdfa_b200._lib import TUNE_GATE_BWD_TMA
     outs = {}
     try:
-        for mode in (1, 0):
+        for mode in (2, 1, 0):       # 2 (default): TMA-staged + pipelined CSR scalars; 1: TMA-staged; 0: register path
             L.call("ddfa_tuning_set", TUNE_GATE_BWD_TMA, mode)
             for h_arg in (None, _p(h32)):
                 ds2, dh2 = torch.empty(N, D, device=DEV), torch.empty(N, D, device=DEV)
@@ -463,14 +463,14 @@ def test_gru_step_image_entries_v2(graphs, nodes):
                 torch.cuda.synchronize()
                 outs[(mode, h_arg is None)] = (ds2, dh2, acc2)
     finally:
-        L.call("ddfa_tuning_set", TUNE_GATE_BWD_TMA, 1)
-    for key in ((1, True), (1, False)):
+        L.call("ddfa_tuning_set", TUNE_GATE_BWD_TMA, 2)
+    for key in ((2, True), (2, False), (1, True), (1, False)):
         a, b = outs[key], outs[(0, key[1])]
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), key
         for n_ in ("dbf", "dbih", "dbhh"):
             assert (a[2][n_] - b[2][n_]).abs().max() < 1e-4 * max(1.0, float(b[2][n_].abs().max())), (key, n_)
-    assert torch.equal(outs[(1, True)][0], ds) and torch.equal(outs[(1, True)][1], dh)
-    assert (outs[(1, False)][0] - ds).abs().max() < 1e-3 * max(1.0, float(ds.abs().max()))      # fp32 h vs hi + lo: 2^-17 apart
+    assert torch.equal(outs[(2, True)][0], ds) and torch.equal(outs[(2, True)][1], dh)
+    assert (outs[(2, False)][0] - ds).abs().max() < 1e-3 * max(1.0, float(ds.abs().max()))      # fp32 h vs hi + lo: 2^-17 apart
 
 
 @pytest.mark.parametrize("graphs,nodes", [(3, 50), (40, 150), (1024, 150)])
