@@ -555,3 +555,33 @@ def test_node_label_style_with_undersampling_matches_oracle(engine):
     for k, p in m.named_parameters():
         r = ref_g[k].grad
         assert (p.grad.cpu() - r).abs().max() < tol * max(1.0, float(r.abs().max())), k
+
+
+def test_module_path_is_immune_to_garbage_in_recycled_memory():
+    """The autograd path allocates its activation images fresh every step and clears only the tile that can hold padding rows
+    (engine._FreshAlloc.get_image).  Poison the caching allocator's free blocks with NaNs and check that a training step over a
+    batch whose node count is not a multiple of the 128-row tile still gives the same finite loss and gradients."""
+    if not tc_available():
+        pytest.skip("tcgen05 engine not compiled into libddfa_b200.so")
+    g = synth.make_batch(sizes=[150, 3, 77, 140, 1, 129], seed=21, vuln_rate=0.5, input_dim=64)
+    assert g.num_nodes() % 128 != 0
+    torch.manual_seed(3)
+    m = D.FlowGNNGGNNModule(FEAT, 64, 32, 8, 2, concat_all_absdf=True, engine="tcgen05").to(DEV)
+
+    def run():
+        m.zero_grad(set_to_none=True)
+        loss = m.training_step((g, {}), 0)
+        loss.backward()
+        return float(loss), {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    loss0, grads0 = run()
+    for _ in range(2):
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        junk = [torch.full((n,), float("nan"), device=DEV) for n in (1 << 14, 1 << 18, 1 << 22, 1 << 24)]
+        del junk                              # freed blocks go back to the caching allocator and are handed out again, unzeroed
+        loss1, grads1 = run()
+        assert loss1 == loss1 and abs(loss1 - loss0) < 1e-6
+        for k, g0 in grads0.items():
+            assert torch.isfinite(grads1[k]).all(), k
+            assert (grads1[k] - g0).abs().max() <= 1e-5 * max(1.0, float(g0.abs().max())), k
