@@ -50,6 +50,7 @@ _SIGNATURES = {
     "ddfa_arena_batch_workspace_bytes": (_sz, [_i32]),
     "ddfa_arena_batch": (_int, [_vp, _i32, _i32] + [_vp] * 6 + [_i32, _vp, _i32, _i32] + [_vp] * 7 + [_vp, _sz, _vp]),
     "ddfa_embed_concat_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "ddfa_embed_concat_fwd_image": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ddfa_embed_concat_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ddfa_gather_sum": (_int, [_vp, _vp, _vp, _i32, _i32, _vp, _int, _vp]),
     "ddfa_gather_sum_variant": (_int, [_int, _vp, _vp, _vp, _i32, _i32, _vp, _int, _vp]),

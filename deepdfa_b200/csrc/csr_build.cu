@@ -76,6 +76,70 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t *a0, int32_t *a1
   }
 }
 
+// Multi-CTA scan for large arrays (the single-CTA scan above is a serial chain of passes: 153 600 counts = 10 passes, ~100 us per
+// CSR build at C1, paid every step on the host-batch path).  Three short launches, blockIdx.y = which array:
+//   csr_block_sum_kernel   sums[y][1 + b] = sum of the b-th block of kScanBlock counts
+//   csr_scan_kernel        in-place inclusive scan of sums[y][1 ..]  ->  sums[y][b] = everything before block b
+//   csr_block_scan_kernel  in-place inclusive scan of each block of counts + its offset sums[y][b]
+constexpr int kScanBlock = 4096;      // 256 threads x 16 items
+__global__ void __launch_bounds__(256) csr_block_sum_kernel(const int32_t *a0, const int32_t *a1, int32_t n, int32_t *s0, int32_t *s1) {
+  const int32_t *a = blockIdx.y == 0 ? a0 : a1;
+  int32_t *sums = blockIdx.y == 0 ? s0 : s1;
+  if (a == nullptr) return;
+  a += 1;
+  const int32_t base = blockIdx.x * kScanBlock;
+  int32_t v = 0;
+#pragma unroll
+  for (int j = 0; j < kScanBlock / 256; ++j) {
+    const int32_t i = base + j * 256 + threadIdx.x;      // coalesced
+    v += i < n ? a[i] : 0;
+  }
+  __shared__ int32_t ws[8];
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    sums[1 + blockIdx.x] = t;
+    if (blockIdx.x == 0) sums[0] = 0;
+  }
+}
+__global__ void __launch_bounds__(256) csr_block_scan_kernel(int32_t *a0, int32_t *a1, int32_t n, const int32_t *s0, const int32_t *s1) {
+  int32_t *a = blockIdx.y == 0 ? a0 : a1;
+  const int32_t *sums = blockIdx.y == 0 ? s0 : s1;
+  if (a == nullptr) return;
+  a += 1;
+  constexpr int kItems = kScanBlock / 256;
+  __shared__ int32_t warp_tot[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t i0 = blockIdx.x * kScanBlock + tid * kItems;
+  int32_t v[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j += 4) {      // 16-byte loads (a + 1 is 4-byte aligned only: scalar loads, four in a row per sector)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[j + q] = (i0 + j + q < n) ? a[i0 + j + q] : 0;
+  }
+#pragma unroll
+  for (int j = 1; j < kItems; ++j) v[j] += v[j - 1];
+  int32_t x = v[kItems - 1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[wid] = x;
+  __syncthreads();
+  int32_t before = sums[blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) before += (w < wid) ? warp_tot[w] : 0;
+  const int32_t excl = x - v[kItems - 1] + before;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j)
+    if (i0 + j < n) a[i0 + j] = v[j] + excl;
+}
+
 template <typename IdxT>
 __global__ void csr_fill_kernel(const IdxT *__restrict__ src, const IdxT *__restrict__ dst, int64_t E,
                                 int32_t N, const int32_t *__restrict__ indptr,
@@ -183,8 +247,19 @@ int ddfa_build_csr(const void *src, const void *dst, int idx_bytes, int64_t E, i
     DDFA_CHECK_LAUNCH("csr_count_kernel");
   }
   if (N > 0) {
-    csr_scan_kernel<<<2, 1024, 0, stream>>>(indptr, indptr_t, N);
-    DDFA_CHECK_LAUNCH("csr_scan_kernel");
+    const int nb = (N + kScanBlock - 1) / kScanBlock;
+    // block sums live in the (not yet used) tmp / tmp_t regions: 1 + nb ints each
+    if (N > 4 * kScanBlock && (int64_t)nb + 1 <= E) {
+      csr_block_sum_kernel<<<dim3(nb, 2), 256, 0, stream>>>(indptr, indptr_t, N, tmp, tmp_t);
+      DDFA_CHECK_LAUNCH("csr_block_sum_kernel");
+      csr_scan_kernel<<<2, 1024, 0, stream>>>(indptr ? tmp : nullptr, indptr_t ? tmp_t : nullptr, nb);
+      DDFA_CHECK_LAUNCH("csr_scan_kernel(block sums)");
+      csr_block_scan_kernel<<<dim3(nb, 2), 256, 0, stream>>>(indptr, indptr_t, N, tmp, tmp_t);
+      DDFA_CHECK_LAUNCH("csr_block_scan_kernel");
+    } else {
+      csr_scan_kernel<<<2, 1024, 0, stream>>>(indptr, indptr_t, N);
+      DDFA_CHECK_LAUNCH("csr_scan_kernel");
+    }
   }
   if (E > 0) {
     const int threads = 256;

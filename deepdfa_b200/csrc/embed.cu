@@ -2,20 +2,29 @@
 // Reference: 4x nn.Embedding(input_dim, hidden_dim) + torch.cat(dim=1) (ggnn.py:47-52,84-89) or a
 // single nn.Embedding (ggnn.py:54,91-92).  Tables total 4*1002*32*4 B = 513 KB -> L2 resident;
 // the op is bound by the index read (8 B/node/table) and the 4*D B/node output write.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ddfa {
 
 constexpr int kMaxTables = 8;
+__device__ __forceinline__ uint32_t bf16x2_pack(float lo_half, float hi_half) {     // cvt.rn.bf16x2.f32: .x -> bits 0-15
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
 struct EmbedPtrs {
   const int64_t *idx[kMaxTables];
   const float *table[kMaxTables];
   float *dtable[kMaxTables];
 };
 
-// one thread per 16-byte output chunk
+// one thread per 16-byte output chunk.  IMG (row width 128 only): the row also goes out as h_0's activation image (bf16 hi / lo,
+// K-major SWIZZLE_128B tiles, include/ddfa_b200.h) — what a separate ddfa_act_to_image pass over x produced before.
+template <bool IMG>
 __global__ void __launch_bounds__(256) embed_concat_fwd_kernel(const EmbedPtrs p, int32_t K, int32_t V, int32_t H,
-                                                               int32_t N, float *__restrict__ x, int32_t *__restrict__ oob) {
+                                                               int32_t N, float *__restrict__ x, uint8_t *__restrict__ image,
+                                                               int32_t *__restrict__ oob) {
   const int hq = H >> 2;           // chunks per table
   const int dq = K * hq;           // chunks per node row
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -30,6 +39,16 @@ __global__ void __launch_bounds__(256) embed_concat_fwd_kernel(const EmbedPtrs p
   }
   const float4 v = ldg_nc_f4(p.table[k] + i * H + j);
   *reinterpret_cast<float4 *>(x + (int64_t)n * (K * H) + c * 4) = v;
+  if constexpr (IMG) {
+    const int col = c * 4, row = n & 127;
+    const uint32_t h01 = bf16x2_pack(v.x, v.y), h23 = bf16x2_pack(v.z, v.w);
+    const uint32_t l01 = bf16x2_pack(v.x - __uint_as_float(h01 << 16), v.y - __uint_as_float(h01 & 0xffff0000u));
+    const uint32_t l23 = bf16x2_pack(v.z - __uint_as_float(h23 << 16), v.w - __uint_as_float(h23 & 0xffff0000u));
+    uint8_t *tile = image + (size_t)(n >> 7) * 65536;
+    const uint32_t sw = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((((col & 63) >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
+    *reinterpret_cast<uint2 *>(tile + (size_t)((0 * 2 + (col >> 6)) * 16384) + sw) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2 *>(tile + (size_t)((1 * 2 + (col >> 6)) * 16384) + sw) = make_uint2(l01, l23);
+  }
 }
 
 // Backward: dtable[k][idx_k[n], :] += (dx + dx2)[n, kH:(k+1)H]   (dx2 optional).
@@ -98,23 +117,37 @@ __global__ void __launch_bounds__(256) embed_concat_bwd_kernel(const EmbedPtrs p
 
 extern "C" {
 
-int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables, int32_t K, int32_t V, int32_t H,
-                          int32_t N, float *x, int32_t *oob_count, void *stream_) {
+static int embed_fwd_impl(const char *who, const int64_t *const *idx, const float *const *tables, int32_t K, int32_t V, int32_t H, int32_t N,
+                          float *x, void *image, int32_t *oob_count, void *stream_) {
   using namespace ddfa;
   DDFA_REQUIRE(K >= 1 && K <= kMaxTables && V > 0 && H > 0 && H % 4 == 0 && N >= 0,
-               "ddfa_embed_concat_fwd: unsupported shape K=%d V=%d H=%d N=%d (H%%4==0, K<=%d)", K, V, H, N, kMaxTables);
+               "%s: unsupported shape K=%d V=%d H=%d N=%d (H%%4==0, K<=%d)", who, K, V, H, N, kMaxTables);
+  DDFA_REQUIRE(image == nullptr || K * H == 128, "%s: the activation image exists for row width 128 only (K*H=%d)", who, K * H);
   if (N == 0) return DDFA_OK;
-  DDFA_REQUIRE(idx && tables && x && aligned16(x), "ddfa_embed_concat_fwd: NULL or unaligned pointer");
+  DDFA_REQUIRE(idx && tables && x && aligned16(x) && aligned16(image), "%s: NULL or unaligned pointer", who);
   EmbedPtrs p{};
   for (int k = 0; k < K; ++k) {
-    DDFA_REQUIRE(idx[k] && tables[k] && aligned16(tables[k]), "ddfa_embed_concat_fwd: table %d pointer NULL or unaligned", k);
+    DDFA_REQUIRE(idx[k] && tables[k] && aligned16(tables[k]), "%s: table %d pointer NULL or unaligned", who, k);
     p.idx[k] = idx[k];
     p.table[k] = tables[k];
   }
   const int64_t tot = (int64_t)N * K * (H / 4);
-  embed_concat_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream_)>>>(p, K, V, H, N, x, oob_count);
+  const unsigned grid = (unsigned)((tot + 255) / 256);
+  if (image) embed_concat_fwd_kernel<true><<<grid, 256, 0, as_stream(stream_)>>>(p, K, V, H, N, x, static_cast<uint8_t *>(image), oob_count);
+  else embed_concat_fwd_kernel<false><<<grid, 256, 0, as_stream(stream_)>>>(p, K, V, H, N, x, nullptr, oob_count);
   DDFA_CHECK_LAUNCH("embed_concat_fwd_kernel");
   return DDFA_OK;
+}
+
+int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables, int32_t K, int32_t V, int32_t H,
+                          int32_t N, float *x, int32_t *oob_count, void *stream_) {
+  return embed_fwd_impl("ddfa_embed_concat_fwd", idx, tables, K, V, H, N, x, nullptr, oob_count, stream_);
+}
+
+int ddfa_embed_concat_fwd_image(const int64_t *const *idx, const float *const *tables, int32_t K, int32_t V, int32_t H,
+                                int32_t N, float *x, void *image, int32_t *oob_count, void *stream_) {
+  DDFA_REQUIRE(image != nullptr, "ddfa_embed_concat_fwd_image: NULL image");
+  return embed_fwd_impl("ddfa_embed_concat_fwd_image", idx, tables, K, V, H, N, x, image, oob_count, stream_);
 }
 
 int ddfa_embed_concat_bwd(const int64_t *const *idx, const float *dx, const float *dx2, int32_t K, int32_t V, int32_t H,

@@ -289,14 +289,23 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
     nl = len(params.mlp_w)
     st = _stream_ptr()
 
+    use_images = engine == ENGINE_TCGEN05     # activations travel as MMA-ready bf16 hi/lo images (include/ddfa_b200.h)
     x = alloc.get("x", (N, D))
-    _call("ddfa_embed_concat_fwd", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
-           K, V, H, N, _p(x), _p(oob_counter), st)
+    h_imgs = None
+    if use_images and OPTIONS["packed_state"]:
+        # the embedding kernel writes h_0 = x as fp32 rows AND as its activation image (one pass instead of embed + ddfa_act_to_image)
+        img_bytes = L.call("ddfa_act_image_bytes", N)
+        n_img = T if training else 2          # training keeps the image of every h_t (the weight-gradient GEMM reads it)
+        h_imgs = [alloc.get_image(f"h_img{i}", img_bytes) for i in range(max(n_img, 1))]
+        _call("ddfa_embed_concat_fwd_image", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
+              K, V, H, N, _p(x), _p(h_imgs[0]), _p(oob_counter), st)
+    else:
+        _call("ddfa_embed_concat_fwd", ptr_array([_p(t) for t in idx]), ptr_array([_p(t) for t in params.tables]),
+              K, V, H, N, _p(x), _p(oob_counter), st)
     w_fold = alloc.get("w_fold", (3 * D, D))
     b_fold = alloc.get("b_fold", (3 * D,))
     L.call("ddfa_fold_weights_fwd", _p(params.w_msg), _p(params.b_msg), _p(params.w_ih), D, _p(w_fold), _p(b_fold), st)
 
-    use_images = engine == ENGINE_TCGEN05     # activations travel as MMA-ready bf16 hi/lo images (include/ddfa_b200.h)
     ws_bytes = L.call("ddfa_gru_step_workspace_bytes", 0 if use_images else N, D, engine)
     ws = alloc.get("gru_ws", (max(ws_bytes, 16),), torch.uint8)
     L.call("ddfa_gru_step_prepare", _p(w_fold), _p(b_fold), _p(params.b_ih), _p(params.w_hh), _p(params.b_hh), D, engine,
@@ -323,11 +332,7 @@ def forward(params: ParamPack, dg: DeviceGraph, idx: List[torch.Tensor], n_steps
         # tcgen05 engine: between steps h_t exists ONLY as its activation image (the GEMM operand; h = hi + lo to 2^-17) — the
         # gather, the z*h term and the backward pass read that; fp32 copies exist of h_0 = x and of h_T (for the readout).  The
         # four saved gate values of an element travel as one 8-byte word (14/14/16-bit fixed point + a 20-bit float, <= 3.1e-5).
-        img_bytes = L.call("ddfa_act_image_bytes", N)
         gate_bytes = L.call("ddfa_gru_gates_packed_bytes", N, D)
-        n_img = T if training else 2          # training keeps the image of every h_t (the weight-gradient GEMM reads it)
-        h_imgs = [alloc.get_image(f"h_img{i}", img_bytes) for i in range(max(n_img, 1))]
-        L.call("ddfa_act_to_image", _p(x), N, D, _p(h_imgs[0]), st)
         for t in range(T):
             last = t == T - 1
             s_t = alloc.get_image(f"s_img{t}" if training else "s_img", img_bytes)

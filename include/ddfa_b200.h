@@ -118,6 +118,12 @@ int ddfa_arena_batch(const int32_t *graph_ids, int32_t batch_size, int32_t num_g
 int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables, int32_t num_tables,
                           int32_t vocab, int32_t width, int32_t num_nodes, float *x,
                           int32_t *oob_count, void *stream);
+/* Same, and the rows also leave as h_0's activation image (row width K*H == 128; layout below, `image` holds
+ * ddfa_act_image_bytes(num_nodes) bytes): what ddfa_act_to_image(x) would write, without the second pass over x.
+ * Rows num_nodes .. (next multiple of 128) of the image are not written. */
+int ddfa_embed_concat_fwd_image(const int64_t *const *idx, const float *const *tables, int32_t num_tables,
+                                int32_t vocab, int32_t width, int32_t num_nodes, float *x, void *image,
+                                int32_t *oob_count, void *stream);
 /* dtables[k][idx_k[n], :] += (dx + dx2)[n, k*H:(k+1)*H]   (autograd of ggnn.py:84-92).
  * dx2 may be NULL; it lets the caller sum the two gradient paths into x (through the GGNN and
  * through the concat of ggnn.py:98) without a separate add kernel. */

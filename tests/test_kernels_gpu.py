@@ -79,6 +79,19 @@ def test_build_csr_large_scan_empty_and_out_of_range():
     assert np.array_equal(dg.indptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=g.num_nodes()))]))
     assert np.array_equal(dg.indices.cpu().numpy()[: g.num_edges()], src[np.lexsort((src, dst))])
     assert np.array_equal(dg.graph_ptr.cpu().numpy(), np.concatenate([[0], np.cumsum(g.batch_num_nodes().numpy())]))
+    # the multi-CTA scan (N > 16 384 rows: block sums -> scan of the sums -> per-block scan) at ragged sizes, both orientations
+    rng = np.random.default_rng(5)
+    for N, E in ((16385, 40000), (20481, 30000), (153677, 307201), (70000, 18)):
+        src = rng.integers(0, N, E); dst = rng.integers(0, N, E)
+        s, d = dev(torch.from_numpy(src)), dev(torch.from_numpy(dst))
+        indptr = torch.empty(N + 1, dtype=torch.int32, device=DEV); indices = torch.empty(E, dtype=torch.int32, device=DEV)
+        indptr_t = torch.empty_like(indptr); indices_t = torch.empty_like(indices)
+        wsb = L.call("ddfa_build_csr_workspace_bytes", E, N); ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        L.call("ddfa_build_csr", _p(s), _p(d), 8, E, N, _p(indptr), _p(indices), _p(indptr_t), _p(indices_t), _p(ws), wsb, st())
+        torch.cuda.synchronize()
+        assert np.array_equal(indptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=N))])), (N, E)
+        assert np.array_equal(indptr_t.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(src, minlength=N))])), (N, E)
+        assert np.array_equal(indices.cpu().numpy(), src[np.lexsort((src, dst))]) and np.array_equal(indices_t.cpu().numpy(), dst[np.lexsort((dst, src))])
     # empty edge list
     indptr = torch.full((6,), -1, dtype=torch.int32, device=DEV); indices = torch.empty(1, dtype=torch.int32, device=DEV)
     wsb = L.call("ddfa_build_csr_workspace_bytes", 0, 5); ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
@@ -162,6 +175,15 @@ def test_embed_concat_fwd_bwd(K, H):
     x = torch.empty(N, K * H, device=DEV); oob = torch.zeros(1, dtype=torch.int32, device=DEV)
     lib().call("ddfa_embed_concat_fwd", ptr_array([_p(i) for i in idd]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x), _p(oob), st())
     assert torch.equal(x.cpu(), ref) and int(oob) == 0
+    if K * H == 128:      # fused form: the same rows AND h_0's activation image, bit-equal to a separate ddfa_act_to_image pass
+        ib = lib().call("ddfa_act_image_bytes", N)
+        img_a, img_b = torch.zeros(ib, dtype=torch.uint8, device=DEV), torch.zeros(ib, dtype=torch.uint8, device=DEV)
+        x2 = torch.empty_like(x)
+        lib().call("ddfa_embed_concat_fwd_image", ptr_array([_p(i) for i in idd]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x2), _p(img_a), _p(oob), st())
+        lib().call("ddfa_act_to_image", _p(x), N, K * H, _p(img_b), st())
+        assert torch.equal(x2, x) and torch.equal(img_a, img_b) and int(oob) == 0
+        with pytest.raises(DdfaError, match="NULL image"):
+            lib().call("ddfa_embed_concat_fwd_image", ptr_array([_p(i) for i in idd]), ptr_array([_p(t) for t in td]), K, V, H, N, _p(x2), None, _p(oob), st())
     dx, dx2 = torch.randn(N, K * H), torch.randn(N, K * H)
     dx_d, dx2_d = dev(dx), dev(dx2)          # keep the device tensors alive across the call (no aliasing temporaries)
     for second in (None, dx2):

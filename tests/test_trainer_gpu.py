@@ -74,8 +74,14 @@ def test_training_decisions_and_f1_follow_the_oracle(engine):
     assert agree >= 0.99 and abs(f1_o - f1_m) <= 0.02
 
 
-def _run_stream(trainer, batches, order):
-    return [float(trainer.step(batches[i])) for i in order]
+def _run_stream(trainer, batches, order, prefetch=False):
+    out = []
+    for k, i in enumerate(order):
+        loss = trainer.step(batches[i])
+        if prefetch and k + 1 < len(order):      # stage the next batch (host padding + H2D on the copy stream) while this step runs
+            trainer.prefetch(batches[order[k + 1]])
+        out.append(float(loss))
+    return out
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
@@ -88,23 +94,25 @@ def test_bucketed_variable_stream_replays_graphs_and_matches_eager(engine):
     assert len(shapes) >= 8
     order = list(range(10)) * 4
     results = {}
-    for mode in ("eager", "bucketed"):
+    for mode in ("eager", "bucketed", "bucketed+prefetch"):
         torch.manual_seed(3)
         m = D.FlowGNNGGNNModule(FEAT, 1002, 32, 4, 2, concat_all_absdf=True, positive_weight=2.0, engine=engine).to(DEV)
         if mode == "eager":
             tr = D.FusedTrainer(m)
         else:
             tr = D.FusedTrainer(m, use_cuda_graph=True, bucket_nodes=256, bucket_edges=512, bucket_min_pad_nodes=8, max_graph_shapes=16)
-        results[mode] = (_run_stream(tr, batches, order), [p.detach().clone() for p in m.param_list()], tr)
+        results[mode] = (_run_stream(tr, [b.pin_memory() for b in batches] if "prefetch" in mode else batches, order, prefetch="prefetch" in mode),
+                         [p.detach().clone() for p in m.param_list()], tr)
     tr = results["bucketed"][2]
     nshapes = tr.num_bucket_shapes()
     assert 1 <= nshapes <= 4, nshapes                      # ten distinct shapes collapse onto a few bucket shapes
     captured = sum(1 for slot in tr._stream_slots.values() for st in slot["sets"] if st["graph"] is not None)
     assert captured >= nshapes                             # ... and those are replayed as CUDA graphs
-    for a, b in zip(results["eager"][0], results["bucketed"][0]):
-        assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (results["eager"][0][:6], results["bucketed"][0][:6])
-    for p, q in zip(results["eager"][1], results["bucketed"][1]):
-        assert float((p - q).abs().max()) < 5e-4           # 40 Adam steps at lr 1e-3; sign-level noise only
+    for mode in ("bucketed", "bucketed+prefetch"):
+        for a, b in zip(results["eager"][0], results[mode][0]):
+            assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (mode, results["eager"][0][:6], results[mode][0][:6])
+        for p, q in zip(results["eager"][1], results[mode][1]):
+            assert float((p - q).abs().max()) < 5e-4       # 40 Adam steps at lr 1e-3; sign-level noise only
 
 
 def test_captured_graphs_survive_workspace_growth():
