@@ -342,7 +342,7 @@ def roofline_lines(prof, ms_region, N, Eg, engine, peaks, mode_tag):
         lines.insert(2, hbm_line(f"wgrad_kernel + wgrad_reduce_kernel (weight gradients of all {T} steps in one launch)",
                                  6 * P * T, wg_ms, wg_n, share["wgrad_batched"], traffic=None,
                                  tensor_tflops_issued=3 * flops_fold * T / (wg_ms * 1e-3) / 1e12))
-    roofline = dict(fwd_line, note="dominant single kernel by time; the other hot kernels are in roofline_kernels; frac = design bytes (bytes_per_launch; 5P with the packed saved state) "
+    roofline = dict(fwd_line, note="the forward GRU step kernel: ~24 % of the step and the hot kernel furthest below its roofline (the gate-backward + dgrad pair is the larger share, ~42 %, at ~0.95 of peak: roofline_kernels); frac = design bytes (bytes_per_launch; 5P with the packed saved state) "
                                    "over the launch time vs the measured HBM peak, frac_8d / tensor_frac_8d = SURVEY.md §8(d)'s algorithmic bytes / FLOPs")
     return roofline, lines
 
