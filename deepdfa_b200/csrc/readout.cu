@@ -294,21 +294,47 @@ __global__ void relu_mask_kernel(const float *in, const float *__restrict__ mask
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < total) out[i] = (mask[i] > 0.f) ? in[i] : 0.f;
 }
-// out[n] += sum_m X[m,n]   (M small: one thread per column, coalesced across threads)
-// block = (32 columns) x (8 row partitions); one block owns its 32 columns, so the += needs no atomics
+// ---- MLP head over the whole batch (large training batches): hidden layers as one GEMM each + this epilogue, last layer below ----
+// a[m, n] = max(a[m, n] + bias[n], 0), 4 columns per thread (n % 4 == 0)
+__global__ void __launch_bounds__(256) bias_relu_kernel(float *__restrict__ a, const float *__restrict__ bias, int64_t total4, int32_t n4) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 v = *reinterpret_cast<const float4 *>(a + 4 * i);
+  const float4 b = *reinterpret_cast<const float4 *>(bias + 4 * (i % n4));
+  v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+  *reinterpret_cast<float4 *>(a + 4 * i) = v;
+}
+// logits[b] = in[b, :] . w + bias[0]: one warp per graph, the lane partition and shuffle tree of the in-CTA last layer (same sums)
+__global__ void __launch_bounds__(256) mlp_out_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                                      int32_t B, int32_t D2, float *__restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = lane * 4; k < D2; k += 128) s += f4_dot(ldg_nc_f4(w + k), *reinterpret_cast<const float4 *>(in + (int64_t)b * D2 + k));
+  s = warp_sum(s);
+  if (lane == 0) logits[b] = s + bias[0];
+}
+
+// out[n] += sum_m X[m,n]   (one thread per column, coalesced across threads)
+// block = (32 columns) x (8 row partitions); gridDim.y slices the rows (a single row slice owns its columns: plain +=; several
+// slices — long M, e.g. the MLP head's bias gradients over a batch of 1024 — accumulate with RED.ADD)
 __global__ void __launch_bounds__(256) colsum_accum_kernel(const float *__restrict__ X, int32_t M, int32_t N, float *__restrict__ out) {
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += X[(int64_t)m * N + n];
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) s += X[(int64_t)m * N + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
-    out[n] += t;
+    if (gridDim.y > 1) atomicAdd(out + n, t);
+    else out[n] += t;
   }
 }
 
@@ -337,14 +363,36 @@ int ddfa_readout_mlp_fwd(const float *h_final, const float *x, const int32_t *gr
   const int D2 = 2 * D;
   const size_t smem = sizeof(float) * ((size_t)kReadoutWarps * D2 + 2 * kReadoutWarps + 2 * D2);
   const int ch = (D / 4 + 31) / 32;
+  // Large training batches: the in-CTA MLP re-reads every weight matrix (2D x 2D floats from L2) once per graph and is a chain of
+  // 2D / 32 load latencies per warp and layer (profiles/r03q: 69 us at B = 1024, ~20 us of it pooling).  With B >= 256 and a place
+  // for the hidden activations (mlp_act: training) the kernel only pools, each hidden layer is ONE GEMM over the batch
+  // (sgemm_small_kernel) + bias / ReLU, and the last layer a warp per graph.  Same values up to fp32 summation order in the
+  // hidden layers; rows are independent of the batch they are in either way.
+  bool batched = L >= 1 && B >= 256 && (L == 1 || mlp_act != nullptr) && D2 % 4 == 0 && aligned16(pooled) && aligned16(mlp_act);
+  for (int i = 0; i + 1 < L; ++i) batched = batched && aligned16(mp.b[i]);
+  const int L_in_kernel = batched ? 0 : L;
 #define LAUNCH(CH)                                                                                              \
-  readout_mlp_fwd_kernel<CH><<<B, kReadoutWarps * 32, smem, stream>>>(h_final, x, graph_ptr, D, w_gate, b_gate, mp, L, pooled, \
+  readout_mlp_fwd_kernel<CH><<<B, kReadoutWarps * 32, smem, stream>>>(h_final, x, graph_ptr, D, w_gate, b_gate, mp, L_in_kernel, pooled, \
                                                                       logits, gate_logit, seg_max, seg_sum, mlp_act, B)
   if (ch == 1) LAUNCH(1);
   else if (ch == 2) LAUNCH(2);
   else LAUNCH(4);
 #undef LAUNCH
   DDFA_CHECK_LAUNCH("readout_mlp_fwd_kernel");
+  if (batched) {
+    const float *in = pooled;
+    for (int i = 0; i + 1 < L; ++i) {
+      float *act = mlp_act + (size_t)i * B * D2;
+      const int rc = sgemm(0, 1, B, D2, D2, 1.f, in, D2, mp.w[i], D2, 0.f, act, D2, 1, stream);     // act = in @ W_i^T
+      if (rc) return rc;
+      const int64_t total4 = (int64_t)B * D2 / 4;
+      bias_relu_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(act, mp.b[i], total4, D2 / 4);
+      DDFA_CHECK_LAUNCH("bias_relu_kernel");
+      in = act;
+    }
+    mlp_out_kernel<<<(B + 7) / 8, 256, 0, stream>>>(in, mp.w[L - 1], mp.b[L - 1], B, D2, logits);
+    DDFA_CHECK_LAUNCH("mlp_out_kernel");
+  }
   return DDFA_OK;
 }
 
@@ -367,7 +415,7 @@ int ddfa_mlp_bwd(const float *dlogits, const float *pooled, const float *mlp_act
     // dW_i[out,2D] += dOut^T[out,B] @ in[B,2D]
     int rc = sgemm(1, 0, out_dim, D2, B, 1.f, dout, out_dim, in, D2, 1.f, dmlp_w[i], D2, 1, stream);
     if (rc) return rc;
-    colsum_accum_kernel<<<(out_dim + 31) / 32, dim3(32, 8), 0, stream>>>(dout, B, out_dim, dmlp_b[i]);
+    colsum_accum_kernel<<<dim3((out_dim + 31) / 32, B >= 256 ? (B + 63) / 64 : 1), dim3(32, 8), 0, stream>>>(dout, B, out_dim, dmlp_b[i]);
     DDFA_CHECK_LAUNCH("colsum_accum_kernel");
     // dIn[B,2D] = dOut[B,out] @ W_i[out,2D]
     float *din = (i == 0) ? dpooled : (dout == buf0 ? buf1 : buf0);

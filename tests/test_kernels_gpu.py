@@ -585,6 +585,58 @@ def test_ggnn_fused_drivers(D, T):
                _p(pd["w_hh"]), _p(pd["b_ih"]), _p(pd["b_hh"]), _p(h_out), _p(ws), 16, 1, ENGINE_SIMT, st())
 
 
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_readout_mlp_batched_head_for_large_training_batches(L):
+    """B >= 256 with a place for the hidden activations (training): the readout kernel only pools, every hidden layer is one GEMM
+    over the batch + bias / ReLU, the last layer a warp per graph.  Held to an fp64 reference and to the in-CTA path (same call
+    without mlp_act, which keeps the whole MLP inside the pooling kernel)."""
+    D, B = 128, 300
+    D2 = 2 * D
+    rng = np.random.default_rng(L)
+    sizes = rng.integers(1, 24, B)
+    bnn = torch.from_numpy(sizes)
+    N = int(bnn.sum())
+    torch.manual_seed(10 + L)
+    h, x = torch.randn(N, D), torch.randn(N, D)
+    gate = torch.nn.Linear(D2, 1)
+    lins = [torch.nn.Linear(D2, 1 if i == L - 1 else D2) for i in range(L)]
+    feat = torch.cat([h, x], 1).double()
+    gl_ref = feat @ gate.weight.double().t() + gate.bias.double()
+    pooled_ref = torch.zeros(B, D2, dtype=torch.float64)
+    acts_ref, off = [], 0
+    for b, n in enumerate(sizes):
+        a = torch.softmax(gl_ref[off:off + n, 0], 0)
+        pooled_ref[b] = (a[:, None] * feat[off:off + n]).sum(0)
+        off += n
+    cur = pooled_ref
+    for i, lin in enumerate(lins):
+        cur = cur @ lin.weight.double().t() + lin.bias.double()
+        if i != L - 1:
+            cur = torch.relu(cur)
+            acts_ref.append(cur)
+    out_ref = cur.squeeze(-1)
+    graph_ptr = dev(torch.cat([torch.zeros(1, dtype=torch.int64), bnn.cumsum(0)]).to(torch.int32))
+    hd, xd = dev(h), dev(x)
+    wg, bg = dev(gate.weight.detach().reshape(-1)), dev(gate.bias.detach())
+    mw, mb = [dev(m.weight.detach()) for m in lins], [dev(m.bias.detach()) for m in lins]
+    Lb = lib()
+    outs = {}
+    for mode in ("batched", "in_cta"):
+        pooled = torch.empty(B, D2, device=DEV); logits = torch.full((B,), float("nan"), device=DEV)
+        gl = torch.empty(N, device=DEV); smax = torch.empty(B, device=DEV); ssum = torch.empty(B, device=DEV)
+        act = torch.full((max(L - 1, 1), B, D2), float("nan"), device=DEV)
+        Lb.call("ddfa_readout_mlp_fwd", _p(hd), _p(xd), _p(graph_ptr), B, D, _p(wg), _p(bg), ptr_array([_p(t) for t in mw]),
+                ptr_array([_p(t) for t in mb]), L, _p(pooled), _p(logits), _p(gl), _p(smax), _p(ssum), _p(act) if mode == "batched" else None, st())
+        torch.cuda.synchronize()
+        outs[mode] = (pooled, logits, act)
+        assert (pooled.cpu().double() - pooled_ref).abs().max() < 1e-5
+        assert (logits.cpu().double() - out_ref.detach()).abs().max() < 2e-5 * max(1.0, float(out_ref.abs().max()))
+    for i, a_ref in enumerate(acts_ref):
+        assert (outs["batched"][2][i].cpu().double() - a_ref.detach()).abs().max() < 2e-5 * max(1.0, float(a_ref.abs().max()))
+    assert torch.equal(outs["batched"][0], outs["in_cta"][0])
+    assert (outs["batched"][1] - outs["in_cta"][1]).abs().max() < 1e-5
+
+
 @pytest.mark.parametrize("D,L", [(128, 3), (128, 1), (32, 2), (64, 0), (256, 2)])
 def test_readout_mlp_fwd_bwd(D, L):
     sizes = [1, 2, 300, 40, 5, 0, 17]          # includes an EMPTY graph (pooled = 0) and a 1-node graph
