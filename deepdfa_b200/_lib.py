@@ -87,7 +87,7 @@ _SIGNATURES = {
     "ddfa_sgemm": (_int, [_int, _int, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _i32, _f32, _vp, _i32, _i32, _vp]),
 }
 
-TUNE_L2_HINTS, TUNE_PDL_MASK, TUNE_GATHER_VARIANT, TUNE_FWD_PAIR, TUNE_GATE_BWD_TMA = 0, 1, 2, 3, 4
+TUNE_L2_HINTS, TUNE_PDL_MASK, TUNE_GATHER_VARIANT, TUNE_FWD_PAIR, TUNE_GATE_BWD_TMA, TUNE_GATHER_SRC_GROUPS = 0, 1, 2, 3, 4, 5
 
 _NO_STATUS = {"ddfa_gru_gates_packed_bytes", "ddfa_tuning_get", "ddfa_abi_version", "ddfa_last_error", "ddfa_device_supported", "ddfa_launch_count", "ddfa_engine_available",
               "ddfa_build_csr_workspace_bytes", "ddfa_arena_batch_workspace_bytes", "ddfa_gru_step_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes", "ddfa_gru_step_bwd_workspace_bytes_steps",
@@ -119,7 +119,8 @@ class _Lib:
             raise DdfaError(f"ABI version mismatch: library {abi}, binding 1")
         # A/B scripts select launch configurations through the environment of the PYTHON layer; the library itself reads none
         for env, key in (("DDFA_L2_HINTS", TUNE_L2_HINTS), ("DDFA_PDL", TUNE_PDL_MASK), ("DDFA_GATHER_VARIANT", TUNE_GATHER_VARIANT),
-                         ("DDFA_FWD_PAIR", TUNE_FWD_PAIR), ("DDFA_GATE_BWD_TMA", TUNE_GATE_BWD_TMA)):
+                         ("DDFA_FWD_PAIR", TUNE_FWD_PAIR), ("DDFA_GATE_BWD_TMA", TUNE_GATE_BWD_TMA),
+                         ("DDFA_GATHER_SRC_GROUPS", TUNE_GATHER_SRC_GROUPS)):
             if os.environ.get(env) is not None:
                 self._dll.ddfa_tuning_set(key, int(os.environ[env]))
 

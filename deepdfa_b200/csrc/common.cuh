@@ -61,6 +61,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 int pdl_mask();       // abi.cu: DDFA_TUNE_PDL_MASK — bit mask of the kernels launched programmatically (1 gather_image, 2 gru_fwd3, 4 gate_bwd, 8 dgrad3)
 int gather_variant(); // abi.cu: DDFA_TUNE_GATHER_VARIANT
 int fwd_pair();       // abi.cu: DDFA_TUNE_FWD_PAIR — forward GRU kernel as CTA pairs (cta_group::2)
+int gather_src_groups();   // abi.cu: DDFA_TUNE_GATHER_SRC_GROUPS — row groups per warp of the image->image gather (0 = by size)
 int gate_bwd_tma();   // abi.cu: DDFA_TUNE_GATE_BWD_TMA — TMA-staged gate backward kernel (packed saved state)
 void chain_break();   // abi.cu: the next launch_chain() on this thread is a normal (fully serialised) launch
 bool chain_take_break();

@@ -229,11 +229,16 @@ __global__ void __launch_bounds__(128) gather_sum_image_kernel(const int32_t *__
 // The same gather for the steps whose h_t exists only as its image (tcgen05 engine, t >= 1: the forward GRU kernel no longer
 // writes an fp32 copy of h').  A node's image row is four 128-byte pieces [hi | lo] x [cols 0-63 | 64-127]; lane l fetches one
 // 16-byte unit (8 bf16) of each of two pieces (mapping: see the kernel).
+// G: row groups per warp.  The CSR data of a group is a chain of dependent loads (indptr -> indices -> rows); with G > 1 a warp walks
+// G consecutive groups and keeps the chain pipelined: while it fetches the rows of group i, the neighbour ids of group i + 1 and the
+// row pointers of group i + 2 are already in flight, so per group only the row fetch is exposed instead of three latencies
+// (the one-group form sat at 3.1 TB/s of DRAM traffic with ~50 % of the warps resident: latency, not bandwidth).
+template <int G>
 __global__ void __launch_bounds__(128) gather_sum_image_src_kernel(const int32_t *__restrict__ indptr,
                                                                    const int32_t *__restrict__ indices,
                                                                    const uint8_t *__restrict__ h_img, int32_t N,
                                                                    uint8_t *__restrict__ out_img) {
-  // A warp owns 4 consecutive destination rows; each HALF-warp sums two of them.  Lane j of a half owns columns 8 j .. 8 j + 7:
+  // A warp owns 4 consecutive destination rows per group; each HALF-warp sums two of them.  Lane j of a half owns columns 8 j .. 8 j + 7:
   // per neighbour it fetches that unit's hi and lo 16-byte pieces (un-swizzling by row & 7), adds them (exact in fp32: h = hi + lo)
   // and accumulates — so every lane ends with final sums, which it splits and stores as the two pieces of the output image.
   constexpr int ROWS = 4, UNROLL = 2;
@@ -241,71 +246,87 @@ __global__ void __launch_bounds__(128) gather_sum_image_src_kernel(const int32_t
   const int hf = lane >> 4, j = lane & 15;
   const uint32_t piece_off = (uint32_t)((j >> 3) * 16384), unit16 = (uint32_t)((j & 7) << 4);
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t v0 = warp_global * ROWS;
   const int64_t Npad = ((int64_t)N + 127) / 128 * 128;
   pdl_launch_dependents();
   pdl_wait();
-  if (v0 >= Npad) return;        // Npad is a multiple of 4: a warp's four rows are all inside the padded range
-  int32_t myptr = 0;
-  if (lane <= ROWS) myptr = __ldcg(indptr + min(v0 + lane, (int64_t)N));   // rows past N: empty neighbour list -> zeros
-  const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
-  const int32_t total = __shfl_sync(0xffffffffu, myptr, ROWS) - beg0;
-  const int32_t pre = (lane < total) ? __ldcg(indices + beg0 + lane) : 0;
-  // this half's two rows: edges [hbeg, hmid) belong to row 2 hf, [hmid, hend) to row 2 hf + 1 (offsets relative to beg0)
-  const int32_t hbeg = __shfl_sync(0xffffffffu, myptr, 2 * hf) - beg0;
-  const int32_t hmid = __shfl_sync(0xffffffffu, myptr, 2 * hf + 1) - beg0;
-  const int32_t hend = __shfl_sync(0xffffffffu, myptr, 2 * hf + 2) - beg0;
-  const int32_t len_other = __shfl_xor_sync(0xffffffffu, hend - hbeg, 16);
-  const int32_t trips = max(hend - hbeg, len_other);       // warp-uniform trip count (the shuffles below need all lanes)
-  float acc[2][8];
+  // row pointers of group i (lanes 0..ROWS; rows past N: empty neighbour list -> zeros) and its first 32 neighbour ids
+  auto load_ptr = [&](int i) -> int32_t {
+    const int64_t v = (warp_global * G + i) * ROWS;
+    return (i < G && v < Npad && lane <= ROWS) ? __ldcg(indptr + min(v + lane, (int64_t)N)) : 0;
+  };
+  auto load_ids = [&](int32_t ptr) -> int32_t {
+    const int32_t b0 = __shfl_sync(0xffffffffu, ptr, 0), tot = __shfl_sync(0xffffffffu, ptr, ROWS) - b0;
+    return (lane < tot) ? __ldcg(indices + b0 + lane) : 0;
+  };
+  int32_t ptr_cur = load_ptr(0), ptr_next = load_ptr(1);
+  int32_t pre_cur = load_ids(ptr_cur);
+#pragma unroll 1
+  for (int gi = 0; gi < G; ++gi) {
+    const int64_t v0 = (warp_global * G + gi) * ROWS;
+    if (v0 >= Npad) return;        // warp-uniform; Npad is a multiple of 4: a group's four rows are all inside the padded range
+    const int32_t myptr = ptr_cur, pre = pre_cur;
+    if (G > 1) {                   // keep the chain of the next groups in flight
+      pre_cur = load_ids(ptr_next);
+      ptr_cur = ptr_next;
+      ptr_next = load_ptr(gi + 2);
+    }
+    const int32_t beg0 = __shfl_sync(0xffffffffu, myptr, 0);
+    // this half's two rows: edges [hbeg, hmid) belong to row 2 hf, [hmid, hend) to row 2 hf + 1 (offsets relative to beg0)
+    const int32_t hbeg = __shfl_sync(0xffffffffu, myptr, 2 * hf) - beg0;
+    const int32_t hmid = __shfl_sync(0xffffffffu, myptr, 2 * hf + 1) - beg0;
+    const int32_t hend = __shfl_sync(0xffffffffu, myptr, 2 * hf + 2) - beg0;
+    const int32_t len_other = __shfl_xor_sync(0xffffffffu, hend - hbeg, 16);
+    const int32_t trips = max(hend - hbeg, len_other);       // warp-uniform trip count (the shuffles below need all lanes)
+    float acc[2][8];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
-  for (int32_t t = 0; t < trips; t += UNROLL) {
-    uint4 vh[UNROLL], vl[UNROLL];
+      for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+    for (int32_t t = 0; t < trips; t += UNROLL) {
+      uint4 vh[UNROLL], vl[UNROLL];
 #pragma unroll
-    for (int q = 0; q < UNROLL; ++q) {
-      const int32_t pos = hbeg + t + q;
-      const bool on = pos < hend;
-      const int32_t pc = on ? pos : 0;
-      int32_t u = __shfl_sync(0xffffffffu, pre, pc & 31);
-      if (on && pc >= 32) u = __ldcg(indices + beg0 + pc);
-      const uint8_t *src = h_img + (size_t)(u >> 7) * 65536 + (size_t)(u & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((u & 7) << 4));
-      vh[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
-      vl[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src + 32768)) : make_uint4(0u, 0u, 0u, 0u);
+      for (int q = 0; q < UNROLL; ++q) {
+        const int32_t pos = hbeg + t + q;
+        const bool on = pos < hend;
+        const int32_t pc = on ? pos : 0;
+        int32_t u = __shfl_sync(0xffffffffu, pre, pc & 31);
+        if (on && pc >= 32) u = __ldcg(indices + beg0 + pc);
+        const uint8_t *src = h_img + (size_t)(u >> 7) * 65536 + (size_t)(u & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((u & 7) << 4));
+        vh[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
+        vl[q] = on ? __ldcg(reinterpret_cast<const uint4 *>(src + 32768)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < UNROLL; ++q) {
+        const int32_t pos = hbeg + t + q;
+        const uint32_t wh[4] = {vh[q].x, vh[q].y, vh[q].z, vh[q].w}, wl[4] = {vl[q].x, vl[q].y, vl[q].z, vl[q].w};
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[2 * i] = __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
+          x[2 * i + 1] = __uint_as_float(wh[i] & 0xffff0000u) + __uint_as_float(wl[i] & 0xffff0000u);
+        }
+        if (pos < hmid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[0][i] += x[i];
+        } else if (pos < hend) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[1][i] += x[i];
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < UNROLL; ++q) {
-      const int32_t pos = hbeg + t + q;
-      const uint32_t wh[4] = {vh[q].x, vh[q].y, vh[q].z, vh[q].w}, wl[4] = {vl[q].x, vl[q].y, vl[q].z, vl[q].w};
-      float x[8];
+    for (int r = 0; r < 2; ++r) {
+      const int64_t node = v0 + 2 * hf + r;
+      uint32_t hw[4], lw[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        x[2 * i] = __uint_as_float(wh[i] << 16) + __uint_as_float(wl[i] << 16);
-        x[2 * i + 1] = __uint_as_float(wh[i] & 0xffff0000u) + __uint_as_float(wl[i] & 0xffff0000u);
+        hw[i] = bf16x2_word(acc[r][2 * i], acc[r][2 * i + 1]);
+        lw[i] = bf16x2_word(acc[r][2 * i] - __uint_as_float(hw[i] << 16), acc[r][2 * i + 1] - __uint_as_float(hw[i] & 0xffff0000u));
       }
-      if (pos < hmid) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[0][i] += x[i];
-      } else if (pos < hend) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[1][i] += x[i];
-      }
+      uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (size_t)(node & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((node & 7) << 4));
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4 *>(dst + 32768) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int64_t node = v0 + 2 * hf + r;
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hw[i] = bf16x2_word(acc[r][2 * i], acc[r][2 * i + 1]);
-      lw[i] = bf16x2_word(acc[r][2 * i] - __uint_as_float(hw[i] << 16), acc[r][2 * i + 1] - __uint_as_float(hw[i] & 0xffff0000u));
-    }
-    uint8_t *dst = out_img + (size_t)(node >> 7) * 65536 + (size_t)(node & 127) * 128 + piece_off + (unit16 ^ (uint32_t)((node & 7) << 4));
-    *reinterpret_cast<uint4 *>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4 *>(dst + 32768) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
@@ -387,10 +408,17 @@ int ddfa_gather_sum_image_src(const int32_t *indptr, const int32_t *indices, con
   DDFA_REQUIRE(indptr && indices && h_image && out_image && aligned16(h_image) && aligned16(out_image) && h_image != out_image,
                "ddfa_gather_sum_image_src: NULL, unaligned or aliased pointer");
   const int64_t rows = ((int64_t)N + 127) / 128 * 128;
-  const int64_t warps = (rows + 3) / 4;
+  // groups of 4 rows per warp: enough warps must stay resident to fill the machine, so small batches keep one group per warp
+  const int g = gather_src_groups() > 0 ? gather_src_groups() : (rows >= 131072 ? 4 : (rows >= 32768 ? 2 : 1));
+  const int64_t warps = (rows / 4 + g - 1) / g;
   const int64_t blocks = (warps * 32 + 127) / 128;
-  DDFA_CUDA(launch_chain(1, gather_sum_image_src_kernel, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices,
-                         static_cast<const uint8_t *>(h_image), N, static_cast<uint8_t *>(out_image)));
+#define DDFA_GSRC(GG)                                                                                                                   \
+  DDFA_CUDA(launch_chain(1, gather_sum_image_src_kernel<GG>, dim3((unsigned)blocks), dim3(128), 0, as_stream(stream_), indptr, indices, \
+                         static_cast<const uint8_t *>(h_image), N, static_cast<uint8_t *>(out_image)))
+  if (g >= 4) DDFA_GSRC(4);
+  else if (g == 2) DDFA_GSRC(2);
+  else DDFA_GSRC(1);
+#undef DDFA_GSRC
   DDFA_CHECK_LAUNCH("gather_sum_image_src_kernel");
   return DDFA_OK;
 }

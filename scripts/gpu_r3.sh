@@ -59,6 +59,9 @@ for STAGE in "$@"; do
     ab-csrp)      # TMA-staged gate backward: CSR scalars fetched inside the iteration (1) vs pipelined one value per lane (2)
       bash scripts/gpu_ab.sh ${TAG} DDFA_GATE_BWD_TMA 1 2 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_csrp_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_GATE_BWD_TMA 1 2 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_csrp_c0.log ;;
+    ab-gsrc)      # image->image gather: one row group per warp (1) vs by size (0: 4 groups at C1, 2 at C0), CSR chain pipelined across groups
+      bash scripts/gpu_ab.sh ${TAG} DDFA_GATHER_SRC_GROUPS 1 0 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_gsrc_c1.log
+      bash scripts/gpu_ab.sh ${TAG}c0 DDFA_GATHER_SRC_GROUPS 1 0 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_gsrc_c0.log ;;
     ab-pair)
       bash scripts/gpu_ab.sh ${TAG} DDFA_FWD_PAIR 0 1 --no-secondary --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c1.log
       bash scripts/gpu_ab.sh ${TAG}c0 DDFA_FWD_PAIR 0 1 --graphs 256 --no-variable 2>&1 | tee $OUT/${TAG}_ab_pair_c0.log ;;

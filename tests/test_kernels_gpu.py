@@ -417,6 +417,16 @@ def test_gru_step_image_entries_v2(graphs, nodes):
     L.call("ddfa_gather_sum_image_src", _p(dg.indptr), _p(dg.indices), _p(h_img), N, D, _p(s_img), st())
     s_got = decode_image(s_img, N)
     assert (s_got - s_ref.detach()).abs().max() < 2e-5 * max(1.0, float(s_ref.abs().max()))
+    # 1, 2 or 4 row groups per warp (CSR chain pipelined across groups): the same sums, bit for bit, incl. the ragged last warps
+    from deepdfa_b200._lib import TUNE_GATHER_SRC_GROUPS
+    try:
+        for groups in (1, 2, 4):
+            L.call("ddfa_tuning_set", TUNE_GATHER_SRC_GROUPS, groups)
+            s_alt = torch.zeros(ib, dtype=torch.uint8, device=DEV)
+            L.call("ddfa_gather_sum_image_src", _p(dg.indptr), _p(dg.indices), _p(h_img), N, D, _p(s_alt), st())
+            assert torch.equal(s_alt, s_img), groups
+    finally:
+        L.call("ddfa_tuning_set", TUNE_GATHER_SRC_GROUPS, 0)
     s_leaf = s_got.clone().requires_grad_(True)     # the forward step below consumes exactly this image
     h_ref, r_ref, z_ref, n_ref, ghn_ref = _gru_reference(s_leaf, leaves[0], deg, *leaves[1:])
     dh_in = dh_part + torch.zeros(N, D, dtype=torch.float64).index_add(0, src, ds_prev[dst])
