@@ -29,7 +29,7 @@ static std::atomic<int> g_tuning[DDFA_TUNE__COUNT] = {
     {9},    // DDFA_TUNE_GATHER_VARIANT: r01b sweep — 2 rows/pass, 4 loads in flight, 128-thread CTAs
     {0},    // DDFA_TUNE_FWD_PAIR: 1 = gru_fwd3_kernel launched as CTA pairs (tcgen05.mma.cta_group::2)
     {2},    // DDFA_TUNE_GATE_BWD_TMA: 0 register loads; 1 TMA-staged streaming operands (packed saved state); 2 = 1 + CSR scalars pipelined
-    {0},    // DDFA_TUNE_GATHER_SRC_GROUPS: image->image gather, row groups per warp (0 = chosen by size; 1 / 2 / 4)
+    {0},    // DDFA_TUNE_GATHER_SRC_GROUPS: image->image gather, row groups per warp (0 = default = 1; 2 / 4 selectable)
 };
 int l2_hints() { return g_tuning[DDFA_TUNE_L2_HINTS].load(std::memory_order_relaxed); }
 int pdl_mask() { return g_tuning[DDFA_TUNE_PDL_MASK].load(std::memory_order_relaxed); }

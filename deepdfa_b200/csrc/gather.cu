@@ -408,8 +408,9 @@ int ddfa_gather_sum_image_src(const int32_t *indptr, const int32_t *indices, con
   DDFA_REQUIRE(indptr && indices && h_image && out_image && aligned16(h_image) && aligned16(out_image) && h_image != out_image,
                "ddfa_gather_sum_image_src: NULL, unaligned or aliased pointer");
   const int64_t rows = ((int64_t)N + 127) / 128 * 128;
-  // groups of 4 rows per warp: enough warps must stay resident to fill the machine, so small batches keep one group per warp
-  const int g = gather_src_groups() > 0 ? gather_src_groups() : (rows >= 131072 ? 4 : (rows >= 32768 ? 2 : 1));
+  // groups of 4 rows per warp (CSR chain pipelined across a warp's groups): measured neutral against one group per warp at C1 and
+  // C0 (profiles/r04d_ab_gather_src_groups_*.log: the kernel is not bound by that chain), so the default stays one group
+  const int g = gather_src_groups() > 0 ? gather_src_groups() : 1;
   const int64_t warps = (rows / 4 + g - 1) / g;
   const int64_t blocks = (warps * 32 + 127) / 128;
 #define DDFA_GSRC(GG)                                                                                                                   \

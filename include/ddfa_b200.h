@@ -56,7 +56,7 @@ enum {
   DDFA_TUNE_GATHER_VARIANT = 2, /* launch shape of the D = 128 edge gather (ddfa_gather_sum_variant ids), default 9 */
   DDFA_TUNE_FWD_PAIR = 3,       /* 1: forward GRU kernel launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (default 0) */
   DDFA_TUNE_GATE_BWD_TMA = 4,   /* gate backward: 0 register loads; 1 dh / gates / h stream through a TMA-fed shared-memory ring; 2 (default) = 1 + the folded gather's CSR scalars pipelined across iterations */
-  DDFA_TUNE_GATHER_SRC_GROUPS = 5, /* image->image edge gather: row groups (of 4 rows) walked per warp with the CSR chain pipelined; 0 (default) = by size, or 1 / 2 / 4 */
+  DDFA_TUNE_GATHER_SRC_GROUPS = 5, /* image->image edge gather: row groups (of 4 rows) walked per warp with the CSR chain pipelined; 0 (default) = 1 group (2 / 4 measured neutral), or 1 / 2 / 4 */
   DDFA_TUNE__COUNT = 6
 };
 int ddfa_tuning_set(int key, int value);
