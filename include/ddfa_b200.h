@@ -121,7 +121,8 @@ int ddfa_embed_concat_fwd(const int64_t *const *idx, const float *const *tables,
                           int32_t *oob_count, void *stream);
 /* Same, and the rows also leave as h_0's activation image (row width K*H == 128; layout below, `image` holds
  * ddfa_act_image_bytes(num_nodes) bytes): what ddfa_act_to_image(x) would write, without the second pass over x.
- * Rows num_nodes .. (next multiple of 128) of the image are not written. */
+ * Rows num_nodes .. (next multiple of 128) of the image are not written: the caller keeps them FINITE (e.g. zero-fills the
+ * buffer once) — they are multiplied by the zero rows of the q images in the weight-gradient GEMM. */
 int ddfa_embed_concat_fwd_image(const int64_t *const *idx, const float *const *tables, int32_t num_tables,
                                 int32_t vocab, int32_t width, int32_t num_nodes, float *x, void *image,
                                 int32_t *oob_count, void *stream);
