@@ -91,7 +91,10 @@ class FusedTrainer:
                     if not auto:
                         raise
                     ok, why = 0, str(exc)
-                if auto:       # all ranks take the same path: one failed set-up sends every rank to NCCL
+                # all ranks take the same path: one failed set-up sends every rank to NCCL.  (The set-up itself contains collectives —
+                # symmetric-memory rendezvous — so this covers failures every rank sees alike: the module missing, peer access
+                # unavailable, an allocation refused; a rank that dies alone is a job failure either way.)
+                if auto:
                     flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
                     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
                     if int(flag.item()) == 0:
